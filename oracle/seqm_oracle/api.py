@@ -1,0 +1,80 @@
+"""End-to-end single point: the oracle's counterpart of Electronic_Structure.forward(dm_prop="SCF").
+
+Restates the orchestration of seqm/basics.py:813-1244 (Energy.forward, ground-state branch),
+1260-1365 (Force.forward) and seqm/ElectronicStructure.py:57-127.
+"""
+import numpy as np
+
+from .density import density_from_fock
+from .energy import elec_energy, isolated_atom_energy, molecule_sums, pair_nuclear_energy
+from .gradient import hf_gradient
+from .hamiltonian import build_fock, build_hcore, initial_density
+from .integrals import atom_multipoles
+from .parser import parse
+from .scf import run_scf
+from .tables import Tables, method_parameters
+
+_SYM = {"H": 1, "He": 2, "Li": 3, "Be": 4, "B": 5, "C": 6, "N": 7, "O": 8, "F": 9, "Ne": 10, "Na": 11, "Mg": 12,
+        "Al": 13, "Si": 14, "P": 15, "S": 16, "Cl": 17, "Ar": 18}  # fmt: skip
+
+
+def read_xyz(files):
+    """seqm/seqm_functions/read_xyz.py:17-54 (sort=True: stable sort by descending Z, zero padding)."""
+    mols = []
+    for fn in files:
+        with open(fn) as f:
+            lines = f.readlines()
+        n = int(lines[0])
+        rows = []
+        for L in lines[2 : 2 + n]:
+            a, *xyz = L.split()
+            z = int(a) if a.isdigit() else _SYM[a]
+            rows.append([z] + [float(t) for t in xyz[:3]])
+        d = np.asarray(rows, dtype=np.float64)
+        d = d[np.argsort(-d[:, 0], kind="stable")]
+        mols.append(d)
+    K = max(m.shape[0] for m in mols)
+    species = np.zeros((len(mols), K), dtype=np.int64)
+    coords = np.zeros((len(mols), K, 3))
+    for i, m in enumerate(mols):
+        species[i, : m.shape[0]] = m[:, 0].astype(np.int64)
+        coords[i, : m.shape[0]] = m[:, 1:]
+    return species, coords
+
+
+def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True):
+    """Returns a dict with the result contract of SURVEY 8(a15)."""
+    T = Tables.get()
+    method = seqm_parameters["method"]
+    if method not in ("MNDO", "AM1", "PM3"):
+        raise NotImplementedError(f"oracle covers MNDO/AM1/PM3, not {method}")
+    eps = float(seqm_parameters["scf_eps"])
+    conv = seqm_parameters.get("scf_converger", [2])
+    sp2 = seqm_parameters.get("sp2", [False])
+    P = parse(species, coordinates, outer_cutoff=seqm_parameters.get("pair_outer_cutoff", 1.0e10))
+    par = method_parameters(method, P.Z)
+    mp = atom_multipoles(P.Z, par)
+    hc = build_hcore(P, par, mp)
+    H, w = hc["H"], hc["w"]
+    D0 = initial_density(P) if P0 is None else np.asarray(P0, dtype=np.float64)
+    D, notconv, n_iter = run_scf(P, par, H, w, D0, eps, conv, sp2)
+    F = build_fock(P, par, H, w, D)
+    _, e_mo, V = density_from_fock(F, P.nHeavy, P.nHydro, P.nocc, want_eig=True)
+    Eelec = elec_energy(D, F, H)
+    EnucAB = pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, P.rij, w[:, 0, 0], par)
+    Enuc = molecule_sums(EnucAB, P.pair_molid, P.nmol)
+    Etot = Eelec + Enuc
+    Eiso = molecule_sums(isolated_atom_energy(P.Z, par), P.atom_molid, P.nmol)
+    Hf = Etot - Eiso
+    if seqm_parameters.get("Hf_flag", True):
+        Hf = Hf + molecule_sums(T.eheat[P.Z], P.atom_molid, P.nmol)
+    ar = np.arange(P.nmol)
+    e_gap = e_mo[ar, P.nocc] - e_mo[ar, P.nocc - 1]
+    q = T.tore[P.species] - np.diagonal(D, axis1=1, axis2=2).reshape(P.nmol, P.molsize, 4).sum(axis=2)
+    out = dict(
+        Etot=Etot, Hf=Hf, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo=e_mo, e_gap=e_gap, dm=D, F=F, H=H, w=w,
+        q=q, notconverged=notconv, n_scf_iter=n_iter, molecular_orbitals=V, parsed=P,
+    )  # fmt: skip
+    if do_force:
+        out["force"] = -hf_gradient(P, par, method, D, mp)
+    return out
