@@ -72,13 +72,28 @@ def sp2_packed(a, nocc, eps):
     return 2.0 * x, k
 
 
-def sp2_density(F, nHeavy, nHydro, nocc, eps, mols=None):
+def sp2_density(F, nHeavy, nHydro, nocc, eps, mols=None, reference_padding=True):
+    """SP2 density per molecule.
+
+    reference_padding=True reproduces the reference exactly: pack() zero-pads every packed matrix to the
+    largest orbital count among the molecules handed to it (pack.py:76-77; the SCF loop hands it only the
+    not-yet-converged ones, scf_loop.py:66-78), so smaller molecules carry extra zero eigenvalues through
+    SP2 and their density differs at the O(eps) level from the unpadded purification.
+    reference_padding=False purifies each molecule at its own size (what pyseqm_b200 does; identical
+    for uniform batches such as MD replicas or a single molecule).
+    """
     nmol = F.shape[0]
     D = np.zeros_like(F)
-    for m in range(nmol):
-        if mols is not None and not mols[m]:
-            continue
+    act = [m for m in range(nmol) if mols is None or mols[m]]
+    nmax = max(int(4 * nHeavy[m] + nHydro[m]) for m in act) if act else 0
+    for m in act:
         idx = packed_index(int(nHeavy[m]), int(nHydro[m]))
-        d, _ = sp2_packed(F[m][np.ix_(idx, idx)], float(nocc[m]), eps)
-        D[m][np.ix_(idx, idx)] = d
+        n = idx.shape[0]
+        a = F[m][np.ix_(idx, idx)]
+        if reference_padding and n < nmax:
+            ap = np.zeros((nmax, nmax))
+            ap[:n, :n] = a
+            a = ap
+        d, _ = sp2_packed(a, float(nocc[m]), eps)
+        D[m][np.ix_(idx, idx)] = d[:n, :n]
     return D

@@ -27,9 +27,11 @@ def _pair_energy(P, par, mp, method, xij, rij, PAi, PBj, Dab, pki, pkj):
     E = np.sum(Dab * di * bsum, axis=(1, 2))
     sym = np.triu(np.ones((4, 4)), 1) + np.triu(np.ones((4, 4)))  # 1 on diagonal, 2 above
     E += np.sum(PAi * e1b * sym, axis=(1, 2)) + np.sum(PBj * e2a * sym, axis=(1, 2))
-    E += np.einsum("pk,pkm,pm->p", pki, w, pkj)
-    w4 = w[:, PACK[:, :, None, None], PACK[None, None, :, :]]
-    E += -0.5 * np.einsum("pml,pmnls,pns->p", Dab, w4, Dab)
+    E += np.matmul(pki[:, None, :], np.matmul(w, pkj[:, :, None]))[:, 0, 0]
+    w4 = w[:, PACK[:, :, None, None], PACK[None, None, :, :]]  # (p, mu, nu, lam, sig)
+    wx = w4.transpose(0, 1, 3, 2, 4).reshape(-1, 16, 16)
+    d16 = Dab.reshape(-1, 16)
+    E += -0.5 * np.matmul(d16[:, None, :], np.matmul(wx, d16[:, :, None]))[:, 0, 0]
     E += pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, rij, w[:, 0, 0], par)
     return E
 

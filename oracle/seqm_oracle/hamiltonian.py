@@ -86,6 +86,16 @@ def initial_density(P):
     return D
 
 
+def exchange_view(P, w):
+    """(npairs,16,16) gather of w with rows (mu,lam) and columns (nu,sig); cached per integral tensor."""
+    c = getattr(P, "_wx_cache", None)
+    if c is None or c[0] is not w:
+        w4 = w[:, PACK[:, :, None, None], PACK[None, None, :, :]]  # (p, mu, nu, lam, sig)
+        c = (w, np.ascontiguousarray(w4.transpose(0, 1, 3, 2, 4)).reshape(-1, 16, 16))
+        P._wx_cache = c
+    return c[1]
+
+
 def build_fock(P, par, H, w, Dm, mols=None):
     """F = H + G(D) for the dense symmetric density Dm (fock.py:132-347).
 
@@ -109,8 +119,8 @@ def build_fock(P, par, H, w, Dm, mols=None):
         G[:, a, b] = PA[:, a, b] * (0.75 * gpp - 1.25 * gp2)
     # two-centre Coulomb (fock.py:278-294)
     pk = PA[:, PACK_ROW, PACK_COL] * WEIGHT  # (nat,10)
-    JA = np.einsum("pkm,pm->pk", w, pk[P.idxj])  # onto atom i
-    JB = np.einsum("pk,pkm->pm", pk[P.idxi], w)  # onto atom j
+    JA = np.matmul(w, pk[P.idxj][:, :, None])[:, :, 0]  # onto atom i
+    JB = np.matmul(pk[P.idxi][:, None, :], w)[:, 0, :]  # onto atom j
     J = np.zeros((nat, 10))
     P.seg_i.add(J, JA)
     P.seg_j.add(J, JB)
@@ -119,8 +129,7 @@ def build_fock(P, par, H, w, Dm, mols=None):
     # two-centre exchange (fock.py:297-345): K[mu,lam] = -1/2 sum_{nu,sig} D_AB[nu,sig] w[pack(mu,nu), pack(lam,sig)]
     mi, ai, aj = P.pair_molid, P.atom_pos[P.idxi], P.atom_pos[P.idxj]
     Dab = Db[mi, ai, aj]
-    w4 = w[:, PACK[:, :, None, None], PACK[None, None, :, :]]  # (p, mu, nu, lam, sig)
-    K = -0.5 * np.einsum("pmnls,pns->pml", w4, Dab)
+    K = -0.5 * np.matmul(exchange_view(P, w), Dab.reshape(-1, 16, 1)).reshape(-1, 4, 4)
     F = H.copy()
     Fb = _blocks_view(F, nmol, molsize)
     Fb[P.atom_molid, P.atom_pos, P.atom_pos] += G

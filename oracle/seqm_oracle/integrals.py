@@ -249,7 +249,7 @@ def two_center_integrals_geom(ni, nj, idxi, idxj, xij, rij, mp, T=None):
             if k < ri.shape[1] and (kind == "XX" or b == 0):
                 L[:, a, b] = ri[:, k]
         Tm = _pair_product_transform(rot[m])
-        wm = np.einsum("pKk,pKM,pMm->pkm", Tm, L, Tm)
+        wm = np.matmul(Tm.transpose(0, 2, 1), np.matmul(L, Tm))
         if kind == "XH":
             wm[:, :, 1:] = 0.0
         w[m] = wm

@@ -79,14 +79,12 @@ def _adaptive_mix(k, P_prev, P_cur, old2_diag):
 
 def _diis_coeff(EVEC, cF):
     """Pseudo-inverse solve of the Pulay system, lower triangle only (scf_loop.py:1011-1035)."""
-    L, Q = np.linalg.eigh(EVEC, UPLO="L")
+    L, Q = np.linalg.eigh(EVEC, UPLO="L")  # batched over active molecules
     absv = np.abs(L)
-    with np.errstate(divide="ignore"):
-        cond = np.max(absv) / np.min(absv)
-    inv = np.zeros_like(L)
-    ok = absv > 1.0e-13
-    inv[ok] = 1.0 / L[ok]
-    coeff = -np.einsum("ki,i,i->k", Q[:cF, :], inv, Q[-1, :])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cond = np.max(absv, axis=-1) / np.min(absv, axis=-1)
+        inv = np.where(absv > 1.0e-13, 1.0 / L, 0.0)
+    coeff = -np.einsum("bki,bi,bi->bk", Q[:, :cF, :], inv, Q[:, -1, :])
     return coeff, cond
 
 
@@ -166,13 +164,12 @@ def run_scf(P, par, H, w, D0, eps, converger=(2,), sp2=(False,), verbose=False):
         EMAT[act, counter, :cF] = np.einsum("at,ajt->aj", Cp, FPPF[act, :cF])
         reset = False
         if cF >= 2:
-            for a in act:
-                EVEC = EMAT[a, : cF + 1, : cF + 1].copy()
-                denom = max(EVEC[counter, counter], 1.0e-15)
-                EVEC[:cF, :cF] /= denom
-                coeff, cond = _diis_coeff(EVEC, cF)
-                reset = reset or bool(cond > 1.0e7)
-                F[a] = np.einsum("k,kij->ij", coeff, FOCK[a, :cF])
+            EVEC = EMAT[act, : cF + 1, : cF + 1].copy()
+            denom = np.maximum(EVEC[:, counter, counter], 1.0e-15)
+            EVEC[:, :cF, :cF] /= denom[:, None, None]
+            coeff, cond = _diis_coeff(EVEC, cF)
+            reset = bool(np.any(cond > 1.0e7))
+            F[act] = np.matmul(coeff[:, None, :], FOCK[act, :cF].reshape(act.shape[0], cF, N * N)).reshape(-1, N, N)
         Pnew[nc] = make_pnew(F, nc)[nc]
         Pold[nc] = Pm[nc]
         if cF < 2:

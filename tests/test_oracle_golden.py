@@ -1,0 +1,133 @@
+"""Pins the numpy oracle (oracle/seqm_oracle) to the reference: the .npz fixtures were produced by the
+unmodified reference (tools/make_golden.py) and ref_json/*.json are the reference's own test goldens
+(SURVEY 8(c)).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import seqm_oracle as so
+from conftest import GOLDEN, TOL_DM, TOL_E, TOL_F, load_golden
+
+XYZ = os.path.join(GOLDEN, "xyz")
+
+CASES = [f"cfg1_{m}_{c}" for m in ("AM1", "PM3", "MNDO") for c in ("c2", "c1", "c0")] + [
+    "cfg1_AM1_sp2", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48", "cfg3_coronene_AM1",
+]  # fmt: skip
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_single_point_matches_reference(name):
+    g = load_golden(name)
+    out = so.single_point(g["species"], g["coordinates"], g["seqm_parameters"])
+    assert out["n_scf_iter"] == g["n_scf_iter"]
+    assert not out["notconverged"].any() and not g["notconverged"].any()
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "Eiso", "e_gap"):
+        assert np.abs(out[k] - g[k]).max() < TOL_E, k
+    assert np.abs(out["dm"] - g["dm"]).max() < TOL_DM
+    assert np.abs(out["e_mo"] - g["e_mo"]).max() < TOL_E
+    assert np.abs(out["q"] - g["q"]).max() < TOL_DM
+    assert np.abs(out["force"] - g["force"]).max() < TOL_F
+
+
+def test_autograd_force_mode_of_reference():
+    """The reference's default (autograd) forces equal the Hellmann-Feynman gradient the oracle takes."""
+    g = load_golden("cfg1_AM1_autograd")
+    out = so.single_point(g["species"], g["coordinates"], g["seqm_parameters"])
+    assert np.abs(out["force"] - g["force"]).max() < TOL_F
+    assert np.abs(out["Etot"] - g["Etot"]).max() < TOL_E
+
+
+def test_operator_level_outputs():
+    """hcore -> (M, w), fock(X), sym_eig_trunc, SP2 against the reference's operators (SURVEY 8(b) level B)."""
+    from seqm_oracle.density import density_from_fock, packed_index, sp2_packed
+    from seqm_oracle.hamiltonian import build_fock, build_hcore, hcore_upper
+
+    for method in ("AM1", "PM3", "MNDO"):
+        g = load_golden(f"cfg1_{method}_c2")
+        P = so.parse(g["species"], g["coordinates"])
+        par = so.method_parameters(method, P.Z)
+        hc = build_hcore(P, par)
+        assert np.abs(hc["w"] - g["op_w"]).max() < 1e-12
+        assert np.abs(hcore_upper(hc["H"], P) - g["op_M"]).max() < 1e-12
+        assert np.abs(hc["rho0i"] - g["op_rho0i"]).max() < 1e-13
+        F = build_fock(P, par, hc["H"], hc["w"], g["op_X"])
+        assert np.abs(F - g["op_F"]).max() < 1e-11
+        D, E, _ = density_from_fock(g["op_F"], P.nHeavy, P.nHydro, P.nocc)
+        assert np.abs(D - g["op_P"]).max() < 1e-10
+        assert np.abs(E - g["op_e"]).max() < 1e-10
+        nmax = g["op_sp2_packed"].shape[1]
+        for m in range(P.nmol):
+            idx = packed_index(int(P.nHeavy[m]), int(P.nHydro[m]))
+            n = idx.shape[0]
+            a = np.zeros((nmax, nmax))  # the reference's pack() zero-pads to the batch maximum (pack.py:76-77)
+            a[:n, :n] = g["op_F"][m][np.ix_(idx, idx)]
+            d, _ = sp2_packed(a, float(P.nocc[m]), 1.0e-5)
+            assert np.abs(d - g["op_sp2_packed"][m]).max() < 1e-9
+
+
+def _json(name):
+    with open(os.path.join(GOLDEN, "ref_json", name + ".json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("method", ["MNDO", "AM1", "PM3"])
+def test_reference_json_smoke_single_point(method):
+    """tests/unit/test_smoke_single_point.py:11-41 of the reference, against its own JSON."""
+    ref = _json(f"smoke_single_point_{method}")
+    s, c = so.read_xyz([os.path.join(XYZ, "methane.xyz")])
+    out = so.single_point(s, c, {"method": method, "scf_eps": 1.0e-6, "scf_converger": [1]})
+    assert abs(out["Etot"][0] - ref["Etot"]) < 1e-5
+    assert abs(out["Eelec"][0] - ref["Eelec"]) < 1e-5
+    assert abs(out["Enuc"][0] - ref["Enuc"]) < 1e-5
+    assert np.abs(out["force"] - np.asarray(ref["force"])).max() < 1e-5
+
+
+def test_reference_json_batch_single_point_am1():
+    """tests/unit/test_batch_single_point.py:10-30."""
+    ref = _json("batch_single_point_am1")
+    s, c = so.read_xyz([os.path.join(XYZ, "methane.xyz"), os.path.join(XYZ, "benzene.xyz")])
+    out = so.single_point(s, c, {"method": "AM1", "scf_eps": 1.0e-6, "scf_converger": [1]})
+    assert np.abs(out["Etot"] - np.asarray(ref["Etot"])).max() < 1e-5
+    assert np.abs(out["force"] - np.asarray(ref["force"])).max() < 1e-4
+
+
+@pytest.mark.parametrize(
+    "name,files",
+    [
+        ("ground_force_methane", ["methane.xyz"]),
+        ("ground_force_batch_methanal", ["methanal.1.xyz", "methanal.2.xyz", "methanal.3.xyz"]),
+        ("ground_force_batch_mixed", ["methane.xyz", "benzene.xyz"]),
+    ],
+)
+def test_reference_json_ground_forces(name, files):
+    """tests/unit/test_force_methods.py:62-95."""
+    ref = _json(name)
+    s, c = so.read_xyz([os.path.join(XYZ, f) for f in files])
+    out = so.single_point(s, c, {"method": "AM1", "scf_eps": 1.0e-7, "scf_converger": [1]})
+    assert np.abs(out["force"] - np.asarray(ref["force"])).max() < 1e-5
+
+
+def test_input_validation_matches_reference_errors():
+    """Molecule.py:188-206 (unsorted rows) and basics.py:297-299 (odd electrons)."""
+    s = np.array([[1, 6, 1, 1, 1]])
+    c = np.zeros((1, 5, 3))
+    with pytest.raises(ValueError, match="non-increasing"):
+        so.parse(s, c)
+    s = np.array([[6, 1, 1, 1, 0]])
+    c = np.random.default_rng(0).normal(size=(1, 5, 3))
+    with pytest.raises(ValueError, match="closed shell"):
+        so.parse(s, c)
+
+
+def test_rotation_invariance():
+    """tests/unit/test_invariants.py:28-55: Etot invariant, forces co-rotate (z rotation by 0.7 rad)."""
+    s, c = so.read_xyz([os.path.join(XYZ, "methane.xyz")])
+    sp = {"method": "AM1", "scf_eps": 1.0e-7, "scf_converger": [2]}
+    a = so.single_point(s, c, sp)
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    b = so.single_point(s, c @ R.T, sp)
+    assert abs(a["Etot"][0] - b["Etot"][0]) < 1e-7
+    assert np.abs(a["force"] @ R.T - b["force"]).max() < 1e-5
