@@ -1,0 +1,132 @@
+/* seqm_b200.h -- C ABI of libseqm_b200.so: the B200-native (sm_100a) kernels behind PYSEQM's batched
+ * ground-state SCF path (seqm.Molecule / Electronic_Structure(seqm_parameters).forward).
+ *
+ * The reference (lanl/PYSEQM v2.0.0) is pure Python/PyTorch and has no FFI; the boundary this library
+ * replaces is the operator level of seqm/seqm_functions (SURVEY.md 8(b) "level B").  Each entry point
+ * names the reference function it stands in for.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - extern "C"; every function returns 0 (SEQM_OK) or a negative error code, never throws, never
+ *    allocates device memory, and enqueues its work on the cudaStream_t passed as `stream`
+ *    (a void* here so that the header needs no CUDA include).  seqm_last_error() gives the message.
+ *  - all pointers inside seqm_batch_t and all array arguments are DEVICE pointers owned by the caller
+ *    (torch allocations in pyseqm_b200); fp64 data, int32 indices, int64 matrix offsets.
+ *  - "packed matrix" = per-molecule n x n row-major fp64 block at offset mol_mat0[m] of one flat buffer,
+ *    n = 4*nheavy + nhyd, orbital order [4 AOs (s,px,py,pz) per heavy atom][one s AO per hydrogen]
+ *    (the reference's pack() layout, seqm/seqm_functions/pack.py:8-16, without padding to the batch max).
+ *  - pairs are all i<j atom pairs inside each molecule, ordered (molecule, i, j)  (seqm/basics.py:306-343).
+ *  - w is the dense (npairs,10,10) tensor of the reference (kl on atom i | mn on atom j), packed pair index
+ *    0:(ss) 1:(x s) 2:(x x) 3:(y s) 4:(y x) 5:(y y) 6:(z s) 7:(z x) 8:(z y) 9:(z z).
+ */
+#ifndef SEQM_B200_H
+#define SEQM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEQM_ABI_VERSION 1
+
+/* rows of the per-atom parameter table atom_par[row * nat + atom] */
+enum seqm_par_row {
+  SEQM_P_USS = 0, SEQM_P_UPP, SEQM_P_ZS, SEQM_P_ZP, SEQM_P_BS, SEQM_P_BP, SEQM_P_GSS, SEQM_P_GSP, SEQM_P_GPP,
+  SEQM_P_GP2, SEQM_P_HSP, SEQM_P_ALPHA,
+  SEQM_P_K1, SEQM_P_K2, SEQM_P_K3, SEQM_P_K4, SEQM_P_L1, SEQM_P_L2, SEQM_P_L3, SEQM_P_L4,
+  SEQM_P_M1, SEQM_P_M2, SEQM_P_M3, SEQM_P_M4,
+  SEQM_P_TORE, SEQM_P_QN,
+  /* filled by seqm_atom_multipoles(): */
+  SEQM_P_DD, SEQM_P_QQ, SEQM_P_RHO0, SEQM_P_RHO1, SEQM_P_RHO2,
+  SEQM_NPAR
+};
+
+enum seqm_method { SEQM_MNDO = 0, SEQM_AM1 = 1, SEQM_PM3 = 2 };
+
+typedef struct seqm_batch {
+  int32_t nmol, nat, npairs, method;
+  int32_t nmax;        /* largest orbital count n in the batch */
+  int32_t molsize;     /* padded atoms per molecule at the API boundary */
+  int64_t mat_total;   /* doubles in one packed-matrix buffer = mol_mat0[nmol] */
+  const int32_t* mol_atom0; /* [nmol+1] first real atom of each molecule */
+  const int32_t* mol_pair0; /* [nmol+1] first pair of each molecule */
+  const int64_t* mol_mat0;  /* [nmol+1] packed-matrix offsets (doubles, even) */
+  const int32_t* mol_nheavy;/* [nmol] */
+  const int32_t* mol_nhyd;  /* [nmol] */
+  const int32_t* mol_nocc;  /* [nmol] doubly occupied orbitals */
+  const int32_t* mol_order; /* [nmol] CTA -> molecule map (largest first) */
+  const int32_t* atom_Z;    /* [nat] */
+  const int32_t* atom_mol;  /* [nat] */
+  const int32_t* pair_i;    /* [npairs] global real-atom index of the first atom */
+  const int32_t* pair_j;    /* [npairs] */
+  double* atom_par;         /* [SEQM_NPAR * nat] */
+} seqm_batch_t;
+
+int seqm_abi_version(void);
+const char* seqm_last_error(void);
+/* largest orbital count a single molecule may have in this build (shared-memory resident solvers) */
+int seqm_max_orbitals(void);
+
+/* cal_par.py:11-28,112-169,198-257 + two_elec_two_center_int.py:116-247: dd, qq, rho0, rho1, rho2 per atom */
+int seqm_atom_multipoles(const seqm_batch_t* b, void* stream);
+
+/* hcore() pair part -- two_elec_two_center_int.py:98-283 (w), diat_overlap_PM6_SP.py:6-444 (di) and the
+ * beta scaling of hcore.py:155-173.  xyz [nat*3] Angstrom; w [npairs*100]; hab [npairs*16] = di*(beta_i+beta_j)/2 */
+int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, double* hab, void* stream);
+
+/* hcore() assembly -- hcore.py:124-173: packed symmetric Hcore (U_ss/U_pp + core attraction, beta*S blocks) */
+int seqm_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, void* stream);
+
+/* fock() -- fock.py:132-347.  active: optional [nmol] int32 mask (NULL = all) */
+int seqm_fock(const seqm_batch_t* b, const double* P, const double* H, const double* w, double* F,
+              const int32_t* active, void* stream);
+
+/* sym_eig_trunc() -- diag.py:110-241: batched Jacobi eigensolver + density P = 2 C_occ C_occ^T.
+ * evals [nmol*nmax] ascending (0 beyond n), C optional packed eigenvector matrices (columns), may be NULL.
+ * Cguess: optional packed orthogonal warm-start basis (e.g. last iteration's C), may be NULL. */
+int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C,
+                     const double* Cguess, const int32_t* active, void* stream);
+
+/* SP2() -- SP2.py:9-85 at each molecule's own size; P packed; niter optional [nmol] */
+int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter,
+                     const int32_t* active, void* stream);
+
+/* elec_energy() -- energy.py:26-53 */
+int seqm_elec_energy(const seqm_batch_t* b, const double* P, const double* H, const double* F, double* Eelec,
+                     const int32_t* active, void* stream);
+
+/* pair_nuclear_energy() + total_energy() sums -- energy.py:91-139,177-192: EnucAB [npairs], Enuc [nmol] */
+int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* w, double* EnucAB, double* Enuc,
+                        void* stream);
+
+/* scf_analytic_grad() -- anal_grad.py:16-225: grad [nat*3] eV/Angstrom (dE/dR per real atom);
+ * pair_scratch [npairs*3] */
+int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
+                  void* stream);
+
+/* pack()/unpack() -- pack.py:64-96 between dense (nmol, 4*molsize, 4*molsize) and packed matrices */
+int seqm_pack(const seqm_batch_t* b, const double* dense, double* packed, void* stream);
+int seqm_unpack(const seqm_batch_t* b, const double* packed, double* dense, void* stream);
+/* scf_loop.py:2066-2081 initial diagonal density, packed */
+int seqm_initial_density(const seqm_batch_t* b, double* P, void* stream);
+
+/* scf_loop() drivers -- scf_loop.py:164-347 (converger 0), 424-635 (1), 639-1132 (2).
+ * P in/out (packed), F out (packed, Fock of the converged P), Eelec out [nmol], notconverged out [nmol].
+ * workspace: device scratch of seqm_scf_workspace_bytes() bytes.  use_sp2 != 0 -> SP2 density with sp2_eps.
+ * n_iter_out: host int, the iteration count the reference prints.  Blocks the host until converged. */
+typedef struct seqm_scf_opts {
+  double eps;        /* scf_eps */
+  int32_t converger; /* 0, 1, 2 */
+  double alpha;      /* mixing for converger 0 */
+  int32_t use_sp2;
+  double sp2_eps;
+  int32_t max_iter;  /* reference: 1000 */
+  int32_t warm_start;/* 1: eigensolver starts from the previous iteration's eigenvectors */
+} seqm_scf_opts_t;
+int64_t seqm_scf_workspace_bytes(const seqm_batch_t* b, const seqm_scf_opts_t* o);
+int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
+             double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,130 @@
+"""ctypes binding of libseqm_b200.so (include/seqm_b200.h).
+
+The product loads the CUDA library only and refuses to work without a CUDA device: there is no CPU
+fallback.  (tests/ may bind the host-emulation build of the same kernel sources through
+`SeqmLib(path)` explicitly to check kernel logic on GPU-less CI; nothing in this package does.)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libseqm_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
+              "-Xcompiler", "-fPIC"]  # fmt: skip
+
+# rows of the per-atom parameter table (enum seqm_par_row)
+PAR_ROWS = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha",
+            "Gaussian1_K", "Gaussian2_K", "Gaussian3_K", "Gaussian4_K", "Gaussian1_L", "Gaussian2_L", "Gaussian3_L",
+            "Gaussian4_L", "Gaussian1_M", "Gaussian2_M", "Gaussian3_M", "Gaussian4_M", "tore", "qn",
+            "dd", "qq", "rho0", "rho1", "rho2"]  # fmt: skip
+NPAR = len(PAR_ROWS)
+METHOD_ID = {"MNDO": 0, "AM1": 1, "PM3": 2}
+
+
+class SeqmBatchStruct(C.Structure):
+    _fields_ = [
+        ("nmol", C.c_int32), ("nat", C.c_int32), ("npairs", C.c_int32), ("method", C.c_int32),
+        ("nmax", C.c_int32), ("molsize", C.c_int32), ("mat_total", C.c_int64),
+        ("mol_atom0", C.c_void_p), ("mol_pair0", C.c_void_p), ("mol_mat0", C.c_void_p),
+        ("mol_nheavy", C.c_void_p), ("mol_nhyd", C.c_void_p), ("mol_nocc", C.c_void_p), ("mol_order", C.c_void_p),
+        ("atom_Z", C.c_void_p), ("atom_mol", C.c_void_p), ("pair_i", C.c_void_p), ("pair_j", C.c_void_p),
+        ("atom_par", C.c_void_p),
+    ]  # fmt: skip
+
+
+class SeqmScfOpts(C.Structure):
+    _fields_ = [("eps", C.c_double), ("converger", C.c_int32), ("alpha", C.c_double), ("use_sp2", C.c_int32),
+                ("sp2_eps", C.c_double), ("max_iter", C.c_int32), ("warm_start", C.c_int32)]  # fmt: skip
+
+
+class SeqmError(RuntimeError):
+    pass
+
+
+def build_library(verbose=False):
+    """Compile pyseqm_b200/csrc for sm_100a into pyseqm_b200/lib/libseqm_b200.so (nvcc cross-compiles without a GPU)."""
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    src = os.path.join(CSRC, "seqm_b200.cu")
+    newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))
+    hdr = os.path.join(_HERE, "..", "include", "seqm_b200.h")
+    newest = max(newest, os.path.getmtime(hdr))
+    if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+class SeqmLib:
+    """Thin typed wrapper around the shared library."""
+
+    _P = C.c_void_p
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise SeqmError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)")
+        self.path = path
+        self.dll = C.CDLL(path)
+        P, B, O = self._P, C.POINTER(SeqmBatchStruct), C.POINTER(SeqmScfOpts)
+        sig = {
+            "seqm_abi_version": ([], C.c_int),
+            "seqm_last_error": ([], C.c_char_p),
+            "seqm_max_orbitals": ([], C.c_int),
+            "seqm_atom_multipoles": ([B, P], C.c_int),
+            "seqm_pair_integrals": ([B, P, P, P, P], C.c_int),
+            "seqm_hcore": ([B, P, P, P, P], C.c_int),
+            "seqm_fock": ([B, P, P, P, P, P, P], C.c_int),
+            "seqm_eig_density": ([B, P, P, P, P, P, P, P], C.c_int),
+            "seqm_sp2_density": ([B, P, P, C.c_double, P, P, P], C.c_int),
+            "seqm_elec_energy": ([B, P, P, P, P, P, P], C.c_int),
+            "seqm_nuclear_energy": ([B, P, P, P, P, P], C.c_int),
+            "seqm_gradient": ([B, P, P, P, P, P], C.c_int),
+            "seqm_pack": ([B, P, P, P], C.c_int),
+            "seqm_unpack": ([B, P, P, P], C.c_int),
+            "seqm_initial_density": ([B, P, P], C.c_int),
+            "seqm_scf_workspace_bytes": ([B, O], C.c_int64),
+            "seqm_scf": ([B, O, P, P, P, P, P, P, P, C.POINTER(C.c_int32), P], C.c_int),
+        }
+        for name, (args, res) in sig.items():
+            fn = getattr(self.dll, name)
+            fn.argtypes = args
+            fn.restype = res
+        self.symbols = list(sig)
+        if self.dll.seqm_abi_version() != 1:
+            raise SeqmError("libseqm_b200 ABI version mismatch")
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise SeqmError(f"{what} failed (code {rc}): {self.dll.seqm_last_error().decode()}")
+
+
+_LIB = None
+
+
+def get_lib():
+    """The CUDA library.  Raises if CUDA is unavailable: pyseqm_b200 has no CPU path."""
+    global _LIB
+    if _LIB is None:
+        if not torch.cuda.is_available():
+            raise SeqmError("pyseqm_b200 needs a CUDA device (B200, sm_100a); it has no CPU fallback")
+        _LIB = SeqmLib(LIB_PATH)
+    return _LIB
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    if t.is_cuda:
+        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return C.c_void_p(0)

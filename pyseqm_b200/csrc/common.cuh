@@ -1,0 +1,168 @@
+// common.cuh -- batch accessors, error plumbing, overlap polynomial tables.
+#pragma once
+#include <cstdarg>
+
+#include "../../include/seqm_b200.h"
+#include "pair_core.cuh"
+
+#define SEQM_MAX_ORB 118  // two n x n fp64 matrices must fit the 227 KB shared memory of one SM
+
+static char g_seqm_err[512] = "";
+void seqm_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_seqm_err, sizeof(g_seqm_err), fmt, ap);
+  va_end(ap);
+}
+int seqm_check_launch(const char* what) {
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    seqm_set_error("%s: %s", what, cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+#endif
+  (void)what;
+  return SEQM_OK;
+}
+
+#ifdef SEQM_HOSTEMU
+thread_local seqm_dim3 threadIdx, blockIdx, blockDim, gridDim;
+unsigned char* seqm_hostemu_smem = nullptr;
+static size_t g_hostemu_smem_bytes = 0;
+void seqm_hostemu_ensure_smem(size_t bytes) {
+  if (bytes > g_hostemu_smem_bytes) {
+    free(seqm_hostemu_smem);
+    seqm_hostemu_smem = (unsigned char*)malloc(bytes);
+    g_hostemu_smem_bytes = bytes;
+  }
+}
+#endif
+
+// ---- per-molecule geometry of the packed layout ---------------------------------------------------
+struct MolView {
+  int m, a0, na, nheavy, nhyd, n, nocc, p0, npair;
+  long long mat0;
+};
+SEQM_HD MolView mol_view(const seqm_batch_t& b, int m) {
+  MolView v;
+  v.m = m;
+  v.a0 = b.mol_atom0[m];
+  v.na = b.mol_atom0[m + 1] - v.a0;
+  v.nheavy = b.mol_nheavy[m];
+  v.nhyd = b.mol_nhyd[m];
+  v.n = 4 * v.nheavy + v.nhyd;
+  v.nocc = b.mol_nocc[m];
+  v.p0 = b.mol_pair0[m];
+  v.npair = b.mol_pair0[m + 1] - v.p0;
+  v.mat0 = b.mol_mat0[m];
+  return v;
+}
+// local atom index a (0..na-1, heavy atoms first) -> first packed orbital / number of orbitals
+SEQM_HD int orb_off(const MolView& v, int a) { return a < v.nheavy ? 4 * a : 4 * v.nheavy + (a - v.nheavy); }
+SEQM_HD int orb_cnt(const MolView& v, int a) { return a < v.nheavy ? 4 : 1; }
+// index of pair (a<b) inside the molecule's dense triangular pair list
+SEQM_HD int pair_local(const MolView& v, int a, int b) { return a * (2 * v.na - a - 1) / 2 + (b - a - 1); }
+SEQM_HD double par(const seqm_batch_t& b, int row, int atom) { return b.atom_par[(long long)row * b.nat + atom]; }
+
+// ---- overlap polynomial tables (host-built, device constant) --------------------------------------
+SEQM_CONSTANT OverlapTables c_ovl;
+
+static void poly_mul(const int a[16][16], const int b[16][16], int out[16][16]) {
+  int t[16][16];
+  memset(t, 0, sizeof(t));
+  for (int i = 0; i < 16; ++i)
+    for (int j = 0; j < 16; ++j)
+      if (a[i][j])
+        for (int k = 0; i + k < 16; ++k)
+          for (int l = 0; j + l < 16; ++l) t[i + k][j + l] += a[i][j] * b[k][l];
+  memcpy(out, t, sizeof(t));
+}
+static void build_overlap_tables(OverlapTables* T) {
+  memset(T, 0, sizeof(*T));
+  // polynomials in (xi, eta): index [power of xi][power of eta]
+  int one[16][16], xpe[16][16], xme[16][16], onep[16][16], monep[16][16], x2m1[16][16], ome2[16][16];
+  memset(one, 0, sizeof(one)); one[0][0] = 1;
+  memset(xpe, 0, sizeof(xpe)); xpe[1][0] = 1; xpe[0][1] = 1;      // xi + eta
+  memset(xme, 0, sizeof(xme)); xme[1][0] = 1; xme[0][1] = -1;     // xi - eta
+  memset(onep, 0, sizeof(onep)); onep[0][0] = 1; onep[1][1] = 1;  // 1 + xi eta
+  memset(monep, 0, sizeof(monep)); monep[0][0] = -1; monep[1][1] = 1;  // xi eta - 1
+  memset(x2m1, 0, sizeof(x2m1)); x2m1[2][0] = 1; x2m1[0][0] = -1;      // xi^2 - 1
+  memset(ome2, 0, sizeof(ome2)); ome2[0][0] = 1; ome2[0][2] = -1;      // 1 - eta^2
+  double fact[8] = {1, 1, 2, 6, 24, 120, 720, 5040};
+  for (int na = 1; na <= 3; ++na)
+    for (int nb = 1; nb <= 3; ++nb) {
+      T->norm[na - 1][nb - 1] = 1.0 / sqrt(fact[2 * na] * fact[2 * nb]);
+      for (int kind = 0; kind < 5; ++kind) {
+        int pa = (kind == 0 || kind == 2) ? na : na - 1;  // power of (xi+eta)
+        int pb = (kind == 0 || kind == 1) ? nb : nb - 1;  // power of (xi-eta)
+        int acc[16][16];
+        memcpy(acc, one, sizeof(acc));
+        for (int i = 0; i < pa; ++i) poly_mul(acc, xpe, acc);
+        for (int i = 0; i < pb; ++i) poly_mul(acc, xme, acc);
+        if (kind == 1) poly_mul(acc, onep, acc);
+        if (kind == 2) poly_mul(acc, monep, acc);
+        if (kind == 3) { poly_mul(acc, onep, acc); poly_mul(acc, monep, acc); }
+        if (kind == 4) { poly_mul(acc, x2m1, acc); poly_mul(acc, ome2, acc); }
+        for (int k = 0; k <= SEQM_KMAX; ++k)
+          for (int l = 0; l <= SEQM_KMAX; ++l) T->poly[na - 1][nb - 1][kind][k][l] = (signed char)acc[k][l];
+      }
+    }
+}
+static int g_tables_ready = 0;
+static int ensure_tables() {
+  if (g_tables_ready) return SEQM_OK;
+  OverlapTables h;
+  build_overlap_tables(&h);
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemcpyToSymbol(c_ovl, &h, sizeof(h));
+  if (e != cudaSuccess) {
+    seqm_set_error("cudaMemcpyToSymbol(overlap tables): %s", cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+#else
+  c_ovl = h;
+#endif
+  g_tables_ready = 1;
+  return SEQM_OK;
+}
+
+// block-wide sum of one double per thread (blockDim.x <= 1024, multiple of 32); result valid in all threads
+SEQM_D double block_sum(double v, double* scratch /* >= 33 doubles */) {
+#ifndef SEQM_HOSTEMU
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < nw) ? scratch[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+#else
+  (void)scratch;
+  return v;
+#endif
+}
+SEQM_D double block_max(double v, double* scratch) {
+#ifndef SEQM_HOSTEMU
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = (lane < nw) ? scratch[lane] : -1.0e300;
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+#else
+  (void)scratch;
+  return v;
+#endif
+}

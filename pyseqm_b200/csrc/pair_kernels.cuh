@@ -1,0 +1,243 @@
+// pair_kernels.cuh -- kernels whose unit of work is an atom pair (or an atom):
+//   atom_multipoles_kernel   per atom    dd, qq, rho0..2
+//   pair_integrals_kernel    per pair    w (10x10), beta-scaled overlap block
+//   hcore_kernel             per molecule packed Hcore from U, w[:,0]/w[0,:] core attraction, overlap blocks
+//   nuclear_energy_kernel    per pair    core-core repulsion  (+ per-molecule sums)
+//   pair_gradient_kernel     per pair    dE_pair/dR_i by forward-mode duals through the same pair code
+//   atom_gradient_kernel     per atom    deterministic +/- gather of the pair gradients
+#pragma once
+#include "common.cuh"
+
+SEQM_GLOBAL void atom_multipoles_kernel(seqm_batch_t b) {
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < b.nat; a += gridDim.x * blockDim.x) {
+    AtomMultipole m = atom_multipole(b.atom_Z[a], par(b, SEQM_P_QN, a), par(b, SEQM_P_ZS, a), par(b, SEQM_P_ZP, a),
+                                     par(b, SEQM_P_GSS, a), par(b, SEQM_P_GPP, a), par(b, SEQM_P_GP2, a),
+                                     par(b, SEQM_P_HSP, a));
+    b.atom_par[(long long)SEQM_P_DD * b.nat + a] = m.dd;
+    b.atom_par[(long long)SEQM_P_QQ * b.nat + a] = m.qq;
+    b.atom_par[(long long)SEQM_P_RHO0 * b.nat + a] = m.rho0;
+    b.atom_par[(long long)SEQM_P_RHO1 * b.nat + a] = m.rho1;
+    b.atom_par[(long long)SEQM_P_RHO2 * b.nat + a] = m.rho2;
+  }
+}
+
+SEQM_HD AtomMultipole load_multipole(const seqm_batch_t& b, int a) {
+  AtomMultipole m;
+  m.dd = par(b, SEQM_P_DD, a);
+  m.qq = par(b, SEQM_P_QQ, a);
+  m.rho0 = par(b, SEQM_P_RHO0, a);
+  m.rho1 = par(b, SEQM_P_RHO1, a);
+  m.rho2 = par(b, SEQM_P_RHO2, a);
+  return m;
+}
+SEQM_HD CorePar load_core(const seqm_batch_t& b, int a) {
+  CorePar c;
+  c.tore = par(b, SEQM_P_TORE, a);
+  c.alpha = par(b, SEQM_P_ALPHA, a);
+  for (int k = 0; k < 4; ++k) {
+    c.gK[k] = par(b, SEQM_P_K1 + k, a);
+    c.gL[k] = par(b, SEQM_P_L1 + k, a);
+    c.gM[k] = par(b, SEQM_P_M1 + k, a);
+  }
+  return c;
+}
+
+// Geometry of a pair as scalars of type T.  For T = Dual3 the derivative slots are d/dR_i.
+template <class T>
+struct PairGeom {
+  T r;     // bohr
+  T e[3];  // unit vector i -> j
+};
+SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<double>& g) {
+  const double dx = xyz[3 * j] - xyz[3 * i], dy = xyz[3 * j + 1] - xyz[3 * i + 1], dz = xyz[3 * j + 2] - xyz[3 * i + 2];
+  const double d = sqrt(dx * dx + dy * dy + dz * dz);
+  g.e[0] = dx / d;
+  g.e[1] = dy / d;
+  g.e[2] = dz / d;
+  g.r = d * (1.0 / SEQM_A0);
+}
+SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<Dual3>& g) {
+  // X = R_j - R_i ; dX/dR_i = -1
+  const Dual3 dx(xyz[3 * j] - xyz[3 * i], -1.0, 0.0, 0.0);
+  const Dual3 dy(xyz[3 * j + 1] - xyz[3 * i + 1], 0.0, -1.0, 0.0);
+  const Dual3 dz(xyz[3 * j + 2] - xyz[3 * i + 2], 0.0, 0.0, -1.0);
+  const Dual3 d = sq_root(dx * dx + dy * dy + dz * dz);
+  g.e[0] = dx / d;
+  g.e[1] = dy / d;
+  g.e[2] = dz / d;
+  g.r = d * (1.0 / SEQM_A0);
+}
+
+// w of one pair in the molecular frame (only the entries that exist for the pair class are non-zero)
+template <class T>
+SEQM_HD void pair_w(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T w[10][10]) {
+  const bool hi = b.atom_Z[i] > 1, hj = b.atom_Z[j] > 1;
+  const int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
+  T ri[22];
+  local_integrals(g.r, load_multipole(b, i), load_multipole(b, j), nint, ri);
+  T v[3] = {-g.e[0], -g.e[1], -g.e[2]};
+  T rot[3][3];
+  rotation_rows(v, rot);
+  T Tm[10][10];
+  pair_transform(rot, Tm);
+  rotate_to_molecular(ri, nint, Tm, w);
+}
+
+template <class T>
+SEQM_HD void pair_overlap(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T S[4][4]) {
+  const bool hi = b.atom_Z[i] > 1, hj = b.atom_Z[j] > 1;
+  overlap_block(c_ovl, (int)par(b, SEQM_P_QN, i), (int)par(b, SEQM_P_QN, j), hi, hj, par(b, SEQM_P_ZS, i),
+                par(b, SEQM_P_ZP, i), par(b, SEQM_P_ZS, j), par(b, SEQM_P_ZP, j), g.r, g.e, S);
+}
+
+SEQM_GLOBAL void pair_integrals_kernel(seqm_batch_t b, const double* __restrict__ xyz, double* __restrict__ w,
+                                       double* __restrict__ hab) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
+    const int i = b.pair_i[p], j = b.pair_j[p];
+    PairGeom<double> g;
+    pair_geom(xyz, i, j, g);
+    double wl[10][10];
+    pair_w(b, i, j, g, wl);
+    double* wp = w + (long long)p * 100;
+    for (int k = 0; k < 10; ++k)
+      for (int l = 0; l < 10; ++l) wp[k * 10 + l] = wl[k][l];
+    double S[4][4];
+    pair_overlap(b, i, j, g, S);
+    const double bsi = par(b, SEQM_P_BS, i), bpi = par(b, SEQM_P_BP, i);
+    const double bsj = par(b, SEQM_P_BS, j), bpj = par(b, SEQM_P_BP, j);
+    double* hp = hab + (long long)p * 16;
+    for (int mu = 0; mu < 4; ++mu)
+      for (int nu = 0; nu < 4; ++nu)
+        hp[mu * 4 + nu] = S[mu][nu] * (0.5 * ((mu ? bpi : bsi) + (nu ? bpj : bsj)));
+  }
+}
+
+// One CTA per molecule: packed, fully symmetric Hcore.
+SEQM_GLOBAL void hcore_kernel(seqm_batch_t b, const double* __restrict__ w, const double* __restrict__ hab,
+                              double* __restrict__ H) {
+  const MolView v = mol_view(b, b.mol_order[blockIdx.x]);
+  double* Hm = H + v.mat0;
+  const int n = v.n;
+  // off-diagonal blocks (both triangles)
+  for (int t = threadIdx.x; t < v.npair * 16; t += blockDim.x) {
+    const int pl = t >> 4, mu = (t >> 2) & 3, nu = t & 3;
+    const int p = v.p0 + pl;
+    const int i = b.pair_i[p] - v.a0, j = b.pair_j[p] - v.a0;
+    if (mu >= orb_cnt(v, i) || nu >= orb_cnt(v, j)) continue;
+    const double h = hab[(long long)p * 16 + mu * 4 + nu];
+    const int r = orb_off(v, i) + mu, c = orb_off(v, j) + nu;
+    Hm[r * n + c] = h;
+    Hm[c * n + r] = h;
+  }
+  // diagonal blocks: U + sum_B core attraction, -tore_B (kl|ss_B)
+  for (int t = threadIdx.x; t < v.na * 10; t += blockDim.x) {
+    const int a = t / 10, kl = t % 10;
+    if (a >= v.nheavy && kl > 0) continue;
+    int mu = 0, nu = 0;  // kl = pack2(mu, nu), mu >= nu
+    while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
+    nu = kl - mu * (mu + 1) / 2;
+    double acc = (mu == nu) ? (mu == 0 ? par(b, SEQM_P_USS, v.a0 + a) : par(b, SEQM_P_UPP, v.a0 + a)) : 0.0;
+    for (int o = 0; o < v.na; ++o) {
+      if (o == a) continue;
+      const double to = par(b, SEQM_P_TORE, v.a0 + o);
+      if (a < o)
+        acc -= to * w[(long long)(v.p0 + pair_local(v, a, o)) * 100 + kl * 10];
+      else
+        acc -= to * w[(long long)(v.p0 + pair_local(v, o, a)) * 100 + kl];
+    }
+    const int oa = orb_off(v, a);
+    Hm[(oa + mu) * n + oa + nu] = acc;
+    Hm[(oa + nu) * n + oa + mu] = acc;
+  }
+}
+
+SEQM_GLOBAL void nuclear_energy_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* __restrict__ w,
+                                       double* __restrict__ EnucAB) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
+    const int i = b.pair_i[p], j = b.pair_j[p];
+    PairGeom<double> g;
+    pair_geom(xyz, i, j, g);
+    EnucAB[p] = core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), g.r,
+                          w[(long long)p * 100]);
+  }
+}
+// per-molecule sum of a per-pair quantity (pairs of a molecule are contiguous): deterministic, no atomics
+SEQM_GLOBAL void pair_sum_kernel(seqm_batch_t b, const double* __restrict__ vals, double* __restrict__ out) {
+  __shared__ double red[33];
+  const MolView v = mol_view(b, blockIdx.x);
+  double s = 0.0;
+  for (int t = threadIdx.x; t < v.npair; t += blockDim.x) s += vals[v.p0 + t];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[v.m] = s;
+}
+
+// Hellmann-Feynman pair gradient dE_pair/dR_i at fixed density (what anal_grad.py:16-225 assembles):
+//   E_pair = 2 sum P_AB o (beta S) + sum_A P o e1b + sum_B P o e2a + Coulomb + exchange + core-core
+SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* __restrict__ P,
+                                      double* __restrict__ gpair) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
+    const int i = b.pair_i[p], j = b.pair_j[p];
+    const MolView v = mol_view(b, b.atom_mol[i]);
+    const double* Pm = P + v.mat0;
+    const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
+    const int ni = orb_cnt(v, i - v.a0), nj = orb_cnt(v, j - v.a0);
+    PairGeom<Dual3> g;
+    pair_geom(xyz, i, j, g);
+    Dual3 E(0.0);
+    {  // resonance term
+      Dual3 S[4][4];
+      pair_overlap(b, i, j, g, S);
+      const double bsi = par(b, SEQM_P_BS, i), bpi = par(b, SEQM_P_BP, i);
+      const double bsj = par(b, SEQM_P_BS, j), bpj = par(b, SEQM_P_BP, j);
+      for (int mu = 0; mu < ni; ++mu)
+        for (int nu = 0; nu < nj; ++nu)
+          E += (Pm[(oi + mu) * n + oj + nu] * ((mu ? bpi : bsi) + (nu ? bpj : bsj))) * S[mu][nu];
+    }
+    Dual3 w[10][10];
+    pair_w(b, i, j, g, w);
+    const int nA = (ni == 4) ? 10 : 1, nB = (nj == 4) ? 10 : 1;
+    double pa[10], pb[10];  // weighted packed diagonal-block densities
+    for (int kl = 0; kl < 10; ++kl) {
+      int mu = 0;
+      while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
+      const int nu = kl - mu * (mu + 1) / 2;
+      const double wt = (mu == nu) ? 1.0 : 2.0;
+      pa[kl] = (kl < nA) ? wt * Pm[(oi + mu) * n + oi + nu] : 0.0;
+      pb[kl] = (kl < nB) ? wt * Pm[(oj + mu) * n + oj + nu] : 0.0;
+    }
+    const double ti = par(b, SEQM_P_TORE, i), tj = par(b, SEQM_P_TORE, j);
+    for (int kl = 0; kl < nA; ++kl) {
+      E += (-tj * pa[kl]) * w[kl][0];  // electrons on i, core of j
+      for (int mn = 0; mn < nB; ++mn) E += (pa[kl] * pb[mn]) * w[kl][mn];
+    }
+    for (int mn = 0; mn < nB; ++mn) E += (-ti * pb[mn]) * w[0][mn];
+    for (int mu = 0; mu < ni; ++mu)
+      for (int la = 0; la < nj; ++la)
+        for (int nu = 0; nu < ni; ++nu)
+          for (int sg = 0; sg < nj; ++sg)
+            E += (-0.5 * Pm[(oi + mu) * n + oj + la] * Pm[(oi + nu) * n + oj + sg]) * w[pack2(mu, nu)][pack2(la, sg)];
+    E += core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), g.r, w[0][0]);
+    gpair[3 * (long long)p] = E.d0;
+    gpair[3 * (long long)p + 1] = E.d1;
+    gpair[3 * (long long)p + 2] = E.d2;
+  }
+}
+// grad[a] = sum_{b>a} g(a,b) - sum_{b<a} g(b,a)   (anal_grad.py:213-221 without atomics)
+SEQM_GLOBAL void atom_gradient_kernel(seqm_batch_t b, const double* __restrict__ gpair, double* __restrict__ grad) {
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < b.nat; a += gridDim.x * blockDim.x) {
+    const MolView v = mol_view(b, b.atom_mol[a]);
+    const int la = a - v.a0;
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    for (int o = 0; o < v.na; ++o) {
+      if (o == la) continue;
+      const long long p = v.p0 + (la < o ? pair_local(v, la, o) : pair_local(v, o, la));
+      const double s = (la < o) ? 1.0 : -1.0;
+      gx += s * gpair[3 * p];
+      gy += s * gpair[3 * p + 1];
+      gz += s * gpair[3 * p + 2];
+    }
+    grad[3 * a] = gx;
+    grad[3 * a + 1] = gy;
+    grad[3 * a + 2] = gz;
+  }
+}

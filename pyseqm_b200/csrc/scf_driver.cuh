@@ -1,0 +1,394 @@
+// scf_driver.cuh -- the SCF fixed-point iteration kept on the device: mixing, Pulay DIIS, convergence
+// bookkeeping; the host only launches and polls two integers per iteration.
+// Replaces seqm/seqm_functions/scf_loop.py: get_error 106-147, scf_forward0 164-347, adaptive_mix 350-420,
+// scf_forward1 424-635, scf_forward2 639-1132 (nFock = 10, batch-global DIIS reset), MAX_ITER = 1000.
+#pragma once
+#include "eig_kernels.cuh"
+#include "fock_kernels.cuh"
+
+#define SEQM_NFOCK 10
+#define SEQM_EM (SEQM_NFOCK + 1)
+
+struct ScfCtrl {  // device-resident control block
+  int nnot;       // molecules still not converged after the last get_error
+  int reset;      // DIIS: some active molecule had cond > 1e7 this iteration
+  int pad[6];
+};
+
+struct ScfWork {  // carved out of the caller's workspace
+  double *Pold, *Pnew, *C;
+  double *FOCK, *RES, *EMAT, *coeff, *diis_err;  // converger 2
+  double *old2, *dnew, *fac, *sum0, *sum3;       // converger 1
+  double *err, *dm_err, *dm_elem, *Eel_new, *Eel_run;
+  int32_t* active;
+  ScfCtrl* ctrl;
+  int has_C;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+static size_t scf_carve(const seqm_batch_t* b, const seqm_scf_opts_t* o, unsigned char* base, ScfWork* W) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    unsigned char* p = base ? base + off : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  const size_t mat = sizeof(double) * (size_t)b->mat_total, nm = sizeof(double) * (size_t)b->nmol;
+  ScfWork w;
+  memset(&w, 0, sizeof(w));
+  w.Pold = (double*)take(mat);
+  w.Pnew = (double*)take(mat);
+  w.C = (double*)take(mat);
+  if (o->converger == 2) {
+    w.FOCK = (double*)take(mat * SEQM_NFOCK);
+    w.RES = (double*)take(mat * SEQM_NFOCK);
+    w.EMAT = (double*)take(nm * SEQM_EM * SEQM_EM);
+    w.coeff = (double*)take(nm * SEQM_NFOCK);
+    w.diis_err = (double*)take(nm);
+  }
+  if (o->converger == 1) {
+    w.old2 = (double*)take(nm * b->nmax);
+    w.dnew = (double*)take(nm * b->nmax);
+    w.fac = (double*)take(nm);
+    w.sum0 = (double*)take(nm);
+    w.sum3 = (double*)take(nm);
+  }
+  w.err = (double*)take(nm);
+  w.dm_err = (double*)take(nm);
+  w.dm_elem = (double*)take(nm);
+  w.Eel_new = (double*)take(nm);
+  w.Eel_run = (double*)take(nm);
+  w.active = (int32_t*)take(sizeof(int32_t) * (size_t)b->nmol);
+  w.ctrl = (ScfCtrl*)take(sizeof(ScfCtrl));
+  if (W) *W = w;
+  return off;
+}
+
+SEQM_GLOBAL void scf_init_kernel(seqm_batch_t b, ScfWork W, int converger) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < b.nmol; m += gridDim.x * blockDim.x) {
+    W.err[m] = 1.0;
+    W.dm_err[m] = 1.0;
+    W.dm_elem[m] = 1.0;
+    W.Eel_new[m] = 0.0;
+    W.active[m] = 1;
+    if (converger == 2) {
+      W.diis_err[m] = 1.79769313486231570e308;
+      double* E = W.EMAT + (long long)m * SEQM_EM * SEQM_EM;
+      for (int i = 0; i < SEQM_EM; ++i)
+        for (int j = 0; j < SEQM_EM; ++j) E[i * SEQM_EM + j] = (j < i) ? -1.0 : 0.0;
+    }
+    if (converger == 1)
+      for (int k = 0; k < b.nmax; ++k) W.old2[(long long)m * b.nmax + k] = 0.0;
+    if (m == 0) {
+      W.ctrl->nnot = b.nmol;
+      W.ctrl->reset = 0;
+    }
+  }
+}
+SEQM_GLOBAL void emat_reset_kernel(seqm_batch_t b, ScfWork W) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < b.nmol; m += gridDim.x * blockDim.x) {
+    double* E = W.EMAT + (long long)m * SEQM_EM * SEQM_EM;
+    for (int i = 0; i < SEQM_EM; ++i)
+      for (int j = 0; j < SEQM_EM; ++j) E[i * SEQM_EM + j] = (j < i) ? -1.0 : 0.0;
+    if (m == 0) W.ctrl->reset = 0;
+  }
+}
+
+// DIIS step 1 (scf_loop.py:994-1007): store F, residual R = F P - P F, max |R|, EMAT row `counter`.
+SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ F, const double* __restrict__ P,
+                                   int counter, int cF) {
+  __shared__ double red[33];
+  const int mol = b.mol_order[blockIdx.x];
+  if (!W.active[mol]) return;
+  const MolView v = mol_view(b, mol);
+  const int n = v.n, nn = n * n;
+  SEQM_DYN_SMEM(double, sm);
+  double* sF = sm;
+  double* sP = sm + nn;
+  const long long h0 = v.mat0 * SEQM_NFOCK;  // this molecule's history block: [slot][n*n]
+  double* Fh = W.FOCK + h0 + (long long)counter * nn;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const double f = F[v.mat0 + t];
+    sF[t] = f;
+    sP[t] = P[v.mat0 + t];
+    Fh[t] = f;
+  }
+  SEQM_SYNC();
+  double* Rh = W.RES + h0 + (long long)counter * nn;
+  double dots[SEQM_NFOCK];
+  for (int j = 0; j < SEQM_NFOCK; ++j) dots[j] = 0.0;
+  double rmax = 0.0;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const int i = t / n, j = t % n;
+    if (j <= i) continue;
+    double s = 0.0;
+    for (int k = 0; k < n; ++k) s += sF[i * n + k] * sP[k * n + j] - sP[i * n + k] * sF[k * n + j];
+    Rh[i * n + j] = s;
+    Rh[j * n + i] = -s;
+    rmax = fmax(rmax, fabs(s));
+    for (int q = 0; q < cF; ++q)
+      dots[q] += s * ((q == counter) ? s : W.RES[h0 + (long long)q * nn + i * n + j]);
+  }
+  for (int t = threadIdx.x; t < n; t += blockDim.x) Rh[t * n + t] = 0.0;
+  rmax = block_max(rmax, red);
+  double* E = W.EMAT + (long long)mol * SEQM_EM * SEQM_EM;
+  for (int q = 0; q < cF; ++q) {
+    const double d = block_sum(dots[q], red);
+    if (threadIdx.x == 0) E[counter * SEQM_EM + q] = d;
+  }
+  if (threadIdx.x == 0) W.diis_err[mol] = rmax;
+}
+
+// cyclic Jacobi for a tiny dense symmetric matrix held by one thread (lower triangle is authoritative)
+SEQM_D void small_eigh(int n, double* A /* n*n, symmetrised in place */, double* Q /* n*n */) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      if (j > i) A[i * n + j] = A[j * n + i];
+      Q[i * n + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    for (int i = 0; i < n; ++i) {
+      dg = fmax(dg, fabs(A[i * n + i]));
+      for (int j = 0; j < i; ++j) off = fmax(off, fabs(A[i * n + j]));
+    }
+    if (off <= 1.0e-18 * dg || off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (fabs(apq) < 1.0e-300) continue;
+        const double tau = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+        for (int k = 0; k < n; ++k) {
+          const double x = A[k * n + p], y = A[k * n + q];
+          A[k * n + p] = c * x - s * y;
+          A[k * n + q] = s * x + c * y;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double x = A[p * n + k], y = A[q * n + k];
+          A[p * n + k] = c * x - s * y;
+          A[q * n + k] = s * x + c * y;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double x = Q[k * n + p], y = Q[k * n + q];
+          Q[k * n + p] = c * x - s * y;
+          Q[k * n + q] = s * x + c * y;
+        }
+      }
+  }
+}
+
+// DIIS step 2 (scf_loop.py:1009-1031): pseudo-inverse solve per molecule, condition-number reset flag.
+SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int cF) {
+  for (int mol = blockIdx.x * blockDim.x + threadIdx.x; mol < b.nmol; mol += gridDim.x * blockDim.x) {
+    if (!W.active[mol]) continue;
+    const int n = cF + 1;
+    double A[SEQM_EM * SEQM_EM], Q[SEQM_EM * SEQM_EM];
+    const double* E = W.EMAT + (long long)mol * SEQM_EM * SEQM_EM;
+    double denom = E[counter * SEQM_EM + counter];
+    if (denom < 1.0e-15) denom = 1.0e-15;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double e = E[i * SEQM_EM + j];
+        if (i < cF && j < cF) e /= denom;
+        A[i * n + j] = e;
+      }
+    small_eigh(n, A, Q);
+    double amax = 0.0, amin = 1.0e300;
+    for (int i = 0; i < n; ++i) {
+      const double a = fabs(A[i * n + i]);
+      amax = fmax(amax, a);
+      amin = fmin(amin, a);
+    }
+    if (amax / amin > 1.0e7) seqm_atomic_or(&W.ctrl->reset, 1);
+    for (int k = 0; k < cF; ++k) {
+      double s = 0.0;
+      for (int i = 0; i < n; ++i) {
+        const double l = A[i * n + i];
+        if (fabs(l) > 1.0e-13) s += Q[k * n + i] * Q[(n - 1) * n + i] / l;
+      }
+      W.coeff[(long long)mol * SEQM_NFOCK + k] = -s;
+    }
+  }
+}
+
+// DIIS step 3 (scf_loop.py:1033-1035): F = sum_k coeff_k FOCK_k
+SEQM_GLOBAL void diis_extrapolate_kernel(seqm_batch_t b, ScfWork W, double* __restrict__ F, int cF) {
+  const int mol = b.mol_order[blockIdx.x];
+  if (!W.active[mol]) return;
+  const MolView v = mol_view(b, mol);
+  const int nn = v.n * v.n;
+  const long long h0 = v.mat0 * SEQM_NFOCK;
+  double c[SEQM_NFOCK];
+  for (int k = 0; k < cF; ++k) c[k] = W.coeff[(long long)mol * SEQM_NFOCK + k];
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < cF; ++k) s += c[k] * W.FOCK[h0 + (long long)k * nn + t];
+    F[v.mat0 + t] = s;
+  }
+}
+
+// Pold <- P ; P <- a P + (1-a) Pnew on active molecules (scf_loop.py:264-267, 1045-1056)
+SEQM_GLOBAL void mix_linear_kernel(seqm_batch_t b, ScfWork W, double* __restrict__ P, double a) {
+  const int mol = b.mol_order[blockIdx.x];
+  if (!W.active[mol]) return;
+  const MolView v = mol_view(b, mol);
+  const int nn = v.n * v.n;
+  const double oma = 1.0 - a;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const double p = P[v.mat0 + t];
+    W.Pold[v.mat0 + t] = p;
+    P[v.mat0 + t] = (a == 0.0) ? W.Pnew[v.mat0 + t] : a * p + oma * W.Pnew[v.mat0 + t];
+  }
+}
+
+// adaptive mixing, diagonal part (scf_loop.py:350-415).  ONE CTA for the whole batch because the
+// renormalisation loop of the reference stops only when EVERY active molecule is normalised
+// (`if torch.all(done): break`, scf_loop.py:404), and until then it rescales all of them.
+// Molecules are statically assigned to threads; per-molecule state lives in W.fac / W.sum0 / W.dnew.
+SEQM_GLOBAL void adaptive_diag_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ P, int k) {
+  __shared__ int s_flag;
+  const bool third = (k % 3) == 0;
+  const double DAMP = (k > 4) ? 0.05 : 1.0e10;
+  const int per = (b.nmol + blockDim.x - 1) / blockDim.x;
+  // FAC, capped / extrapolated diagonal, SUM0
+  for (int q = 0; q < per; ++q) {
+    const int mol = threadIdx.x + q * blockDim.x;
+    if (mol >= b.nmol || !W.active[mol]) continue;
+    const MolView v = mol_view(b, mol);
+    const int n = v.n;
+    double* dn = W.dnew + (long long)mol * b.nmax;
+    const double* o2 = W.old2 + (long long)mol * b.nmax;
+    const double* Pc = W.Pnew + v.mat0;  // "current": the freshly diagonalised density
+    const double* Pp = P + v.mat0;       // "previous": the density F was built from
+    double fac = 0.0;
+    if (third) {
+      double num = 0.0, den = 0.0;
+      for (int i = 0; i < n; ++i) {
+        const double dc = Pc[i * n + i], dp = Pp[i * n + i];
+        const double d1 = dc - dp, d2 = dc - 2.0 * dp + o2[i];
+        num += d1 * d1;
+        den += d2 * d2;
+      }
+      if (den > 0.0 && num < 100.0 * den) fac = sqrt(num / den);
+    }
+    W.fac[mol] = fac;
+    double sum0 = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const double dc = Pc[i * n + i], dp = Pp[i * n + i];
+      const double delta = dc - dp;
+      double d;
+      if (fabs(delta) > DAMP)
+        d = dp + (delta > 0.0 ? DAMP : (delta < 0.0 ? -DAMP : 0.0));
+      else
+        d = dc + fac * delta;
+      dn[i] = fmin(fmax(d, 0.0), 2.0);
+      sum0 += dc;
+    }
+    W.sum0[mol] = sum0;
+  }
+  // renormalise sum(diag) to SUM0, at most 20 passes, batch-global exit test
+  for (int pass = 0; pass < 20; ++pass) {
+    if (threadIdx.x == 0) s_flag = 1;
+    SEQM_SYNC();
+    for (int q = 0; q < per; ++q) {
+      const int mol = threadIdx.x + q * blockDim.x;
+      if (mol >= b.nmol || !W.active[mol]) continue;
+      const int n = mol_view(b, mol).n;
+      const double* dn = W.dnew + (long long)mol * b.nmax;
+      double sum2 = 0.0;
+      for (int i = 0; i < n; ++i) sum2 += dn[i];
+      const bool large = sum2 > 1.0e-3;
+      const double sum3 = large ? W.sum0[mol] / sum2 : 0.0;
+      W.sum3[mol] = sum3;
+      if (large && !(fabs(sum3 - 1.0) <= 1.0e-5)) s_flag = 0;  // benign race: every writer stores 0
+    }
+    SEQM_SYNC();
+    const int alldone = s_flag;
+    SEQM_SYNC();
+    if (alldone) break;
+    for (int q = 0; q < per; ++q) {
+      const int mol = threadIdx.x + q * blockDim.x;
+      if (mol >= b.nmol || !W.active[mol]) continue;
+      const int n = mol_view(b, mol).n;
+      double* dn = W.dnew + (long long)mol * b.nmax;
+      const double sum3 = W.sum3[mol];
+      int nfull = 0;
+      for (int i = 0; i < n; ++i) {
+        double s = fmax(dn[i] * sum3, 0.0);
+        if (s > 2.0) {
+          s = 2.0;
+          ++nfull;
+        }
+        dn[i] = s;
+      }
+      W.sum0[mol] -= 2.0 * nfull;
+    }
+    SEQM_SYNC();
+  }
+}
+// adaptive mixing, matrix part (scf_loop.py:373-383, 417-420, 546-554)
+SEQM_GLOBAL void adaptive_apply_kernel(seqm_batch_t b, ScfWork W, double* __restrict__ P) {
+  const int mol = b.mol_order[blockIdx.x];
+  if (!W.active[mol]) return;
+  const MolView v = mol_view(b, mol);
+  const int n = v.n, nn = n * n;
+  const double f = W.fac[mol];
+  const double* dn = W.dnew + (long long)mol * b.nmax;
+  double* o2 = W.old2 + (long long)mol * b.nmax;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const int i = t / n, j = t % n;
+    const double pp = P[v.mat0 + t], pc = W.Pnew[v.mat0 + t];
+    W.Pold[v.mat0 + t] = pp;
+    if (i == j) {
+      o2[i] = pp;
+      P[v.mat0 + t] = dn[i];
+    } else {
+      P[v.mat0 + t] = (f != 0.0) ? (1.0 + f) * pc - f * pp : pc;
+    }
+  }
+}
+
+// get_error (scf_loop.py:106-147) fused with elec_energy of the new density; one CTA per molecule.
+SEQM_GLOBAL void energy_error_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ P, const double* __restrict__ H,
+                                     const double* __restrict__ F, int32_t* __restrict__ notconv, double eps,
+                                     int use_diis) {
+  __shared__ double red[33];
+  const int mol = b.mol_order[blockIdx.x];
+  if (!W.active[mol]) return;
+  const MolView v = mol_view(b, mol);
+  const int nn = v.n * v.n;
+  double e = 0.0, d2 = 0.0, dmax = 0.0;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const double p = P[v.mat0 + t];
+    e += p * (H[v.mat0 + t] + F[v.mat0 + t]);
+    const double d = p - W.Pold[v.mat0 + t];
+    d2 += d * d;
+    dmax = fmax(dmax, fabs(d));
+  }
+  e = 0.5 * block_sum(e, red);
+  d2 = block_sum(d2, red);
+  dmax = block_max(dmax, red);
+  if (threadIdx.x == 0) {
+    const double err = e - W.Eel_run[mol];
+    W.err[mol] = err;
+    bool bad = fabs(err) > eps;
+    if (use_diis) bad = bad || (W.diis_err[mol] > 50.0 * eps);
+    if (!bad) {
+      W.dm_err[mol] = sqrt(d2) / (double)(4 * v.nheavy + 4 * v.nhyd);
+      W.dm_elem[mol] = dmax;
+    }
+    const bool nc = bad || (W.dm_err[mol] > 2.0 * eps) || (W.dm_elem[mol] > 15.0 * eps);
+    W.Eel_new[mol] = e;
+    notconv[mol] = nc ? 1 : 0;
+    if (nc) {
+      W.Eel_run[mol] = e;
+      seqm_atomic_add(&W.ctrl->nnot, 1);
+    }
+  }
+}
+SEQM_GLOBAL void commit_active_kernel(seqm_batch_t b, ScfWork W, const int32_t* __restrict__ notconv) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < b.nmol; m += gridDim.x * blockDim.x)
+    W.active[m] = notconv[m];
+}

@@ -1,0 +1,349 @@
+// seqm_b200.cu -- C-ABI entry points of libseqm_b200.so (see include/seqm_b200.h) and the SCF host loop.
+// Single translation unit: all kernels live in the .cuh files included below.
+#include "pair_kernels.cuh"
+#include "scf_driver.cuh"
+
+#ifndef SEQM_HOSTEMU
+#define SEQM_STREAM(s) ((cudaStream_t)(s))
+#else
+#define SEQM_STREAM(s) (s)
+#endif
+
+static int g_num_sms = 148;
+static int g_smem_optin = 227 * 1024;
+static int g_dev_ready = 0;
+static int ensure_device() {
+  if (g_dev_ready) return SEQM_OK;
+#ifndef SEQM_HOSTEMU
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    seqm_set_error("cudaGetDevice: %s (libseqm_b200 needs a CUDA device; there is no CPU fallback)", cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncSetAttribute(jacobi_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+#endif
+  g_dev_ready = 1;
+  return ensure_tables();
+}
+static int check_batch(const seqm_batch_t* b) {
+  if (!b || b->nmol <= 0 || b->nat <= 0) {
+    seqm_set_error("empty batch");
+    return SEQM_ERR_ARG;
+  }
+  if (b->method < 0 || b->method > 2) {
+    seqm_set_error("method %d not supported by this build (MNDO=0, AM1=1, PM3=2)", b->method);
+    return SEQM_ERR_UNSUPPORTED;
+  }
+  if (b->nmax > SEQM_MAX_ORB) {
+    seqm_set_error("molecule with %d orbitals exceeds the shared-memory resident limit of %d", b->nmax, SEQM_MAX_ORB);
+    return SEQM_ERR_TOO_LARGE;
+  }
+  return ensure_device();
+}
+static int threads_for(int nmax) { return nmax <= 24 ? 128 : (nmax <= 64 ? 256 : 512); }
+static int grid1d(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  const long long cap = (long long)g_num_sms * 16;
+  return (int)(g > cap ? cap : g);
+}
+
+// ---- layout conversion kernels ---------------------------------------------------------------------
+// dense (nmol, 4*molsize, 4*molsize) <-> packed.  Real atoms occupy the first na positions of a molecule.
+SEQM_HD int dense_index(const MolView& v, int orb) {  // packed orbital -> row in the dense padded matrix
+  return orb < 4 * v.nheavy ? orb : 4 * v.nheavy + 4 * (orb - 4 * v.nheavy);
+}
+SEQM_GLOBAL void pack_kernel(seqm_batch_t b, const double* __restrict__ dense, double* __restrict__ packed) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n, N = 4 * b.molsize;
+  const double* D = dense + (long long)v.m * N * N;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x)
+    packed[v.mat0 + t] = D[(long long)dense_index(v, t / n) * N + dense_index(v, t % n)];
+}
+SEQM_GLOBAL void unpack_kernel(seqm_batch_t b, const double* __restrict__ packed, double* __restrict__ dense) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n, N = 4 * b.molsize;
+  double* D = dense + (long long)v.m * N * N;
+  for (int t = threadIdx.x; t < N * N; t += blockDim.x) D[t] = 0.0;
+  SEQM_SYNC();
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x)
+    D[(long long)dense_index(v, t / n) * N + dense_index(v, t % n)] = packed[v.mat0 + t];
+}
+SEQM_GLOBAL void initial_density_kernel(seqm_batch_t b, double* __restrict__ P) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    const int i = t / n, j = t % n;
+    double x = 0.0;
+    if (i == j) {
+      const int a = (i < 4 * v.nheavy) ? i / 4 : v.nheavy + (i - 4 * v.nheavy);
+      x = (a < v.nheavy) ? par(b, SEQM_P_TORE, v.a0 + a) / 4.0 : 1.0;
+    }
+    P[v.mat0 + t] = x;
+  }
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------
+extern "C" {
+
+int seqm_abi_version(void) { return SEQM_ABI_VERSION; }
+const char* seqm_last_error(void) { return g_seqm_err; }
+int seqm_max_orbitals(void) { return SEQM_MAX_ORB; }
+
+int seqm_atom_multipoles(const seqm_batch_t* b, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(atom_multipoles_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b);
+  return seqm_check_launch("atom_multipoles_kernel");
+}
+
+int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, double* hab, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (b->npairs == 0) return SEQM_OK;
+  SEQM_LAUNCH(pair_integrals_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, w, hab);
+  return seqm_check_launch("pair_integrals_kernel");
+}
+
+int seqm_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(hcore_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, w, hab, H);
+  return seqm_check_launch("hcore_kernel");
+}
+
+int seqm_fock(const seqm_batch_t* b, const double* P, const double* H, const double* w, double* F,
+              const int32_t* active, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  const size_t smem = sizeof(double) * (size_t)b->nmax * b->nmax;
+  SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, P, H, w, F, active);
+  return seqm_check_launch("fock_kernel");
+}
+
+int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const double* Cguess,
+                     const int32_t* active, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(jacobi_density_kernel, b->nmol, threads_for(b->nmax), jacobi_smem_bytes(b->nmax), SEQM_STREAM(stream), *b, F,
+              P, evals, C, P ? Cguess : nullptr, active);
+  return seqm_check_launch("jacobi_density_kernel");
+}
+
+int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter, const int32_t* active,
+                     void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  const size_t smem = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
+  SEQM_LAUNCH(sp2_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, F, P, eps, niter, active);
+  return seqm_check_launch("sp2_kernel");
+}
+
+int seqm_elec_energy(const seqm_batch_t* b, const double* P, const double* H, const double* F, double* Eelec,
+                     const int32_t* active, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, P, H, F, Eelec, active);
+  return seqm_check_launch("elec_energy_kernel");
+}
+
+int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* w, double* EnucAB, double* Enuc,
+                        void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (b->npairs > 0) {
+    SEQM_LAUNCH(nuclear_energy_kernel, grid1d(b->npairs, 128), 128, 0, SEQM_STREAM(stream), *b, xyz, w, EnucAB);
+    rc = seqm_check_launch("nuclear_energy_kernel");
+    if (rc) return rc;
+  }
+  SEQM_LAUNCH(pair_sum_kernel, b->nmol, 64, 0, SEQM_STREAM(stream), *b, EnucAB, Enuc);
+  return seqm_check_launch("pair_sum_kernel");
+}
+
+int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
+                  void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (b->npairs > 0) {
+    SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, pair_scratch);
+    rc = seqm_check_launch("pair_gradient_kernel");
+    if (rc) return rc;
+  }
+  SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad);
+  return seqm_check_launch("atom_gradient_kernel");
+}
+
+int seqm_pack(const seqm_batch_t* b, const double* dense, double* packed, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(pack_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, dense, packed);
+  return seqm_check_launch("pack_kernel");
+}
+int seqm_unpack(const seqm_batch_t* b, const double* packed, double* dense, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(unpack_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, packed, dense);
+  return seqm_check_launch("unpack_kernel");
+}
+int seqm_initial_density(const seqm_batch_t* b, double* P, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(initial_density_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, P);
+  return seqm_check_launch("initial_density_kernel");
+}
+
+int64_t seqm_scf_workspace_bytes(const seqm_batch_t* b, const seqm_scf_opts_t* o) {
+  if (!b || !o) return -1;
+  return (int64_t)scf_carve(b, o, nullptr, nullptr) + 256;
+}
+
+// Read the control block back; blocks until the stream has drained.
+static int read_ctrl(const ScfWork& W, void* stream, ScfCtrl* h) {
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemcpyAsync(h, W.ctrl, sizeof(ScfCtrl), cudaMemcpyDeviceToHost, SEQM_STREAM(stream));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(SEQM_STREAM(stream));
+  if (e != cudaSuccess) {
+    seqm_set_error("SCF control read-back: %s", cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+#else
+  (void)stream;
+  *h = *W.ctrl;
+#endif
+  return SEQM_OK;
+}
+static int zero_nnot(const ScfWork& W, void* stream) {
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemsetAsync(&W.ctrl->nnot, 0, sizeof(int), SEQM_STREAM(stream));
+  if (e != cudaSuccess) {
+    seqm_set_error("cudaMemsetAsync: %s", cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+#else
+  (void)stream;
+  W.ctrl->nnot = 0;
+#endif
+  return SEQM_OK;
+}
+
+int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
+             double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (o->converger < 0 || o->converger > 2) {
+    seqm_set_error("scf_converger %d not supported (0: constant mixing, 1: adaptive, 2: Pulay DIIS)", o->converger);
+    return SEQM_ERR_UNSUPPORTED;
+  }
+  ScfWork W;
+  unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  scf_carve(b, o, base, &W);
+  cudaStream_t st = SEQM_STREAM(stream);
+  const int nt = threads_for(b->nmax);
+  const size_t sm1 = sizeof(double) * (size_t)b->nmax * b->nmax;
+  const size_t smj = jacobi_smem_bytes(b->nmax);
+  const size_t smsp2 = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
+  const int gm = grid1d(b->nmol, 128);
+  const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
+#define CHK(name)                     \
+  rc = seqm_check_launch(name);       \
+  if (rc) return rc
+  SEQM_LAUNCH(scf_init_kernel, gm, 128, 0, st, *b, W, o->converger);
+  CHK("scf_init_kernel");
+  // F(P0), Eelec(P0)
+  SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)nullptr);
+  CHK("fock_kernel");
+  SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, st, *b, P, H, F, W.Eel_run, (const int32_t*)nullptr);
+  CHK("elec_energy_kernel");
+  int have_C = 0;
+  int counter = -1, cF = 0;
+  int nnot = b->nmol;
+  int printed = 0;
+  // iteration index conventions of the reference: converger 0 counts from 0, converger 1 from 1,
+  // converger 2 reports the number of completed iterations.
+  const int k_first = (o->converger == 1) ? 1 : 0;
+  const int k_last = max_iter;
+  int k = k_first;
+  for (; k <= k_last; ++k) {
+    if (o->converger == 2) {
+      if (nnot == 0) break;
+      cF = (cF < SEQM_NFOCK) ? cF + 1 : SEQM_NFOCK;
+      counter = (counter + 1) % SEQM_NFOCK;
+      SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF);
+      CHK("diis_store_kernel");
+      if (cF >= 2) {
+        SEQM_LAUNCH(diis_solve_kernel, grid1d(b->nmol, 64), 64, 0, st, *b, W, counter, cF);
+        CHK("diis_solve_kernel");
+        SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF);
+        CHK("diis_extrapolate_kernel");
+      }
+    }
+    // Pnew from F on the active molecules
+    if (o->use_sp2) {
+      SEQM_LAUNCH(sp2_kernel, b->nmol, nt, smsp2, st, *b, F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, W.active);
+      CHK("sp2_kernel");
+    } else {
+      SEQM_LAUNCH(jacobi_density_kernel, b->nmol, nt, smj, st, *b, F, W.Pnew, (double*)nullptr, W.C,
+                  (o->warm_start && have_C) ? (const double*)W.C : (const double*)nullptr, W.active);
+      CHK("jacobi_density_kernel");
+      have_C = 1;
+    }
+    // mixing
+    if (o->converger == 0) {
+      SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, o->alpha);
+      CHK("mix_linear_kernel");
+    } else if (o->converger == 1) {
+      SEQM_LAUNCH(adaptive_diag_kernel, 1, 1024, 0, st, *b, W, P, k);
+      CHK("adaptive_diag_kernel");
+      SEQM_LAUNCH(adaptive_apply_kernel, b->nmol, 256, 0, st, *b, W, P);
+      CHK("adaptive_apply_kernel");
+    } else {
+      SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, (cF < 2) ? 0.5 : 0.0);
+      CHK("mix_linear_kernel");
+    }
+    SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)W.active);
+    CHK("fock_kernel");
+    rc = zero_nnot(W, stream);
+    if (rc) return rc;
+    SEQM_LAUNCH(energy_error_kernel, b->nmol, 128, 0, st, *b, W, P, H, F, notconverged, o->eps, o->converger == 2);
+    CHK("energy_error_kernel");
+    SEQM_LAUNCH(commit_active_kernel, gm, 128, 0, st, *b, W, notconverged);
+    CHK("commit_active_kernel");
+    ScfCtrl h;
+    rc = read_ctrl(W, stream, &h);
+    if (rc) return rc;
+    nnot = h.nnot;
+    if (o->converger == 2) {
+      if (h.reset) {
+        counter = -1;
+        cF = 0;
+        SEQM_LAUNCH(emat_reset_kernel, gm, 128, 0, st, *b, W);
+        CHK("emat_reset_kernel");
+      }
+    } else if (nnot == 0) {
+      printed = k;
+      break;
+    }
+    printed = k;
+  }
+  if (o->converger == 2) printed = (k > k_last) ? k_last + 1 : k;
+  if (n_iter_out) *n_iter_out = printed;
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemcpyAsync(Eelec, W.Eel_new, sizeof(double) * b->nmol, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) {
+    seqm_set_error("Eelec copy: %s", cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+#else
+  memcpy(Eelec, W.Eel_new, sizeof(double) * b->nmol);
+#endif
+#undef CHK
+  return SEQM_OK;
+}
+
+}  // extern "C"
