@@ -126,6 +126,14 @@ int64_t seqm_scf_workspace_bytes(const seqm_batch_t* b, const seqm_scf_opts_t* o
 int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
              double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, void* stream);
 
+/* Optional per-kernel timing with CUDA events on the launch stream (bench.py roofline evidence).
+ * enable(1) clears and starts recording; collect() synchronises and returns summed ms / launch counts
+ * per kernel kind (seqm_profile_kinds() entries, names from seqm_profile_name()). */
+int seqm_profile_enable(int on);
+int seqm_profile_kinds(void);
+const char* seqm_profile_name(int kind);
+int seqm_profile_collect(double* ms, int32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,155 @@
+"""`Molecule`: the batch container with the reference's attribute contract (seqm/Molecule.py:11-206).
+
+Construction runs the parser (pair list and index maps, seqm/basics.py:219-403) and the parameter gather
+(seqm/basics.py:406-448) as torch index arithmetic on the molecule's device and builds the device batch
+plan (`_plan`) that every kernel call uses.  Results are delivered by mutation, as in the reference.
+"""
+from typing import Optional
+
+import torch
+
+from . import engine
+from ._lib import get_lib
+
+SUPPORTED_METHODS = ("MNDO", "AM1", "PM3")
+
+
+def check_input(species):
+    """Rows must be non-increasing in Z (Molecule.py:188-206, same message)."""
+    ok = species[:, :-1] >= species[:, 1:]
+    row_ok = ok.all(dim=1)
+    if not bool(row_ok.all()):
+        bad = (~row_ok).nonzero(as_tuple=False).squeeze(1).tolist()
+        rows = ", ".join(map(str, bad))
+        row_word = "row" if len(bad) == 1 else "rows"
+        verb = "is" if len(bad) == 1 else "are"
+        raise ValueError(f"species must be non-increasing along each row, but {row_word} {rows} {verb} not sorted.")
+
+
+def reject_unsupported(seqm_parameters):
+    """The fast path never falls back silently (SURVEY 8(b) option matrix)."""
+    sp = seqm_parameters
+    if sp.get("method") not in SUPPORTED_METHODS:
+        raise NotImplementedError(f"method {sp.get('method')!r}: the B200 path implements {SUPPORTED_METHODS}")
+    bad = []
+    if sp.get("UHF", False):
+        bad.append("UHF=True")
+    if sp.get("excited_states"):
+        bad.append("excited_states")
+    if sp.get("active_state", 0):
+        bad.append("active_state>0")
+    if sp.get("scf_backward", 0) not in (0,):
+        bad.append("scf_backward in {1,2}")
+    if sp.get("2nd_grad", False):
+        bad.append("2nd_grad")
+    if sp.get("dispersion", False):
+        bad.append("dispersion")
+    if sp.get("normal modes", False):
+        bad.append("normal modes")
+    conv = sp.get("scf_converger", [2])
+    if conv[0] not in (0, 1, 2):
+        bad.append(f"scf_converger={conv}")
+    if sp.get("learned"):
+        bad.append("learned parameter gradients")
+    if bad:
+        raise NotImplementedError("not implemented by the B200 SCF path: " + ", ".join(bad))
+
+
+class Molecule(torch.nn.Module):
+    def __init__(self, const, seqm_parameters, coordinates, species, charges=0, mult=1, learned_parameters=dict(),
+                 do_large_tensors=True, _lib=None, *args, **kwargs):  # fmt: skip
+        super().__init__()
+        self.const = const
+        check_input(species)
+        reject_unsupported(seqm_parameters)
+        if coordinates.dtype != torch.float64:
+            raise NotImplementedError("the B200 path is fp64 only: pass float64 coordinates")
+        self.species = species
+        self.coordinates = torch.nn.Parameter(coordinates)
+        self.coordinates.requires_grad_(False)
+        if not torch.is_tensor(charges):
+            charges = charges * torch.ones(coordinates.shape[0], device=coordinates.device)
+        self.tot_charge = charges
+        if not torch.is_tensor(mult):
+            mult = mult * torch.ones(coordinates.shape[0], device=coordinates.device)
+        self.mult = mult
+        if seqm_parameters.get("elements") is None:
+            seqm_parameters["elements"] = [0] + sorted(set(species.reshape(-1).tolist()))
+        self.seqm_parameters = seqm_parameters
+        self.method = seqm_parameters["method"]
+        if callable(learned_parameters):
+            raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
+        lib = _lib if _lib is not None else get_lib()
+        plan = engine.BatchPlan(lib, species, self.method, parameters=learned_parameters, charges=charges)
+        self._plan = plan
+        dev = coordinates.device
+        self.nmol, self.molsize = plan.nmol, plan.molsize
+        self.nHeavy, self.nHydro, self.nocc = plan.nheavy, plan.nhyd, plan.nocc
+        self.nSuperHeavy = torch.zeros_like(plan.nheavy)
+        self.Z = plan.Z
+        self.atom_molid = plan.atom_mol
+        ms = plan.molsize
+        pos = plan.atom_local
+        self.maskd = plan.atom_mol * ms * ms + pos * (ms + 1)
+        self.idxi, self.idxj = plan.pair_i, plan.pair_j
+        self.ni, self.nj = plan.Z[plan.pair_i], plan.Z[plan.pair_j]
+        self.pair_molid = plan.atom_mol[plan.pair_i]
+        self.mask = self.pair_molid * ms * ms + pos[plan.pair_i] * ms + pos[plan.pair_j]
+        self.mask_l = self.pair_molid * ms * ms + pos[plan.pair_j] * ms + pos[plan.pair_i]
+        self._refresh_geometry()
+        cutoff = seqm_parameters.get("pair_outer_cutoff", 1.0e10)
+        if bool((self.rij / const.length_conversion_factor >= cutoff).any()):
+            raise NotImplementedError("pair_outer_cutoff that removes pairs is not supported by the B200 path yet")
+        # per-atom parameter dict (Molecule.py:86-115)
+        names = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha"]
+        ng = {"MNDO": 0, "AM1": 4, "PM3": 2}[self.method]
+        for g in range(1, ng + 1):
+            names += [f"Gaussian{g}_K", f"Gaussian{g}_L", f"Gaussian{g}_M"]
+        self.parameters = {k: plan.parameter(k) for k in names}
+        self.parameters["beta"] = torch.stack((self.parameters["beta_s"], self.parameters["beta_p"]), dim=1)
+        zeros = torch.zeros_like(self.parameters["zeta_s"])
+        for k in ("zeta_d", "s_orb_exp_tail", "p_orb_exp_tail", "d_orb_exp_tail", "U_dd", "F0SD", "G2SD", "rho_core"):
+            self.parameters[k] = zeros
+        self.parameters["Kbeta"] = None
+        zmax = int(species.max())
+        self.alp = torch.zeros((zmax + 1, zmax + 1), dtype=torch.float64, device=dev)
+        self.chi = torch.zeros_like(self.alp)
+        self.norb = self.nHydro + 4 * self.nHeavy
+        non_zero = species != 0
+        self.num_atoms = non_zero.sum(dim=1).to(coordinates.dtype)
+        self.mass = const.mass[species].unsqueeze(2)
+        self.mass_inverse = torch.zeros_like(self.mass)
+        self.mass_inverse[non_zero] = 1.0 / self.mass[non_zero]
+
+        self.force = None
+        self.velocities = None
+        self.acc = None
+        self.dm: Optional[torch.Tensor] = None
+        self.q: Optional[torch.Tensor] = None
+        self.w: Optional[torch.Tensor] = None
+        self._parnuc = None
+        self._gam = None
+        self.Hf = self.Etot = self.Eelec = self.Enuc = self.Eiso = None
+        self.e_mo = self.e_gap = None
+        self.molecular_orbitals = None
+        self.charge = None
+        self.dipole = None
+        self.verbose = True
+        self.analytical_gradient = None
+        self.active_state = 0
+        self.n_scf_iter: Optional[int] = None  # the count the reference only prints (scf_loop.py:975-992)
+
+    def _refresh_geometry(self):
+        """xij (unit vector i->j) and rij in bohr (basics.py:737-746)."""
+        xyz = self._plan.real_xyz(self.coordinates)
+        d = xyz[self.idxj] - xyz[self.idxi]
+        dist = torch.linalg.norm(d, dim=1)
+        self.xij = d / dist.unsqueeze(1)
+        self.rij = dist * self.const.length_conversion_factor
+        return xyz
+
+    def get_coordinates(self):
+        return self.coordinates
+
+    def get_species(self):
+        return self.species

@@ -90,6 +90,10 @@ class SeqmLib:
             "seqm_initial_density": ([B, P, P], C.c_int),
             "seqm_scf_workspace_bytes": ([B, O], C.c_int64),
             "seqm_scf": ([B, O, P, P, P, P, P, P, P, C.POINTER(C.c_int32), P], C.c_int),
+            "seqm_profile_enable": ([C.c_int], C.c_int),
+            "seqm_profile_kinds": ([], C.c_int),
+            "seqm_profile_name": ([C.c_int], C.c_char_p),
+            "seqm_profile_collect": ([C.POINTER(C.c_double), C.POINTER(C.c_int32)], C.c_int),
         }
         for name, (args, res) in sig.items():
             fn = getattr(self.dll, name)
@@ -98,6 +102,17 @@ class SeqmLib:
         self.symbols = list(sig)
         if self.dll.seqm_abi_version() != 1:
             raise SeqmError("libseqm_b200 ABI version mismatch")
+
+    def profile_enable(self, on=True):
+        self.dll.seqm_profile_enable(1 if on else 0)
+
+    def profile_collect(self):
+        """{kernel kind: (milliseconds, launches)} since profile_enable(True)."""
+        n = self.dll.seqm_profile_kinds()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int32 * n)()
+        self.check(self.dll.seqm_profile_collect(ms, cnt), "seqm_profile_collect")
+        return {self.dll.seqm_profile_name(k).decode(): (ms[k], cnt[k]) for k in range(n)}
 
     def check(self, rc, what):
         if rc != 0:

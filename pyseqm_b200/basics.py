@@ -1,0 +1,163 @@
+"""Energy / force assembly with the reference's call contract (seqm/basics.py: Hamiltonian 451-533,
+Energy 813-1244 ground-state branch, Force 1260-1365).  Everything between "pair list exists" and
+"P, E, forces exist" is one sequence of C-ABI kernel launches on the current CUDA stream."""
+import time
+import warnings
+
+import torch
+
+from . import engine
+from .Molecule import reject_unsupported
+from .seqm_functions.constants import ev_kcalpmol  # noqa: F401
+
+
+def _timing(molecule, key, t0):
+    if molecule.const.do_timing:
+        if molecule.coordinates.is_cuda:
+            torch.cuda.synchronize()
+        molecule.const.timing[key].append(time.time() - t0)
+        return time.time()
+    return t0
+
+
+class Energy(torch.nn.Module):
+    def __init__(self, seqm_parameters):
+        super().__init__()
+        reject_unsupported(seqm_parameters)
+        self.seqm_parameters = seqm_parameters
+        self.method = seqm_parameters["method"]
+        self.Hf_flag = seqm_parameters.get("Hf_flag", True)
+        self.eig = seqm_parameters.get("eig", True)
+        self.eps = float(seqm_parameters["scf_eps"])
+        self.sp2 = seqm_parameters.get("sp2", [False])
+        self.scf_converger = seqm_parameters.get("scf_converger", [2])
+        self.warm_start = bool(seqm_parameters.get("b200_eig_warm_start", True))
+        self.notconverged = None
+
+    def forward(self, molecule, learned_parameters=dict(), all_terms=False, P0=None, do_force=False, *args, **kwargs):
+        if learned_parameters:
+            raise NotImplementedError("pass learned parameters (dict of (nat,) tensors) to Molecule(...), not to forward()")
+        plan = molecule._plan
+        const = molecule.const
+        t0 = time.time()
+        xyz = molecule._refresh_geometry()
+        # hcore(): pair integrals + Hcore assembly
+        w, hab = engine.op_pair_integrals(plan, xyz)
+        H = engine.op_hcore(plan, w, hab)
+        t0 = _timing(molecule, "Hcore + STO Integrals", t0)
+        # density: initial guess or the caller's P0 (overwritten in place, ElectronicStructure.py:78)
+        P = engine.op_initial_density(plan) if P0 is None else engine.op_pack(plan, P0)
+        F, Eelec, notconv, n_iter = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
+                                                  warm_start=self.warm_start)  # fmt: skip
+        molecule.n_scf_iter = n_iter
+        if molecule.verbose:
+            tag = {0: "scf direct step  ", 1: "scf adaptive step    ", 2: "scf pulay diis   "}[self.scf_converger[0]]
+            print(f"{tag}: {n_iter:>3d} | N not converged: {int(notconv.sum())}")
+        if bool(notconv.any()):
+            nnot = int(notconv.sum())
+            print("did not converge", nnot)
+            warnings.warn("SCF for %d/%d molecules doesn't converge after %d iterations" % (nnot, plan.nmol, 1000))
+        t0 = _timing(molecule, "SCF", t0)
+        self.notconverged = notconv
+        molecule.w = w
+        molecule._gam = w[:, 0, 0]
+        if self.eig:
+            e_mo_n, _, Cm = engine.op_eig_density(plan, F, want_P=False, want_C=True)
+            N = 4 * plan.molsize
+            e_mo = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
+            e_mo[:, : plan.nmax] = e_mo_n
+            lumo = plan.nocc.unsqueeze(1)
+            e_gap = (e_mo.gather(1, lumo) - e_mo.gather(1, lumo - 1)).reshape(-1)
+            molecule.molecular_orbitals = _orbitals_dense(plan, Cm)
+        else:
+            e_mo, e_gap = None, None
+        EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)
+        grad = None
+        if do_force:
+            g = engine.op_gradient(plan, xyz, P)
+            grad = torch.zeros((plan.nmol * plan.molsize, 3), dtype=torch.float64, device=plan.device)
+            grad[plan.real_atoms] = g
+            grad = grad.reshape(plan.nmol, plan.molsize, 3)
+            molecule.analytical_gradient = grad
+            t0 = _timing(molecule, "Force", t0)
+        Pd = engine.op_unpack(plan, P, out=P0 if (P0 is not None and P0.is_contiguous()) else None)
+        if P0 is not None and Pd is not P0:
+            P0.copy_(Pd)
+            Pd = P0
+        _ground_dipole(molecule, Pd)
+        Etot = Eelec + Enuc
+        Z = plan.Z
+        Eiso_atom = (
+            plan.parameter("U_ss") * const.ussc[Z] + plan.parameter("U_pp") * const.uppc[Z]
+            + plan.parameter("g_ss") * const.gssc[Z] + plan.parameter("g_pp") * const.gppc[Z]
+            + plan.parameter("g_sp") * const.gspc[Z] + plan.parameter("g_p2") * const.gp2c[Z]
+            + plan.parameter("h_sp") * const.hspc[Z]
+        )  # fmt: skip  (energy.py:8-23)
+        Eiso = torch.zeros_like(Etot).index_add_(0, plan.atom_mol, Eiso_atom)
+        Hf = Etot - Eiso
+        if self.Hf_flag:
+            Hf = Hf + torch.zeros_like(Etot).index_add_(0, plan.atom_mol, const.eheat[Z])
+        self._grad = grad
+        if all_terms:
+            return Hf, Etot, Eelec, Enuc, Eiso, EnucAB, e_gap, e_mo, Pd, None, notconv
+        return Eelec, EnucAB, Pd, notconv
+
+
+def _orbitals_dense(plan, Cm):
+    """(nmol, nmax, nmax) eigenvector matrices, identity on the padding (diag.py:110-241 `v`)."""
+    nmol, nmax = plan.nmol, plan.nmax
+    V = torch.zeros((nmol, nmax, nmax), dtype=torch.float64, device=plan.device)
+    idx = torch.arange(nmax, device=plan.device)
+    V[:, idx, idx] = 1.0
+    mat0 = plan.t["mol_mat0"]
+    norb = plan.norb
+    for n in torch.unique(norb).tolist():
+        sel = torch.nonzero(norb == n, as_tuple=False).squeeze(1)
+        off = mat0[sel].unsqueeze(1) + torch.arange(n * n, device=plan.device).unsqueeze(0)
+        blk = Cm[off].reshape(-1, n, n)
+        V[sel, :n, :n] = blk
+        if n < nmax:
+            V[sel.unsqueeze(1), idx[n:].unsqueeze(0), idx[n:].unsqueeze(0)] = 1.0
+            V[sel, :n, n:] = 0.0
+    return V
+
+
+def _ground_dipole(molecule, Pd):
+    """calc_ground_dipole (seqm/seqm_functions/dipole.py:85-107) on the dense density."""
+    from .seqm_functions.constants import a0, debye_to_AU, to_debye
+
+    const = molecule.const
+    b, n = molecule.coordinates.shape[:2]
+    sp = molecule.species
+    coord = molecule.coordinates.detach()
+    blocks = Pd.view(b, n, 4, n, 4).diagonal(0, 1, 3).permute(0, 3, 1, 2)  # (b, n, 4, 4)
+    trace = blocks.diagonal(0, 2, 3).sum(-1)
+    heavy = (sp > 1).to(Pd.dtype)
+    hyd = (sp == 1).to(Pd.dtype)
+    # -R * (population of the atom) ; hydrogens only count their s orbital
+    pop = trace * heavy + blocks[:, :, 0, 0] * hyd
+    elec = -(pop.unsqueeze(-1) * coord).sum(dim=1)
+    # sp hybridisation term: -2 * dd * a0 * P[s, p_k]
+    dd = torch.zeros((b * n,), dtype=Pd.dtype, device=Pd.device)
+    dd[molecule._plan.real_atoms] = molecule._plan.parameter("dd") * a0
+    dd = dd.view(b, n) * heavy
+    elec = elec - 2.0 * (dd.unsqueeze(-1) * blocks[:, :, 0, 1:4]).sum(dim=1)
+    nuc = (const.tore[sp].unsqueeze(-1) * coord).sum(dim=1)
+    molecule.dipole = (elec + nuc) * to_debye * debye_to_AU
+
+
+class Force(torch.nn.Module):
+    """Force.forward (basics.py:1260-1365): all three force modes of the reference (autograd,
+    analytical, semi-numerical) compute the same Hellmann-Feynman gradient; one kernel serves them."""
+
+    def __init__(self, seqm_parameters):
+        super().__init__()
+        self.energy = Energy(seqm_parameters)
+        self.seqm_parameters = seqm_parameters
+
+    def forward(self, molecule, learned_parameters=dict(), P0=None, do_force=True, *args, **kwargs):
+        Hf, Etot, Eelec, Enuc, Eiso, _, e_gap, e, D, charge, notconverged = self.energy(
+            molecule, learned_parameters=learned_parameters, all_terms=True, P0=P0, do_force=do_force
+        )
+        force = -self.energy._grad if do_force else torch.tensor([])
+        return force, D, Hf, Etot, Eelec, Enuc, Eiso, e, e_gap, charge, notconverged

@@ -9,6 +9,40 @@
 #define SEQM_STREAM(s) (s)
 #endif
 
+
+// ---- optional per-kernel timing (CUDA events on the launch stream; used by bench.py for the roofline) ----
+enum { PK_PAIR = 0, PK_HCORE, PK_FOCK, PK_JACOBI, PK_SP2, PK_DIIS_STORE, PK_DIIS_SOLVE, PK_DIIS_EXTRAP, PK_MIX,
+       PK_ENERGY_ERR, PK_NUC, PK_GRAD, PK_OTHER, PK_COUNT };
+static const char* g_pk_names[PK_COUNT] = {"pair_integrals", "hcore", "fock", "jacobi_density", "sp2", "diis_store",
+                                           "diis_solve", "diis_extrapolate", "mix", "energy_error", "nuclear_energy",
+                                           "gradient", "other"};
+static int g_prof_on = 0;
+#ifndef SEQM_HOSTEMU
+#define SEQM_PROF_MAX 32768
+static cudaEvent_t g_ev0[SEQM_PROF_MAX], g_ev1[SEQM_PROF_MAX];
+static int g_ev_kind[SEQM_PROF_MAX];
+static int g_ev_n = 0, g_ev_created = 0;
+static void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on || g_ev_n >= SEQM_PROF_MAX) return;
+  if (g_ev_n >= g_ev_created) {
+    cudaEventCreate(&g_ev0[g_ev_n]);
+    cudaEventCreate(&g_ev1[g_ev_n]);
+    g_ev_created = g_ev_n + 1;
+  }
+  g_ev_kind[g_ev_n] = kind;
+  cudaEventRecord(g_ev0[g_ev_n], st);
+}
+static void prof_end(cudaStream_t st) {
+  if (!g_prof_on || g_ev_n >= SEQM_PROF_MAX) return;
+  cudaEventRecord(g_ev1[g_ev_n], st);
+  ++g_ev_n;
+}
+#else
+static void prof_begin(int, cudaStream_t) {}
+static void prof_end(cudaStream_t) {}
+#endif
+#define PROF(kind, st, stmt) do { prof_begin(kind, st); stmt; prof_end(st); } while (0)
+
 static int g_num_sms = 148;
 static int g_smem_optin = 227 * 1024;
 static int g_dev_ready = 0;
@@ -23,10 +57,16 @@ static int ensure_device() {
   }
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaFuncSetAttribute(jacobi_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-  cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-  cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
-  cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin);
+  const int dyn = g_smem_optin - 2048;  // leave room for the kernels' small static shared arrays
+  e = cudaFuncSetAttribute(jacobi_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e != cudaSuccess) {
+    seqm_set_error("cudaFuncSetAttribute(max dynamic shared memory %d): %s", dyn, cudaGetErrorString(e));
+    cudaGetLastError();
+    return SEQM_ERR_CUDA;
+  }
 #endif
   g_dev_ready = 1;
   return ensure_tables();
@@ -96,6 +136,31 @@ int seqm_abi_version(void) { return SEQM_ABI_VERSION; }
 const char* seqm_last_error(void) { return g_seqm_err; }
 int seqm_max_orbitals(void) { return SEQM_MAX_ORB; }
 
+
+int seqm_profile_enable(int on) {
+  g_prof_on = on;
+#ifndef SEQM_HOSTEMU
+  g_ev_n = 0;
+#endif
+  return SEQM_OK;
+}
+int seqm_profile_kinds(void) { return PK_COUNT; }
+const char* seqm_profile_name(int kind) { return (kind >= 0 && kind < PK_COUNT) ? g_pk_names[kind] : ""; }
+/* sums the recorded intervals per kernel kind (ms) and their launch counts; synchronises the device */
+int seqm_profile_collect(double* ms, int32_t* counts) {
+  for (int k = 0; k < PK_COUNT; ++k) { ms[k] = 0.0; counts[k] = 0; }
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { seqm_set_error("profile collect: %s", cudaGetErrorString(e)); return SEQM_ERR_CUDA; }
+  for (int i = 0; i < g_ev_n; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_ev0[i], g_ev1[i]) == cudaSuccess) { ms[g_ev_kind[i]] += t; counts[g_ev_kind[i]]++; }
+  }
+  g_ev_n = 0;
+#endif
+  return SEQM_OK;
+}
+
 int seqm_atom_multipoles(const seqm_batch_t* b, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
@@ -107,14 +172,14 @@ int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, dou
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs == 0) return SEQM_OK;
-  SEQM_LAUNCH(pair_integrals_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, w, hab);
+  PROF(PK_PAIR, SEQM_STREAM(stream), SEQM_LAUNCH(pair_integrals_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, w, hab));
   return seqm_check_launch("pair_integrals_kernel");
 }
 
 int seqm_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
-  SEQM_LAUNCH(hcore_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, w, hab, H);
+  PROF(PK_HCORE, SEQM_STREAM(stream), SEQM_LAUNCH(hcore_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, w, hab, H));
   return seqm_check_launch("hcore_kernel");
 }
 
@@ -123,7 +188,7 @@ int seqm_fock(const seqm_batch_t* b, const double* P, const double* H, const dou
   int rc = check_batch(b);
   if (rc) return rc;
   const size_t smem = sizeof(double) * (size_t)b->nmax * b->nmax;
-  SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, P, H, w, F, active);
+  PROF(PK_FOCK, SEQM_STREAM(stream), SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, P, H, w, F, active));
   return seqm_check_launch("fock_kernel");
 }
 
@@ -131,8 +196,8 @@ int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* 
                      const int32_t* active, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
-  SEQM_LAUNCH(jacobi_density_kernel, b->nmol, threads_for(b->nmax), jacobi_smem_bytes(b->nmax), SEQM_STREAM(stream), *b, F,
-              P, evals, C, P ? Cguess : nullptr, active);
+  PROF(PK_JACOBI, SEQM_STREAM(stream), SEQM_LAUNCH(jacobi_density_kernel, b->nmol, threads_for(b->nmax), jacobi_smem_bytes(b->nmax), SEQM_STREAM(stream), *b, F,
+              P, evals, C, P ? Cguess : nullptr, active));
   return seqm_check_launch("jacobi_density_kernel");
 }
 
@@ -141,7 +206,7 @@ int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double e
   int rc = check_batch(b);
   if (rc) return rc;
   const size_t smem = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
-  SEQM_LAUNCH(sp2_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, F, P, eps, niter, active);
+  PROF(PK_SP2, SEQM_STREAM(stream), SEQM_LAUNCH(sp2_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, F, P, eps, niter, active));
   return seqm_check_launch("sp2_kernel");
 }
 
@@ -149,7 +214,7 @@ int seqm_elec_energy(const seqm_batch_t* b, const double* P, const double* H, co
                      const int32_t* active, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
-  SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, P, H, F, Eelec, active);
+  PROF(PK_OTHER, SEQM_STREAM(stream), SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, P, H, F, Eelec, active));
   return seqm_check_launch("elec_energy_kernel");
 }
 
@@ -158,7 +223,7 @@ int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* 
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    SEQM_LAUNCH(nuclear_energy_kernel, grid1d(b->npairs, 128), 128, 0, SEQM_STREAM(stream), *b, xyz, w, EnucAB);
+    PROF(PK_NUC, SEQM_STREAM(stream), SEQM_LAUNCH(nuclear_energy_kernel, grid1d(b->npairs, 128), 128, 0, SEQM_STREAM(stream), *b, xyz, w, EnucAB));
     rc = seqm_check_launch("nuclear_energy_kernel");
     if (rc) return rc;
   }
@@ -171,11 +236,11 @@ int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, dou
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, pair_scratch);
+    PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, pair_scratch));
     rc = seqm_check_launch("pair_gradient_kernel");
     if (rc) return rc;
   }
-  SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad);
+  PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad));
   return seqm_check_launch("atom_gradient_kernel");
 }
 
@@ -256,9 +321,9 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   SEQM_LAUNCH(scf_init_kernel, gm, 128, 0, st, *b, W, o->converger);
   CHK("scf_init_kernel");
   // F(P0), Eelec(P0)
-  SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)nullptr);
+  PROF(PK_FOCK, SEQM_STREAM(stream), SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)nullptr));
   CHK("fock_kernel");
-  SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, st, *b, P, H, F, W.Eel_run, (const int32_t*)nullptr);
+  PROF(PK_OTHER, SEQM_STREAM(stream), SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, st, *b, P, H, F, W.Eel_run, (const int32_t*)nullptr));
   CHK("elec_energy_kernel");
   int have_C = 0;
   int counter = -1, cF = 0;
@@ -274,43 +339,43 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       if (nnot == 0) break;
       cF = (cF < SEQM_NFOCK) ? cF + 1 : SEQM_NFOCK;
       counter = (counter + 1) % SEQM_NFOCK;
-      SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF);
+      PROF(PK_DIIS_STORE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF));
       CHK("diis_store_kernel");
       if (cF >= 2) {
-        SEQM_LAUNCH(diis_solve_kernel, grid1d(b->nmol, 64), 64, 0, st, *b, W, counter, cF);
+        PROF(PK_DIIS_SOLVE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_solve_kernel, grid1d(b->nmol, 64), 64, 0, st, *b, W, counter, cF));
         CHK("diis_solve_kernel");
-        SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF);
+        PROF(PK_DIIS_EXTRAP, SEQM_STREAM(stream), SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF));
         CHK("diis_extrapolate_kernel");
       }
     }
     // Pnew from F on the active molecules
     if (o->use_sp2) {
-      SEQM_LAUNCH(sp2_kernel, b->nmol, nt, smsp2, st, *b, F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, W.active);
+      PROF(PK_SP2, SEQM_STREAM(stream), SEQM_LAUNCH(sp2_kernel, b->nmol, nt, smsp2, st, *b, F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, W.active));
       CHK("sp2_kernel");
     } else {
-      SEQM_LAUNCH(jacobi_density_kernel, b->nmol, nt, smj, st, *b, F, W.Pnew, (double*)nullptr, W.C,
-                  (o->warm_start && have_C) ? (const double*)W.C : (const double*)nullptr, W.active);
+      PROF(PK_JACOBI, SEQM_STREAM(stream), SEQM_LAUNCH(jacobi_density_kernel, b->nmol, nt, smj, st, *b, F, W.Pnew, (double*)nullptr, W.C,
+                  (o->warm_start && have_C) ? (const double*)W.C : (const double*)nullptr, W.active));
       CHK("jacobi_density_kernel");
       have_C = 1;
     }
     // mixing
     if (o->converger == 0) {
-      SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, o->alpha);
+      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, o->alpha));
       CHK("mix_linear_kernel");
     } else if (o->converger == 1) {
-      SEQM_LAUNCH(adaptive_diag_kernel, 1, 1024, 0, st, *b, W, P, k);
+      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_diag_kernel, 1, 1024, 0, st, *b, W, P, k));
       CHK("adaptive_diag_kernel");
-      SEQM_LAUNCH(adaptive_apply_kernel, b->nmol, 256, 0, st, *b, W, P);
+      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_apply_kernel, b->nmol, 256, 0, st, *b, W, P));
       CHK("adaptive_apply_kernel");
     } else {
-      SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, (cF < 2) ? 0.5 : 0.0);
+      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, (cF < 2) ? 0.5 : 0.0));
       CHK("mix_linear_kernel");
     }
-    SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)W.active);
+    PROF(PK_FOCK, SEQM_STREAM(stream), SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)W.active));
     CHK("fock_kernel");
     rc = zero_nnot(W, stream);
     if (rc) return rc;
-    SEQM_LAUNCH(energy_error_kernel, b->nmol, 128, 0, st, *b, W, P, H, F, notconverged, o->eps, o->converger == 2);
+    PROF(PK_ENERGY_ERR, SEQM_STREAM(stream), SEQM_LAUNCH(energy_error_kernel, b->nmol, 128, 0, st, *b, W, P, H, F, notconverged, o->eps, o->converger == 2));
     CHK("energy_error_kernel");
     SEQM_LAUNCH(commit_active_kernel, gm, 128, 0, st, *b, W, notconverged);
     CHK("commit_active_kernel");

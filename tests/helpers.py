@@ -1,0 +1,90 @@
+"""Shared checks: run a golden case through the C ABI (CUDA library on the GPU box, host-emulation
+build of the same kernel sources on CPU-only CI) and compare with the reference-generated fixture."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+from conftest import ROOT, TOL_DM, TOL_E, TOL_F, load_golden
+
+import pyseqm_b200 as seqm
+from pyseqm_b200 import engine
+from pyseqm_b200._lib import SeqmLib
+
+
+def hostemu_lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+
+    return SeqmLib(ge.build_hostemu())
+
+
+def cuda_lib():
+    from pyseqm_b200._lib import get_lib
+
+    return get_lib()
+
+
+def run_molecule(lib, device, species, coordinates, sp, P0=None):
+    torch.set_default_dtype(torch.float64)
+    const = seqm.Constants().to(device)
+    mol = seqm.Molecule(const, dict(sp), torch.as_tensor(coordinates, device=device),
+                        torch.as_tensor(species, device=device), _lib=lib)  # fmt: skip
+    mol.verbose = False
+    es = seqm.Electronic_Structure(dict(sp))
+    es(mol, P0=P0)
+    return mol, es
+
+
+def check_golden_case(lib, device, name, sp2_tolerant=False):
+    g = load_golden(name)
+    mol, es = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"])
+    assert mol.n_scf_iter == g["n_scf_iter"], (mol.n_scf_iter, g["n_scf_iter"])
+    assert not bool(es.notconverged.any())
+    te, tdm, tf = (TOL_E, TOL_DM, TOL_F) if not sp2_tolerant else (2e-4, 5e-6, 5e-5)
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "Eiso", "e_gap"):
+        assert np.abs(getattr(mol, k).cpu().numpy() - g[k]).max() < te, k
+    for k, tol in (("dm", tdm), ("q", tdm), ("e_mo", te), ("force", tf)):
+        if k in g:
+            assert np.abs(getattr(mol, k).cpu().numpy() - g[k]).max() < tol, k
+    if "dipole" in g and not sp2_tolerant:
+        assert np.abs(mol.dipole.cpu().numpy() - g["dipole"]).max() < 1e-6
+    return mol
+
+
+def check_operator_level(lib, device, method):
+    """hcore -> (w, M), fock(X), sym_eig_trunc(F), SP2(F) against the reference's operator outputs."""
+    g = load_golden(f"cfg1_{method}_c2")
+    species = torch.as_tensor(g["species"], device=device)
+    coords = torch.as_tensor(g["coordinates"], device=device)
+    plan = engine.BatchPlan(lib, species, method)
+    xyz = plan.real_xyz(coords)
+    w, hab = engine.op_pair_integrals(plan, xyz)
+    assert np.abs(w.cpu().numpy() - g["op_w"]).max() < 1e-12
+    H = engine.op_hcore(plan, w, hab)
+    Hd = engine.op_unpack(plan, H).cpu().numpy()
+    nmol, ms = plan.nmol, plan.molsize
+    Mref = g["op_M"].reshape(nmol, ms, ms, 4, 4).transpose(0, 1, 3, 2, 4).reshape(nmol, 4 * ms, 4 * ms)
+    assert np.abs(np.triu(Hd) - Mref).max() < 1e-12  # the reference keeps the upper triangle only
+    assert np.abs(Hd - Hd.transpose(0, 2, 1)).max() == 0.0
+    X = engine.op_pack(plan, torch.as_tensor(g["op_X"], device=device))
+    F = engine.op_fock(plan, X, H, w)
+    assert np.abs(engine.op_unpack(plan, F).cpu().numpy() - g["op_F"]).max() < 1e-11
+    Fg = engine.op_pack(plan, torch.as_tensor(g["op_F"], device=device))
+    e, P, Cm = engine.op_eig_density(plan, Fg, want_C=True)
+    assert np.abs(engine.op_unpack(plan, P).cpu().numpy() - g["op_P"]).max() < 1e-10
+    assert np.abs(e.cpu().numpy() - g["op_e"][:, : plan.nmax]).max() < 1e-10
+    # warm start from the exact eigenvectors must reproduce the same density
+    e2, P2, _ = engine.op_eig_density(plan, Fg, Cguess=Cm)
+    assert np.abs((P2 - P).cpu().numpy()).max() < 1e-11
+    # SP2 at native size: the largest molecule (toluene) carries no padding in the reference either
+    Psp2, nit = engine.op_sp2_density(plan, Fg, 1.0e-5)
+    d = engine.op_unpack(plan, Psp2).cpu().numpy()
+    m = int(np.argmax(plan.norb.cpu().numpy()))
+    from seqm_oracle.density import packed_index
+
+    idx = packed_index(int(plan.nheavy[m]), int(plan.nhyd[m]))
+    assert np.abs(d[m][np.ix_(idx, idx)] - g["op_sp2_packed"][m]).max() < 1e-9
+    return plan

@@ -1,0 +1,138 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against
+ (1) the reference-generated golden fixtures (operator level and end to end),
+ (2) the numpy oracle on seeded synthetic inputs at sizes it finishes in seconds,
+ (3) size-independent properties at the full BASELINE size (4096 QM9-size molecules).
+Tolerances are BASELINE.json's: energies 1e-6 eV, density 1e-8, forces 1e-5 eV/A, equal iteration counts."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TOL_DM, TOL_E, TOL_F, load_golden
+from helpers import check_golden_case, check_operator_level, cuda_lib, run_molecule
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return cuda_lib()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_cuda_library_is_the_one_loaded(lib):
+    assert lib.path.endswith("pyseqm_b200/lib/libseqm_b200.so")
+    assert lib.dll.seqm_abi_version() == 1
+
+
+@pytest.mark.parametrize("method", ["AM1", "PM3", "MNDO"])
+def test_operator_level(lib, dev, method):
+    check_operator_level(lib, dev, method)
+
+
+@pytest.mark.parametrize(
+    "name",
+    ["cfg1_AM1_c2", "cfg1_AM1_c1", "cfg1_AM1_c0", "cfg1_PM3_c2", "cfg1_PM3_c1", "cfg1_PM3_c0", "cfg1_MNDO_c2",
+     "cfg1_MNDO_c1", "cfg1_MNDO_c0", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48",
+     "cfg3_coronene_AM1"],
+)  # fmt: skip
+def test_single_point_golden(lib, dev, name):
+    check_golden_case(lib, dev, name)
+
+
+def test_autograd_mode_forces_of_reference(lib, dev):
+    g = load_golden("cfg1_AM1_autograd")
+    mol, _ = run_molecule(lib, dev, g["species"], g["coordinates"], g["seqm_parameters"])
+    assert np.abs(mol.force.cpu().numpy() - g["force"]).max() < TOL_F
+
+
+def test_sp2_route(lib, dev):
+    mol = check_golden_case(lib, dev, "cfg1_AM1_sp2", sp2_tolerant=True)
+    g = load_golden("cfg1_AM1_sp2")
+    assert abs(float(mol.Etot[2]) - g["Etot"][2]) < TOL_E  # the unpadded molecule
+
+
+@pytest.mark.parametrize("method,conv,eps", [("PM3", [2], 1e-7), ("AM1", [1], 1e-6), ("MNDO", [0, 0.2], 1e-6)])
+def test_against_oracle_on_seeded_batch(lib, dev, method, conv, eps):
+    import seqm_oracle as so
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    species, coords = qm9_like_batch(96, seed=11)
+    sp = {"method": method, "scf_eps": eps, "scf_converger": conv, "sp2": [False]}
+    ref = so.single_point(species, coords, sp)
+    mol, es = run_molecule(lib, dev, species, coords, sp)
+    assert mol.n_scf_iter == ref["n_scf_iter"]
+    assert not bool(es.notconverged.any())
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "e_gap"):
+        assert np.abs(getattr(mol, k).cpu().numpy() - ref[k]).max() < TOL_E, k
+    assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < TOL_DM
+    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F
+
+
+def test_ragged_and_tiny_inputs(lib, dev):
+    """H2 next to a 27-atom molecule, single-molecule batch, hydrogen-only molecule."""
+    import seqm_oracle as so
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    s, c = qm9_like_batch(8, seed=5)
+    s[0] = 0
+    c[0] = 0.0
+    s[0, :2] = 1
+    c[0, 1, 0] = 0.74
+    sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2]}
+    ref = so.single_point(s, c, sp)
+    mol, _ = run_molecule(lib, dev, s, c, sp)
+    assert mol.n_scf_iter == ref["n_scf_iter"]
+    assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < TOL_E
+    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F
+    ref1 = so.single_point(s[3:4], c[3:4], sp)
+    mol1, _ = run_molecule(lib, dev, s[3:4], c[3:4], sp)
+    assert np.abs(mol1.Etot.cpu().numpy() - ref1["Etot"]).max() < TOL_E
+    assert float(mol.force[0, 2:].abs().max()) == 0.0  # padding rows stay zero
+
+
+def test_full_size_properties(lib, dev):
+    """BASELINE configs[1] size: 4096 molecules, PM3, DIIS, 1e-7 -- checked through invariants."""
+    from pyseqm_b200 import engine
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    species, coords = qm9_like_batch(4096, seed=0)
+    sp = {"method": "PM3", "scf_eps": 1e-7, "scf_converger": [2], "sp2": [False]}
+    mol, es = run_molecule(lib, dev, species, coords, sp)
+    assert not bool(es.notconverged.any())
+    P = mol.dm
+    nocc = mol.nocc.to(torch.float64)
+    assert float((P.diagonal(dim1=1, dim2=2).sum(1) - 2.0 * nocc).abs().max()) < 1e-9  # tr P = N_electrons
+    assert float((torch.bmm(P, P) - 2.0 * P).abs().max()) < 1e-9  # idempotent (orthogonal AO basis)
+    assert float((P - P.transpose(1, 2)).abs().max()) == 0.0
+    assert float(mol.force.sum(dim=1).abs().max()) < 1e-8  # no net force on any molecule
+    torque = torch.cross(mol.coordinates.detach(), mol.force, dim=2).sum(dim=1)
+    assert float(torque.abs().max()) < 1e-4  # no net torque (to the accuracy the 1e-7 SCF leaves in P)
+    assert float((mol.q.sum(dim=1)).abs().max()) < 1e-9  # neutral molecules
+    # a shuffled sub-batch gives the same per-molecule answers (no cross-talk between molecules);
+    # iteration paths are batch independent for the constant-mixing converger
+    sp0 = {"method": "PM3", "scf_eps": 1e-8, "scf_converger": [0, 0.2], "sp2": [False]}
+    idx = np.random.default_rng(0).permutation(4096)[:64]
+    a, _ = run_molecule(lib, dev, species[idx], coords[idx], sp0)
+    b, _ = run_molecule(lib, dev, species[np.sort(idx)], coords[np.sort(idx)], sp0)
+    order = np.argsort(idx)
+    assert float((a.Etot[order] - b.Etot).abs().max()) < 1e-9
+    assert float((a.Etot.cpu() - mol.Etot[idx].cpu()).abs().max()) < 1e-5  # different convergers, same fixed point
+
+
+def test_rotation_and_translation_invariance(lib, dev):
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    s, c = qm9_like_batch(32, seed=3)
+    sp = {"method": "AM1", "scf_eps": 1e-8, "scf_converger": [2]}
+    a, _ = run_molecule(lib, dev, s, c, sp)
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    c2 = (c @ R.T + np.array([1.0, -2.0, 0.5])) * (s > 0)[:, :, None]
+    b, _ = run_molecule(lib, dev, s, c2, sp)
+    assert float((a.Etot - b.Etot).abs().max()) < 1e-7
+    fa = a.force.cpu().numpy() @ R.T
+    assert np.abs(fa - b.force.cpu().numpy()).max() < 1e-5
