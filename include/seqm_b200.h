@@ -129,6 +129,10 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
 /* Optional per-kernel timing with CUDA events on the launch stream (bench.py roofline evidence).
  * enable(1) clears and starts recording; collect() synchronises and returns summed ms / launch counts
  * per kernel kind (seqm_profile_kinds() entries, names from seqm_profile_name()). */
+/* number of kernel launches issued by this library since load (bench.py gpu_launches) */
+long long seqm_launch_count(void);
+/* measured FP64 FMA peak (TFLOP/s) of the current device: roofline denominator of the FP64-bound kernels */
+double seqm_fp64_peak_tflops(void);
 int seqm_profile_enable(int on);
 int seqm_profile_kinds(void);
 const char* seqm_profile_name(int kind);

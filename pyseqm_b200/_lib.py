@@ -90,6 +90,8 @@ class SeqmLib:
             "seqm_initial_density": ([B, P, P], C.c_int),
             "seqm_scf_workspace_bytes": ([B, O], C.c_int64),
             "seqm_scf": ([B, O, P, P, P, P, P, P, P, C.POINTER(C.c_int32), P], C.c_int),
+            "seqm_launch_count": ([], C.c_longlong),
+            "seqm_fp64_peak_tflops": ([], C.c_double),
             "seqm_profile_enable": ([C.c_int], C.c_int),
             "seqm_profile_kinds": ([], C.c_int),
             "seqm_profile_name": ([C.c_int], C.c_char_p),

@@ -8,6 +8,7 @@
 #define SEQM_MAX_ORB 118  // two n x n fp64 matrices must fit the 227 KB shared memory of one SM
 
 static char g_seqm_err[512] = "";
+long long g_seqm_launches = 0;
 void seqm_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

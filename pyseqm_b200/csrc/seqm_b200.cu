@@ -129,6 +129,17 @@ SEQM_GLOBAL void initial_density_kernel(seqm_batch_t b, double* __restrict__ P) 
   }
 }
 
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, 2 flops per FMA.
+SEQM_GLOBAL void fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+    a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 123.456) out[0] = a0;
+}
+
 // ---- C ABI ---------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -136,6 +147,38 @@ int seqm_abi_version(void) { return SEQM_ABI_VERSION; }
 const char* seqm_last_error(void) { return g_seqm_err; }
 int seqm_max_orbitals(void) { return SEQM_MAX_ORB; }
 
+
+long long seqm_launch_count(void) { return g_seqm_launches; }
+
+/* measured FP64 FMA peak of the device in TFLOP/s (all SMs, 8 chains/thread); blocks the host */
+double seqm_fp64_peak_tflops(void) {
+#ifndef SEQM_HOSTEMU
+  if (ensure_device()) return -1.0;
+  double* d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return -1.0;
+  const int iters = 20000, block = 256, grid = g_num_sms * 8;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    fp64_peak_kernel<<<grid, block>>>(d, iters);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8.0 * iters * (double)block * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return best;
+#else
+  return 0.0;
+#endif
+}
 
 int seqm_profile_enable(int on) {
   g_prof_on = on;

@@ -21,7 +21,9 @@
 #define SEQM_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char seqm_dyn_smem_[];   \
   type* name = reinterpret_cast<type*>(seqm_dyn_smem_)
-#define SEQM_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+extern long long g_seqm_launches;
+#define SEQM_LAUNCH(kern, grid, block, smem, stream, ...) \
+  do { ++g_seqm_launches; kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__); } while (0)
 #define SEQM_SYNC() __syncthreads()
 SEQM_D int seqm_sync_or(int p) { return __syncthreads_or(p); }
 SEQM_D double seqm_rsqrt(double x) { return rsqrt(x); }
@@ -42,8 +44,10 @@ void seqm_hostemu_ensure_smem(size_t bytes);
 #define __restrict__
 #define __shared__ static
 #define SEQM_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(seqm_hostemu_smem)
+extern long long g_seqm_launches;
 #define SEQM_LAUNCH(kern, grid, block, smem, stream, ...)              \
   do {                                                                 \
+    ++g_seqm_launches;                                                 \
     seqm_hostemu_ensure_smem((size_t)(smem) + 64);                     \
     unsigned g_ = (unsigned)(grid);                                    \
     gridDim = {g_, 1, 1};                                              \

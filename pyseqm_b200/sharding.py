@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing: molecules (and MD replicas) are independent units, so a batch is dealt to the ranks
+of one node and nothing is exchanged inside the SCF; the only collective gathers per-molecule results
+(SURVEY 8(e)).  One process per GPU, torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(cost, world_size, rank):
+    """Deal molecules to ranks round-robin in order of decreasing cost (~ n_orbitals^3) so that every GPU
+    gets the same size mix.  Returns the sorted global indices owned by `rank`."""
+    order = torch.argsort(torch.as_tensor(cost), descending=True, stable=True)
+    mine = order[rank::world_size]
+    return torch.sort(mine).values
+
+
+def gather_results(local, index, nmol_total, group=None):
+    """all_gather per-molecule tensors (first dim = local molecules) back into global molecule order.
+    `local`: dict name -> tensor; `index`: global indices of the local molecules."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return {k: v for k, v in local.items()}
+    ws = dist.get_world_size(group)
+    dev = index.device
+    n_local = torch.tensor([index.shape[0]], device=dev, dtype=torch.int64)
+    counts = [torch.zeros_like(n_local) for _ in range(ws)]
+    dist.all_gather(counts, n_local, group=group)
+    nmax = int(max(int(c) for c in counts))
+    pad_idx = torch.full((nmax,), -1, device=dev, dtype=torch.int64)
+    pad_idx[: index.shape[0]] = index
+    all_idx = [torch.empty_like(pad_idx) for _ in range(ws)]
+    dist.all_gather(all_idx, pad_idx, group=group)
+    out = {}
+    for k, v in local.items():
+        buf = torch.zeros((nmax,) + tuple(v.shape[1:]), device=dev, dtype=v.dtype)
+        buf[: v.shape[0]] = v
+        parts = [torch.empty_like(buf) for _ in range(ws)]
+        dist.all_gather(parts, buf, group=group)
+        full = torch.zeros((nmol_total,) + tuple(v.shape[1:]), device=dev, dtype=v.dtype)
+        for r in range(ws):
+            c = int(counts[r])
+            full[all_idx[r][:c]] = parts[r][:c]
+        out[k] = full
+    return out
+
+
+def run_sharded(species, coordinates, seqm_parameters, const, make_molecule, make_driver, group=None):
+    """Shard a global batch over the ranks, run the drop-in forward on the local shard, gather
+    Etot / Hf / force / notconverged in global order.  Iteration counts are per shard (the reference's DIIS
+    reset is a batch-global decision)."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nheavy = (species > 1).sum(dim=1)
+    nhyd = (species == 1).sum(dim=1)
+    cost = (4 * nheavy + nhyd).to(torch.float64) ** 3
+    idx = shard_indices(cost.cpu(), ws, rank).to(species.device)
+    mol = make_molecule(const, dict(seqm_parameters), coordinates[idx].contiguous(), species[idx].contiguous())
+    drv = make_driver(dict(seqm_parameters))
+    drv(mol)
+    local = dict(Etot=mol.Etot, Hf=mol.Hf, force=mol.force, notconverged=drv.notconverged.to(torch.int32))
+    out = gather_results(local, idx, species.shape[0], group)
+    out["n_scf_iter_local"] = mol.n_scf_iter
+    return out
