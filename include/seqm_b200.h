@@ -59,6 +59,11 @@ typedef struct seqm_batch {
   const int32_t* pair_i;    /* [npairs] global real-atom index of the first atom */
   const int32_t* pair_j;    /* [npairs] */
   double* atom_par;         /* [SEQM_NPAR * nat] */
+  /* HOST arrays: eigensolver size classes.  Class c holds the molecules with n <= 2*np_c orbitals
+   * (np_c = 4,8,...,32,40,48,56,60) that do not fit class c-1; they occupy the contiguous range
+   * mol_order[cls_begin[c] .. cls_begin[c]+cls_count[c]) because mol_order is sorted by descending n. */
+  int32_t cls_begin[12];
+  int32_t cls_count[12];
 } seqm_batch_t;
 
 int seqm_abi_version(void);
@@ -131,6 +136,8 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
  * per kernel kind (seqm_profile_kinds() entries, names from seqm_profile_name()). */
 /* number of kernel launches issued by this library since load (bench.py gpu_launches) */
 long long seqm_launch_count(void);
+/* eigensolver statistics since the last reset: out[0] molecules solved, out[1] Jacobi sweeps, out[2] rotation steps */
+int seqm_jacobi_stats(unsigned long long* out, int reset);
 /* measured FP64 FMA peak (TFLOP/s) of the current device: roofline denominator of the FP64-bound kernels */
 double seqm_fp64_peak_tflops(void);
 int seqm_profile_enable(int on);

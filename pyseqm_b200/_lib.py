@@ -32,8 +32,10 @@ class SeqmBatchStruct(C.Structure):
         ("mol_atom0", C.c_void_p), ("mol_pair0", C.c_void_p), ("mol_mat0", C.c_void_p),
         ("mol_nheavy", C.c_void_p), ("mol_nhyd", C.c_void_p), ("mol_nocc", C.c_void_p), ("mol_order", C.c_void_p),
         ("atom_Z", C.c_void_p), ("atom_mol", C.c_void_p), ("pair_i", C.c_void_p), ("pair_j", C.c_void_p),
-        ("atom_par", C.c_void_p),
+        ("atom_par", C.c_void_p), ("cls_begin", C.c_int32 * 12), ("cls_count", C.c_int32 * 12),
     ]  # fmt: skip
+
+JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 60)
 
 
 class SeqmScfOpts(C.Structure):
@@ -92,6 +94,7 @@ class SeqmLib:
             "seqm_scf": ([B, O, P, P, P, P, P, P, P, C.POINTER(C.c_int32), P], C.c_int),
             "seqm_launch_count": ([], C.c_longlong),
             "seqm_fp64_peak_tflops": ([], C.c_double),
+            "seqm_jacobi_stats": ([C.POINTER(C.c_ulonglong), C.c_int], C.c_int),
             "seqm_profile_enable": ([C.c_int], C.c_int),
             "seqm_profile_kinds": ([], C.c_int),
             "seqm_profile_name": ([C.c_int], C.c_char_p),
@@ -104,6 +107,11 @@ class SeqmLib:
         self.symbols = list(sig)
         if self.dll.seqm_abi_version() != 1:
             raise SeqmError("libseqm_b200 ABI version mismatch")
+
+    def jacobi_stats(self, reset=True):
+        out = (C.c_ulonglong * 4)()
+        self.check(self.dll.seqm_jacobi_stats(out, 1 if reset else 0), "seqm_jacobi_stats")
+        return {"molecules": out[0], "sweeps": out[1], "rotation_steps": out[2]}
 
     def profile_enable(self, on=True):
         self.dll.seqm_profile_enable(1 if on else 0)

@@ -10,193 +10,294 @@
 #pragma once
 #include "common.cuh"
 
-#define SEQM_JACOBI_MAX_SWEEPS 40
-
-// circle-method pairing: round s of m-1, pair k of m/2  (m even)
-SEQM_HD void rr_pair(int m, int s, int k, int& p, int& q) {
-  if (k == 0) {
-    p = m - 1;
-    q = s;
-  } else {
-    p = (s + k) % (m - 1);
-    q = (s - k + (m - 1)) % (m - 1);
-  }
-  if (p > q) { int t = p; p = q; q = t; }
+#define SEQM_JACOBI_MAX_SWEEPS 60
+// debug/statistics counters: [0] molecules solved, [1] sweeps, [2] steps with at least one rotation
+#ifndef SEQM_HOSTEMU
+__device__ unsigned long long g_jacobi_stats[4];
+#else
+static unsigned long long g_jacobi_stats[4];
+#endif
+SEQM_D void stat_add(int k, unsigned long long v) {
+#ifndef SEQM_HOSTEMU
+  atomicAdd(&g_jacobi_stats[k], v);
+#else
+  g_jacobi_stats[k] += v;
+#endif
 }
 
-// shared layout: A[n*n] | V[n*n] | cs[2*(m/2)] | scratch
-SEQM_GLOBAL void jacobi_density_kernel(seqm_batch_t b, const double* __restrict__ F, double* __restrict__ Pout,
-                                       double* __restrict__ evals, double* __restrict__ Cout,
-                                       const double* __restrict__ Cguess, const int32_t* __restrict__ active) {
-  const int mol = b.mol_order[blockIdx.x];
+struct alignas(16) seqm_d2 { double x, y; };
+
+// ---------------------------------------------------------------------------------------------------
+// Two-sided Jacobi on m = 2*NP FIXED slots (Brent-Luk odd-even ordering): even steps pair (0,1)(2,3)...,
+// odd steps pair (1,2)(3,4)...(m-1,0); every rotation is followed by a swap of the two slots, so after m
+// steps every pair has met exactly once.  Static positions mean no index tables, no integer division by
+// runtime values and compile-time register indices:
+//   * A lives in shared memory in two column planes (even columns | odd columns, row stride LD padded so
+//     that the row segments touched by one warp fall in disjoint banks): every access of both the even and
+//     the odd step is a conflict-free 64-bit access with unit lane stride.
+//   * V never touches shared memory during the sweeps: thread (row i, quarter s) keeps m/4 consecutive
+//     entries of row i in registers; the one pair that straddles two quarters in odd steps is exchanged with
+//     two 64-bit shuffles inside the 4-lane group.
+//   * per pair l the transform is x' = a x + b y, y' = b x - a y with (a,b) = (sin, cos) [rotate + swap],
+//     (0,1) [swap only, |a_pq| below threshold] or (1,0) for the wrap pair (m-1,0) of odd steps (identity up
+//     to the sign of slot 0, which is irrelevant for an eigenbasis).
+// Slots n..m-1 are decoupled dummies whose diagonal lies above the Gershgorin bound; they rank last.
+// blockDim.x must be 4*m (V ownership); tiles are strided over all threads.
+// shared: A[m*LD] | cs[NP] (double2) | scr[40] | dg[m] | perm[m] (int)
+// ---------------------------------------------------------------------------------------------------
+template <int NP>
+struct JacobiCfg {
+  static constexpr int M = 2 * NP;
+  static constexpr int LD = M + ((NP / 2) % 8);
+  static constexpr int SEG = NP / 2;  // V entries per thread (4 threads per row)
+  static constexpr int THREADS = 4 * M;
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)M * LD + 2 * NP + 40 + M) + sizeof(int) * (M + 4);
+};
+
+// element (r, c) of the plane-split matrix
+#define SEQM_AIDX(r, c) ((r) * LD + (((c) & 1) ? NP : 0) + ((c) >> 1))
+
+template <int NP>
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
+                                     double* __restrict__ evals, double* __restrict__ Cout,
+                                     const double* __restrict__ Cguess, const int32_t* __restrict__ active) {
+  typedef JacobiCfg<NP> K;
+  constexpr int M = K::M, LD = K::LD, SEG = K::SEG;
+  const int mol = b.mol_order[first + blockIdx.x];
   if (active && !active[mol]) return;
   const MolView v = mol_view(b, mol);
   const int n = v.n;
-  const int m = (n + 1) & ~1;  // even number of tournament slots; slot n (if any) is a bye
-  const int np = m / 2;
   SEQM_DYN_SMEM(double, sm);
   double* A = sm;
-  double* V = A + n * n;
-  double* cs = V + n * n;      // c[k], s[k]
-  double* scr = cs + 2 * np;   // 40 doubles of scratch
-  int* perm = reinterpret_cast<int*>(scr + 40);  // n ints
+  seqm_d2* cs = reinterpret_cast<seqm_d2*>(A + M * LD);
+  double* scr = reinterpret_cast<double*>(cs + NP);
+  double* dg = scr + 40;
+  int* perm = reinterpret_cast<int*>(dg + M);
   const double* Fm = F + v.mat0;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const bool warm = (Cguess != nullptr);
+#ifndef SEQM_HOSTEMU
+  double vr[SEG];  // V[row][seg*SEG .. seg*SEG+SEG-1]
+  const int vrow = tid >> 2, vseg = tid & 3;
+#else
+  static double Vh[128 * 128];  // host emulation keeps V in memory (one "thread" plays all owners)
+#endif
 
-  if (Cguess) {
-    // warm start: V = C0, A = C0^t F C0 (A used as scratch for T = F C0 first would need a third matrix;
-    // instead form A column block by column block through global F, which is L1/L2 resident)
+  if (warm) {
+    // V = C0 ; A = C0^t F C0 through two global scratch slots (the caller's P and C slots, L2 resident)
     const double* C0 = Cguess + v.mat0;
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) V[t] = C0[t];
-    SEQM_SYNC();
-    // T = F V  -> A
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-      const int i = t / n, j = t % n;
-      double s = 0.0;
-      for (int k = 0; k < n; ++k) s += Fm[i * n + k] * V[k * n + j];
-      A[t] = s;
-    }
-    SEQM_SYNC();
-    // A <- V^t T, done in place row-block-wise is not possible; use Pout's global slot as scratch
     double* G = Pout + v.mat0;
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-      const int i = t / n, j = t % n;
-      double s = 0.0;
-      for (int k = 0; k < n; ++k) s += V[k * n + i] * A[k * n + j];
-      G[t] = s;
+    double* G2 = Cout + v.mat0;
+    double* S = A;  // C0 staged in shared memory, standard layout, row stride n
+    for (int t = tid; t < n * n; t += nthr) S[t] = C0[t];
+    SEQM_SYNC();
+    for (int t = tid; t < n * n; t += nthr) {
+      const int i = t / n, j = t - i * n;
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += Fm[i * n + k] * S[k * n + j];
+      G[t] = acc;  // T = F C0
+    }
+#ifndef SEQM_HOSTEMU
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) {
+      const int c = vseg * SEG + e;
+      vr[e] = (vrow < n && c < n) ? S[vrow * n + c] : ((vrow == c) ? 1.0 : 0.0);
+    }
+#else
+    for (int i = 0; i < M; ++i)
+      for (int c = 0; c < M; ++c) Vh[i * M + c] = (i < n && c < n) ? S[i * n + c] : ((i == c) ? 1.0 : 0.0);
+#endif
+    SEQM_SYNC();
+    for (int t = tid; t < n * n; t += nthr) {
+      const int i = t / n, j = t - i * n;
+      if (j < i) continue;
+      double acc = 0.0;
+      for (int k = 0; k < n; ++k) acc += S[k * n + i] * G[k * n + j];
+      G2[t] = acc;  // upper triangle of C0^t T
     }
     SEQM_SYNC();
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-      const int i = t / n, j = t % n;
-      A[t] = 0.5 * (G[t] + G[j * n + i]);
+    for (int t = tid; t < M * M; t += nthr) {
+      const int i = t / M, j = t - i * M;
+      double a = 0.0;
+      if (i < n && j < n) a = (j >= i) ? G2[i * n + j] : G2[j * n + i];
+      A[SEQM_AIDX(i, j)] = a;
     }
   } else {
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-      A[t] = Fm[t];
-      V[t] = ((t / n) == (t % n)) ? 1.0 : 0.0;
+    for (int t = tid; t < M * M; t += nthr) {
+      const int i = t / M, j = t - i * M;
+      A[SEQM_AIDX(i, j)] = (i < n && j < n) ? Fm[i * n + j] : 0.0;
     }
+#ifndef SEQM_HOSTEMU
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) vr[e] = (vrow == vseg * SEG + e) ? 1.0 : 0.0;
+#else
+    for (int i = 0; i < M; ++i)
+      for (int c = 0; c < M; ++c) Vh[i * M + c] = (i == c) ? 1.0 : 0.0;
+#endif
   }
   SEQM_SYNC();
-
-  // scale for the convergence test
   double dmax = 0.0;
-  for (int t = threadIdx.x; t < n * n; t += blockDim.x) dmax = fmax(dmax, fabs(A[t]));
+  for (int t = tid; t < M * LD; t += nthr) {
+    const int c = t % LD;
+    if (c < M) dmax = fmax(dmax, fabs(A[t]));
+  }
   dmax = block_max(dmax, scr);
-  const double tol = 1.0e-15 * fmax(dmax, 1.0e-300);
+  const double tol = 1.0e-14 * fmax(dmax, 1.0e-300);
+  for (int d = n + tid; d < M; d += nthr) A[SEQM_AIDX(d, d)] = (d + 2.0) * dmax + 1.0 + d;  // dummies above the spectrum
+  SEQM_SYNC();
 
+  int nsweep = 0, nsteps = 0;
   for (int sweep = 0; sweep < SEQM_JACOBI_MAX_SWEEPS; ++sweep) {
     int rotated = 0;
-    for (int s = 0; s < m - 1; ++s) {
-      // rotation parameters for the np disjoint pairs
+    ++nsweep;
+    for (int step = 0; step < M; ++step) {
+      const int ph = step & 1;
       int any = 0;
-      for (int k = threadIdx.x; k < np; k += blockDim.x) {
-        int p, q;
-        rr_pair(m, s, k, p, q);
-        double c = 1.0, sn = 0.0;
-        if (q < n) {
-          const double apq = A[p * n + q];
+      for (int k = tid; k < NP; k += nthr) {
+        seqm_d2 ab;
+        ab.x = 0.0;
+        ab.y = 1.0;  // swap only
+        if (ph && k == NP - 1) {
+          ab.x = 1.0;
+          ab.y = 0.0;  // wrap pair (m-1, 0)
+        } else {
+          const int p = 2 * k + ph, q = p + 1;
+          const double apq = A[SEQM_AIDX(p, q)];
           if (fabs(apq) > tol) {
-            const double app = A[p * n + p], aqq = A[q * n + q];
-            const double tau = (aqq - app) / (2.0 * apq);
-            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-            c = 1.0 / sqrt(1.0 + t * t);
-            sn = t * c;
+            // rotation with |theta| <= pi/4 from two reciprocal square roots (no division on the critical
+            // path): cos 2t = |d|/h, sin 2t = sgn(d) 2 a_pq / h, c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c)
+            const double d = A[SEQM_AIDX(q, q)] - A[SEQM_AIDX(p, p)], b2 = 2.0 * apq;
+            const double rh = seqm_rsqrt(d * d + b2 * b2);
+            const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+            const double ic = seqm_rsqrt(c2);
+            ab.y = c2 * ic;                                             // cos
+            ab.x = (d >= 0.0 ? 0.5 : -0.5) * b2 * rh * ic;              // sin
             any = 1;
           }
         }
-        cs[2 * k] = c;
-        cs[2 * k + 1] = sn;
+        cs[k] = ab;
       }
       any = seqm_sync_or(any);
-      if (!any) continue;
-      rotated = 1;
-      // A <- J^t A J : tile (k,l) = rows {pk,qk} x cols {pl,ql}
-      for (int t = threadIdx.x; t < np * np; t += blockDim.x) {
-        const int k = t / np, l = t % np;
-        int pk, qk, pl, ql;
-        rr_pair(m, s, k, pk, qk);
-        rr_pair(m, s, l, pl, ql);
-        if (qk >= n || ql >= n) {
-          // a bye slot: only the real row/column of the other pair rotates
-          if (qk >= n && ql >= n) continue;
-          if (qk >= n) {  // row pk untouched by rows; rotate its columns pl,ql
-            const double c = cs[2 * l], sn = cs[2 * l + 1];
-            const double x = A[pk * n + pl], y = A[pk * n + ql];
-            A[pk * n + pl] = c * x - sn * y;
-            A[pk * n + ql] = sn * x + c * y;
-          } else {  // column pl untouched by columns; rotate rows pk,qk
-            const double c = cs[2 * k], sn = cs[2 * k + 1];
-            const double x = A[pk * n + pl], y = A[qk * n + pl];
-            A[pk * n + pl] = c * x - sn * y;
-            A[qk * n + pl] = sn * x + c * y;
-          }
-          continue;
+      rotated |= any;
+      nsteps += any;
+      // ---- A <- M_k^t A M_l on the NP x NP tiles
+      for (int t = tid; t < NP * NP; t += nthr) {
+        const int k = t / NP, l = t - k * NP;
+        const seqm_d2 ck = cs[k], cl = cs[l];
+        int r0, r1, ix, iy;
+        if (!ph) {
+          r0 = (2 * k) * LD;
+          r1 = r0 + LD;
+          ix = l;
+          iy = NP + l;
+        } else {
+          r0 = (2 * k + 1) * LD;
+          r1 = (k == NP - 1) ? 0 : r0 + LD;
+          ix = NP + l;
+          iy = (l == NP - 1) ? 0 : l + 1;
         }
-        const double ck = cs[2 * k], sk = cs[2 * k + 1], cl = cs[2 * l], sl = cs[2 * l + 1];
-        const double a00 = A[pk * n + pl], a01 = A[pk * n + ql], a10 = A[qk * n + pl], a11 = A[qk * n + ql];
-        // columns: [x y] -> [c x - s y, s x + c y]
-        const double b00 = cl * a00 - sl * a01, b01 = sl * a00 + cl * a01;
-        const double b10 = cl * a10 - sl * a11, b11 = sl * a10 + cl * a11;
-        // rows
-        A[pk * n + pl] = ck * b00 - sk * b10;
-        A[qk * n + pl] = sk * b00 + ck * b10;
-        A[pk * n + ql] = ck * b01 - sk * b11;
-        A[qk * n + ql] = sk * b01 + ck * b11;
+        const double x0 = A[r0 + ix], y0 = A[r0 + iy], x1 = A[r1 + ix], y1 = A[r1 + iy];
+        const double bx0 = cl.x * x0 + cl.y * y0, by0 = cl.y * x0 - cl.x * y0;
+        const double bx1 = cl.x * x1 + cl.y * y1, by1 = cl.y * x1 - cl.x * y1;
+        A[r0 + ix] = ck.x * bx0 + ck.y * bx1;
+        A[r1 + ix] = ck.y * bx0 - ck.x * bx1;
+        A[r0 + iy] = ck.x * by0 + ck.y * by1;
+        A[r1 + iy] = ck.y * by0 - ck.x * by1;
       }
-      // V <- V J
-      for (int t = threadIdx.x; t < n * np; t += blockDim.x) {
-        const int i = t / np, l = t % np;
-        int pl, ql;
-        rr_pair(m, s, l, pl, ql);
-        if (ql >= n) continue;
-        const double c = cs[2 * l], sn = cs[2 * l + 1];
-        const double x = V[i * n + pl], y = V[i * n + ql];
-        V[i * n + pl] = c * x - sn * y;
-        V[i * n + ql] = sn * x + c * y;
+      // ---- V <- V M
+#ifndef SEQM_HOSTEMU
+      if (!ph) {
+#pragma unroll
+        for (int j = 0; j < SEG / 2; ++j) {
+          const seqm_d2 c = cs[vseg * (SEG / 2) + j];
+          const double x = vr[2 * j], y = vr[2 * j + 1];
+          vr[2 * j] = c.x * x + c.y * y;
+          vr[2 * j + 1] = c.y * x - c.x * y;
+        }
+      } else {
+        const int lane = tid & 31;
+        const double first_old = vr[0], last_old = vr[SEG - 1];
+        const double y_next = __shfl_sync(0xffffffffu, first_old, (lane & ~3) | ((lane + 1) & 3));
+        const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~3) | ((lane + 3) & 3));
+#pragma unroll
+        for (int j = 0; j < SEG / 2 - 1; ++j) {
+          const seqm_d2 c = cs[vseg * (SEG / 2) + j];
+          const double x = vr[2 * j + 1], y = vr[2 * j + 2];
+          vr[2 * j + 1] = c.x * x + c.y * y;
+          vr[2 * j + 2] = c.y * x - c.x * y;
+        }
+        const seqm_d2 cn = cs[vseg * (SEG / 2) + SEG / 2 - 1];            // pair (my last, next quarter's first)
+        const seqm_d2 cp = cs[(vseg * (SEG / 2) + NP - 1) % NP];          // pair (previous quarter's last, my first)
+        vr[SEG - 1] = cn.x * last_old + cn.y * y_next;
+        vr[0] = cp.y * x_prev - cp.x * first_old;
       }
+#else
+      for (int i = 0; i < M; ++i)
+        for (int l = 0; l < NP; ++l) {
+          const int p = 2 * l + ph, q = (p + 1) % M;
+          const double x = Vh[i * M + p], y = Vh[i * M + q];
+          Vh[i * M + p] = cs[l].x * x + cs[l].y * y;
+          Vh[i * M + q] = cs[l].y * x - cs[l].x * y;
+        }
+#endif
       SEQM_SYNC();
     }
     if (!rotated) break;
   }
-
-  // rank eigenvalues (ascending, ties by index): perm[rank] = column
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double ei = A[i * n + i];
+  if (tid == 0) {
+    stat_add(0, 1);
+    stat_add(1, nsweep);
+    stat_add(2, nsteps);
+  }
+  // eigenvalues -> dg, then reuse the A storage for V in standard layout (row stride M)
+  for (int i = tid; i < M; i += nthr) dg[i] = A[SEQM_AIDX(i, i)];
+  SEQM_SYNC();
+  double* V = A;
+#ifndef SEQM_HOSTEMU
+#pragma unroll
+  for (int e = 0; e < SEG; ++e) V[vrow * M + vseg * SEG + e] = vr[e];
+#else
+  for (int t = 0; t < M * M; ++t) V[t] = Vh[t];
+#endif
+  for (int i = tid; i < M; i += nthr) {
+    const double ei = dg[i];
     int r = 0;
-    for (int j = 0; j < n; ++j) {
-      const double ej = A[j * n + j];
-      r += (ej < ei) || (ej == ei && j < i);
-    }
+    for (int j = 0; j < M; ++j) r += (dg[j] < ei) || (dg[j] == ei && j < i);
     perm[r] = i;
   }
   SEQM_SYNC();
-  if (evals) {
-    for (int r = threadIdx.x; r < b.nmax; r += blockDim.x)
-      evals[(long long)mol * b.nmax + r] = (r < n) ? A[perm[r] * n + perm[r]] : 0.0;
-  }
+  if (evals)
+    for (int r = tid; r < b.nmax; r += nthr) evals[(long long)mol * b.nmax + r] = (r < n) ? dg[perm[r]] : 0.0;
   if (Cout) {
     double* Cm = Cout + v.mat0;
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) Cm[t] = V[(t / n) * n + perm[t % n]];
+    for (int t = tid; t < n * n; t += nthr) Cm[t] = V[(t / n) * M + perm[t % n]];
   }
   if (Pout) {
     double* Pm = Pout + v.mat0;
     const int nocc = v.nocc;
-    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
-      const int i = t / n, j = t % n;
+    for (int t = tid; t < n * n; t += nthr) {
+      const int i = t / n, j = t - i * n;
       if (j < i) continue;
-      double s = 0.0;
+      double acc = 0.0;
       for (int r = 0; r < nocc; ++r) {
         const int c = perm[r];
-        s += V[i * n + c] * V[j * n + c];
+        acc += V[i * M + c] * V[j * M + c];
       }
-      s *= 2.0;
-      Pm[i * n + j] = s;
-      Pm[j * n + i] = s;
+      acc *= 2.0;
+      Pm[i * n + j] = acc;
+      Pm[j * n + i] = acc;
     }
   }
 }
-static inline size_t jacobi_smem_bytes(int n) {
-  const int m = (n + 1) & ~1;
-  return sizeof(double) * ((size_t)2 * n * n + m + 40) + sizeof(int) * (n + 2);
+
+// size classes: a molecule with n orbitals runs in the smallest NP with 2*NP >= n
+#define SEQM_JACOBI_CLASSES(X) X(4) X(8) X(12) X(16) X(20) X(24) X(28) X(32) X(40) X(48) X(56) X(60)
+static const int g_jacobi_np[] = {4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 60};
+static const int g_jacobi_ncls = 12;
+static inline int jacobi_class_of(int n) {
+  for (int c = 0; c < g_jacobi_ncls; ++c)
+    if (2 * g_jacobi_np[c] >= n) return c;
+  return -1;
 }
 
 // SP2 purification of one molecule per CTA: X and X^2 in shared memory.

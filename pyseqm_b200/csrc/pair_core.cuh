@@ -233,10 +233,14 @@ SEQM_HD int pack_class(int kl) { return (kl == 0) ? 0 : ((kl == 1 || kl == 3 || 
 // ncolA / ncolB: 1 for a hydrogen (only the ss product exists), 10 for a heavy atom.
 template <class T>
 SEQM_HD void rotate_to_molecular(const T* ri, int nint, const T Tm[10][10], T w[10][10]) {
+  const int nB = (nint == 22) ? 10 : 1, nA = (nint == 1) ? 1 : 10;
+  if (nint == 1) {  // H-H: (ss|ss) is rotation invariant
+    w[0][0] = ri[0];
+    return;
+  }
   T U[10][10];  // U[KL][mn] = sum_MN L[KL][MN] T[MN][mn]
   for (int i = 0; i < 10; ++i)
-    for (int j = 0; j < 10; ++j) { U[i][j] = T(0.0); w[i][j] = T(0.0); }
-  const int nB = (nint == 22) ? 10 : 1, nA = (nint == 1) ? 1 : 10;
+    for (int j = 0; j < nB; ++j) { U[i][j] = T(0.0); w[i][j] = T(0.0); }
   for (int e = 0; e < SEQM_NL; ++e) {
     const LEntry le = l_entry(e);
     if (le.k >= nint || le.mn >= nB) continue;

@@ -69,12 +69,17 @@ SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<Dual3>& g) {
 }
 
 // w of one pair in the molecular frame (only the entries that exist for the pair class are non-zero)
+// Only the entries that exist for the pair class are written: [0][0] (H-H), [0..9][0] (X-H), all (X-X).
 template <class T>
 SEQM_HD void pair_w(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T w[10][10]) {
   const bool hi = b.atom_Z[i] > 1, hj = b.atom_Z[j] > 1;
   const int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
   T ri[22];
   local_integrals(g.r, load_multipole(b, i), load_multipole(b, j), nint, ri);
+  if (nint == 1) {
+    w[0][0] = ri[0];
+    return;
+  }
   T v[3] = {-g.e[0], -g.e[1], -g.e[2]};
   T rot[3][3];
   rotation_rows(v, rot);
@@ -98,9 +103,10 @@ SEQM_GLOBAL void pair_integrals_kernel(seqm_batch_t b, const double* __restrict_
     pair_geom(xyz, i, j, g);
     double wl[10][10];
     pair_w(b, i, j, g, wl);
+    const int nA = (b.atom_Z[i] > 1) ? 10 : 1, nB = (b.atom_Z[j] > 1) ? 10 : 1;
     double* wp = w + (long long)p * 100;
     for (int k = 0; k < 10; ++k)
-      for (int l = 0; l < 10; ++l) wp[k * 10 + l] = wl[k][l];
+      for (int l = 0; l < 10; ++l) wp[k * 10 + l] = (k < nA && l < nB) ? wl[k][l] : 0.0;
     double S[4][4];
     pair_overlap(b, i, j, g, S);
     const double bsi = par(b, SEQM_P_BS, i), bpi = par(b, SEQM_P_BP, i);

@@ -139,20 +139,45 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
   if (threadIdx.x == 0) W.diis_err[mol] = rmax;
 }
 
-// cyclic Jacobi for a tiny dense symmetric matrix held by one thread (lower triangle is authoritative)
-SEQM_D void small_eigh(int n, double* A /* n*n, symmetrised in place */, double* Q /* n*n */) {
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < n; ++j) {
-      if (j > i) A[i * n + j] = A[j * n + i];
-      Q[i * n + j] = (i == j) ? 1.0 : 0.0;
-    }
+#ifndef SEQM_HOSTEMU
+#define SEQM_SYNCWARP() __syncwarp()
+#else
+#define SEQM_SYNCWARP() do { } while (0)
+#endif
+#define SEQM_DIIS_WARPS 4
+
+// DIIS step 2 (scf_loop.py:1009-1031): pseudo-inverse solve of the (cF+1)x(cF+1) Pulay system, one WARP per
+// molecule (lanes own rows/columns of the tiny matrix in shared memory; cyclic Jacobi, the lower triangle of
+// EMAT is authoritative exactly as torch.linalg.eigh(UPLO='L') reads it), condition-number reset flag.
+SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int cF) {
+  __shared__ double sA[SEQM_DIIS_WARPS][SEQM_EM * SEQM_EM];
+  __shared__ double sQ[SEQM_DIIS_WARPS][SEQM_EM * SEQM_EM];
+  const int L = (blockDim.x >= 32) ? 32 : 1;
+  const int lane = threadIdx.x % L, wib = threadIdx.x / L, wpb = blockDim.x / L;
+  const int mol = blockIdx.x * wpb + wib;
+  if (mol >= b.nmol || !W.active[mol]) return;
+  const int n = cF + 1;
+  double* A = sA[wib];
+  double* Q = sQ[wib];
+  const double* E = W.EMAT + (long long)mol * SEQM_EM * SEQM_EM;
+  double denom = E[counter * SEQM_EM + counter];
+  if (denom < 1.0e-15) denom = 1.0e-15;
+  for (int t = lane; t < n * n; t += L) {
+    const int i = t / n, j = t % n;
+    const int r = (i >= j) ? i : j, c = (i >= j) ? j : i;  // read the lower triangle only
+    double e = E[r * SEQM_EM + c];
+    if (r < cF && c < cF) e /= denom;
+    A[t] = e;
+    Q[t] = (i == j) ? 1.0 : 0.0;
+  }
+  SEQM_SYNCWARP();
   for (int sweep = 0; sweep < 60; ++sweep) {
     double off = 0.0, dg = 0.0;
     for (int i = 0; i < n; ++i) {
       dg = fmax(dg, fabs(A[i * n + i]));
       for (int j = 0; j < i; ++j) off = fmax(off, fabs(A[i * n + j]));
     }
-    if (off <= 1.0e-18 * dg || off == 0.0) break;
+    if (off <= 2.0e-16 * dg || off == 0.0) break;  // at the rounding floor; identical in every lane
     for (int p = 0; p < n - 1; ++p)
       for (int q = p + 1; q < n; ++q) {
         const double apq = A[p * n + q];
@@ -160,56 +185,39 @@ SEQM_D void small_eigh(int n, double* A /* n*n, symmetrised in place */, double*
         const double tau = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
         const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-        for (int k = 0; k < n; ++k) {
+        SEQM_SYNCWARP();
+        for (int k = lane; k < n; k += L) {  // columns p,q of A and Q
           const double x = A[k * n + p], y = A[k * n + q];
           A[k * n + p] = c * x - s * y;
           A[k * n + q] = s * x + c * y;
+          const double u = Q[k * n + p], w2 = Q[k * n + q];
+          Q[k * n + p] = c * u - s * w2;
+          Q[k * n + q] = s * u + c * w2;
         }
-        for (int k = 0; k < n; ++k) {
+        SEQM_SYNCWARP();
+        for (int k = lane; k < n; k += L) {  // rows p,q of A
           const double x = A[p * n + k], y = A[q * n + k];
           A[p * n + k] = c * x - s * y;
           A[q * n + k] = s * x + c * y;
         }
-        for (int k = 0; k < n; ++k) {
-          const double x = Q[k * n + p], y = Q[k * n + q];
-          Q[k * n + p] = c * x - s * y;
-          Q[k * n + q] = s * x + c * y;
-        }
+        SEQM_SYNCWARP();
       }
   }
-}
-
-// DIIS step 2 (scf_loop.py:1009-1031): pseudo-inverse solve per molecule, condition-number reset flag.
-SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int cF) {
-  for (int mol = blockIdx.x * blockDim.x + threadIdx.x; mol < b.nmol; mol += gridDim.x * blockDim.x) {
-    if (!W.active[mol]) continue;
-    const int n = cF + 1;
-    double A[SEQM_EM * SEQM_EM], Q[SEQM_EM * SEQM_EM];
-    const double* E = W.EMAT + (long long)mol * SEQM_EM * SEQM_EM;
-    double denom = E[counter * SEQM_EM + counter];
-    if (denom < 1.0e-15) denom = 1.0e-15;
-    for (int i = 0; i < n; ++i)
-      for (int j = 0; j <= i; ++j) {
-        double e = E[i * SEQM_EM + j];
-        if (i < cF && j < cF) e /= denom;
-        A[i * n + j] = e;
-      }
-    small_eigh(n, A, Q);
-    double amax = 0.0, amin = 1.0e300;
+  SEQM_SYNCWARP();
+  double amax = 0.0, amin = 1.0e300;
+  for (int i = 0; i < n; ++i) {
+    const double a = fabs(A[i * n + i]);
+    amax = fmax(amax, a);
+    amin = fmin(amin, a);
+  }
+  if (lane == 0 && amax / amin > 1.0e7) seqm_atomic_or(&W.ctrl->reset, 1);
+  for (int k = lane; k < cF; k += L) {
+    double s = 0.0;
     for (int i = 0; i < n; ++i) {
-      const double a = fabs(A[i * n + i]);
-      amax = fmax(amax, a);
-      amin = fmin(amin, a);
+      const double l = A[i * n + i];
+      if (fabs(l) > 1.0e-13) s += Q[k * n + i] * Q[(n - 1) * n + i] / l;
     }
-    if (amax / amin > 1.0e7) seqm_atomic_or(&W.ctrl->reset, 1);
-    for (int k = 0; k < cF; ++k) {
-      double s = 0.0;
-      for (int i = 0; i < n; ++i) {
-        const double l = A[i * n + i];
-        if (fabs(l) > 1.0e-13) s += Q[k * n + i] * Q[(n - 1) * n + i] / l;
-      }
-      W.coeff[(long long)mol * SEQM_NFOCK + k] = -s;
-    }
+    W.coeff[(long long)mol * SEQM_NFOCK + k] = -s;
   }
 }
 

@@ -58,7 +58,12 @@ static int ensure_device() {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int dyn = g_smem_optin - 2048;  // leave room for the kernels' small static shared arrays
-  e = cudaFuncSetAttribute(jacobi_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  e = cudaSuccess;
+#define SEQM_ATTR(NPV)                                                                                                 \
+  if (e == cudaSuccess && JacobiCfg<NPV>::SMEM > 48 * 1024)                                                             \
+    e = cudaFuncSetAttribute(jacobi_fixed_kernel<NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JacobiCfg<NPV>::SMEM);
+  SEQM_JACOBI_CLASSES(SEQM_ATTR)
+#undef SEQM_ATTR
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
@@ -85,6 +90,79 @@ static int check_batch(const seqm_batch_t* b) {
     return SEQM_ERR_TOO_LARGE;
   }
   return ensure_device();
+}
+static int diis_grid(int nmol) {
+#ifdef SEQM_HOSTEMU
+  return nmol;  // one single-thread "warp" per emulated CTA
+#else
+  return (nmol + SEQM_DIIS_WARPS - 1) / SEQM_DIIS_WARPS;
+#endif
+}
+// Launch the fixed-slot Jacobi kernel once per populated size class (right-sized shared memory / threads).
+// One molecule is a long dependent chain (sweeps x steps x barrier latency), so the classes are forked onto
+// their own streams and run concurrently; the caller's stream joins them afterwards.
+#ifndef SEQM_HOSTEMU
+static cudaStream_t g_cls_stream[16];
+static cudaEvent_t g_cls_fork, g_cls_join[16];
+static int g_cls_streams_ready = 0;
+static int ensure_class_streams() {
+  if (g_cls_streams_ready) return SEQM_OK;
+  for (int c = 0; c < g_jacobi_ncls; ++c) {
+    if (cudaStreamCreateWithFlags(&g_cls_stream[c], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_cls_join[c], cudaEventDisableTiming) != cudaSuccess) {
+      seqm_set_error("could not create eigensolver class streams");
+      return SEQM_ERR_CUDA;
+    }
+  }
+  if (cudaEventCreateWithFlags(&g_cls_fork, cudaEventDisableTiming) != cudaSuccess) return SEQM_ERR_CUDA;
+  g_cls_streams_ready = 1;
+  return SEQM_OK;
+}
+#endif
+static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const double* Cguess,
+                         const int32_t* active, cudaStream_t st) {
+  const double* cg = (Cguess && P && C) ? Cguess : nullptr;
+  int npop = 0;
+  for (int c = 0; c < g_jacobi_ncls; ++c) npop += (b->cls_count[c] > 0);
+#ifndef SEQM_HOSTEMU
+  const bool fork = npop > 1;
+  if (fork) {
+    int rc = ensure_class_streams();
+    if (rc) return rc;
+    cudaEventRecord(g_cls_fork, st);
+  }
+#else
+  const bool fork = false;
+#endif
+  for (int c = g_jacobi_ncls - 1; c >= 0; --c) {
+    const int cnt = b->cls_count[c], first = b->cls_begin[c];
+    if (cnt <= 0) continue;
+    cudaStream_t cst = st;
+#ifndef SEQM_HOSTEMU
+    if (fork) {
+      cst = g_cls_stream[c];
+      cudaStreamWaitEvent(cst, g_cls_fork, 0);
+    }
+#endif
+    switch (g_jacobi_np[c]) {
+#define SEQM_CASE(NPV)                                                                                               \
+  case NPV:                                                                                                          \
+    SEQM_LAUNCH(jacobi_fixed_kernel<NPV>, cnt, JacobiCfg<NPV>::THREADS, JacobiCfg<NPV>::SMEM, cst, *b, first, F, P, evals, \
+                C, cg, active);                                                                                      \
+    break;
+      SEQM_JACOBI_CLASSES(SEQM_CASE)
+#undef SEQM_CASE
+    }
+    int rc = seqm_check_launch("jacobi_fixed_kernel");
+    if (rc) return rc;
+#ifndef SEQM_HOSTEMU
+    if (fork) {
+      cudaEventRecord(g_cls_join[c], cst);
+      cudaStreamWaitEvent(st, g_cls_join[c], 0);
+    }
+#endif
+  }
+  return SEQM_OK;
 }
 static int threads_for(int nmax) { return nmax <= 24 ? 128 : (nmax <= 64 ? 256 : 512); }
 static int grid1d(long long n, int block) {
@@ -149,6 +227,22 @@ int seqm_max_orbitals(void) { return SEQM_MAX_ORB; }
 
 
 long long seqm_launch_count(void) { return g_seqm_launches; }
+
+/* eigensolver statistics since the last call: [0] molecules solved, [1] Jacobi sweeps, [2] rotation steps */
+int seqm_jacobi_stats(unsigned long long* out, int reset) {
+#ifndef SEQM_HOSTEMU
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_jacobi_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) return SEQM_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_jacobi_stats, z, sizeof(z));
+  }
+#else
+  for (int i = 0; i < 4; ++i) out[i] = g_jacobi_stats[i];
+  if (reset) for (int i = 0; i < 4; ++i) g_jacobi_stats[i] = 0;
+#endif
+  return SEQM_OK;
+}
 
 /* measured FP64 FMA peak of the device in TFLOP/s (all SMs, 8 chains/thread); blocks the host */
 double seqm_fp64_peak_tflops(void) {
@@ -239,9 +333,8 @@ int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* 
                      const int32_t* active, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
-  PROF(PK_JACOBI, SEQM_STREAM(stream), SEQM_LAUNCH(jacobi_density_kernel, b->nmol, threads_for(b->nmax), jacobi_smem_bytes(b->nmax), SEQM_STREAM(stream), *b, F,
-              P, evals, C, P ? Cguess : nullptr, active));
-  return seqm_check_launch("jacobi_density_kernel");
+  PROF(PK_JACOBI, SEQM_STREAM(stream), rc = launch_jacobi(b, F, P, evals, C, Cguess, active, SEQM_STREAM(stream)));
+  return rc;
 }
 
 int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter, const int32_t* active,
@@ -354,7 +447,6 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   cudaStream_t st = SEQM_STREAM(stream);
   const int nt = threads_for(b->nmax);
   const size_t sm1 = sizeof(double) * (size_t)b->nmax * b->nmax;
-  const size_t smj = jacobi_smem_bytes(b->nmax);
   const size_t smsp2 = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
   const int gm = grid1d(b->nmol, 128);
   const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
@@ -385,7 +477,7 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       PROF(PK_DIIS_STORE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF));
       CHK("diis_store_kernel");
       if (cF >= 2) {
-        PROF(PK_DIIS_SOLVE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_solve_kernel, grid1d(b->nmol, 64), 64, 0, st, *b, W, counter, cF));
+        PROF(PK_DIIS_SOLVE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_solve_kernel, diis_grid(b->nmol), 32 * SEQM_DIIS_WARPS, 0, st, *b, W, counter, cF));
         CHK("diis_solve_kernel");
         PROF(PK_DIIS_EXTRAP, SEQM_STREAM(stream), SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF));
         CHK("diis_extrapolate_kernel");
@@ -396,9 +488,9 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       PROF(PK_SP2, SEQM_STREAM(stream), SEQM_LAUNCH(sp2_kernel, b->nmol, nt, smsp2, st, *b, F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, W.active));
       CHK("sp2_kernel");
     } else {
-      PROF(PK_JACOBI, SEQM_STREAM(stream), SEQM_LAUNCH(jacobi_density_kernel, b->nmol, nt, smj, st, *b, F, W.Pnew, (double*)nullptr, W.C,
-                  (o->warm_start && have_C) ? (const double*)W.C : (const double*)nullptr, W.active));
-      CHK("jacobi_density_kernel");
+      PROF(PK_JACOBI, SEQM_STREAM(stream), rc = launch_jacobi(b, F, W.Pnew, (double*)nullptr, W.C,
+                (o->warm_start && have_C) ? (const double*)W.C : (const double*)nullptr, W.active, st));
+      if (rc) return rc;
       have_C = 1;
     }
     // mixing

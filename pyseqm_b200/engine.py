@@ -10,7 +10,7 @@ import os
 
 import torch
 
-from ._lib import METHOD_ID, NPAR, PAR_ROWS, SeqmBatchStruct, SeqmError, SeqmScfOpts, ptr, stream_of
+from ._lib import JACOBI_NP, METHOD_ID, NPAR, PAR_ROWS, SeqmBatchStruct, SeqmError, SeqmScfOpts, ptr, stream_of
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 _TABLE_CACHE = {}
@@ -115,6 +115,13 @@ class BatchPlan:
         for k, v in self.t.items():
             setattr(s, k, v.data_ptr())
         s.atom_par = self.par.data_ptr()
+        # eigensolver size classes over the descending-n processing order (host arrays inside the struct)
+        n_sorted = norb[order].cpu().tolist()
+        cls = [next((c for c, q in enumerate(JACOBI_NP) if 2 * q >= n), -1) for n in n_sorted]
+        for c in range(len(JACOBI_NP)):
+            idx = [k for k, x in enumerate(cls) if x == c]
+            s.cls_begin[c] = idx[0] if idx else 0
+            s.cls_count[c] = len(idx)
         self.struct = s
         self.ref = C.byref(s)
         if self.nmax > lib.dll.seqm_max_orbitals():
@@ -156,8 +163,8 @@ def op_fock(plan, P, H, w, active=None, out=None):
 
 
 def op_eig_density(plan, F, want_P=True, want_C=False, Cguess=None, active=None):
-    P = plan.new_mat() if want_P else None
-    Cm = plan.new_mat() if want_C else None
+    P = plan.new_mat() if (want_P or Cguess is not None) else None
+    Cm = plan.new_mat() if (want_C or Cguess is not None) else None  # the warm start needs both scratch slots
     e = torch.zeros((plan.nmol, plan.nmax), dtype=torch.float64, device=plan.device)
     plan.lib.check(
         plan.lib.dll.seqm_eig_density(plan.ref, ptr(F), ptr(P), ptr(e), ptr(Cm), ptr(Cguess), ptr(active), stream_of(F)),
