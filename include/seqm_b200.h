@@ -108,6 +108,13 @@ int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* 
 int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
                   void* stream);
 
+/* the same gradient by forward-mode differentiation of the whole pair code (slower; cross-check of seqm_gradient) */
+int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
+                          void* stream);
+
+/* packed eigenvector matrices -> dense (nmol, nmax, nmax), identity on the padding: the `v` of diag.py:110-241 */
+int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void* stream);
+
 /* pack()/unpack() -- pack.py:64-96 between dense (nmol, 4*molsize, 4*molsize) and packed matrices */
 int seqm_pack(const seqm_batch_t* b, const double* dense, double* packed, void* stream);
 int seqm_unpack(const seqm_batch_t* b, const double* packed, double* dense, void* stream);
@@ -128,8 +135,10 @@ typedef struct seqm_scf_opts {
   int32_t warm_start;/* 1: eigensolver starts from the previous iteration's eigenvectors */
 } seqm_scf_opts_t;
 int64_t seqm_scf_workspace_bytes(const seqm_batch_t* b, const seqm_scf_opts_t* o);
+/* C_last: optional packed buffer receiving the eigenvectors of the last density solve (a warm start for the
+ * final seqm_eig_density of the converged Fock matrix); NULL or unused when use_sp2 != 0. */
 int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
-             double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, void* stream);
+             double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, double* C_last, void* stream);
 
 /* Optional per-kernel timing with CUDA events on the launch stream (bench.py roofline evidence).
  * enable(1) clears and starts recording; collect() synchronises and returns summed ms / launch counts

@@ -47,8 +47,8 @@ class Energy(torch.nn.Module):
         t0 = _timing(molecule, "Hcore + STO Integrals", t0)
         # density: initial guess or the caller's P0 (overwritten in place, ElectronicStructure.py:78)
         P = engine.op_initial_density(plan) if P0 is None else engine.op_pack(plan, P0)
-        F, Eelec, notconv, n_iter = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
-                                                  warm_start=self.warm_start)  # fmt: skip
+        F, Eelec, notconv, n_iter, Clast = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
+                                                         warm_start=self.warm_start, want_C=True)  # fmt: skip
         molecule.n_scf_iter = n_iter
         if molecule.verbose:
             tag = {0: "scf direct step  ", 1: "scf adaptive step    ", 2: "scf pulay diis   "}[self.scf_converger[0]]
@@ -62,13 +62,15 @@ class Energy(torch.nn.Module):
         molecule.w = w
         molecule._gam = w[:, 0, 0]
         if self.eig:
-            e_mo_n, _, Cm = engine.op_eig_density(plan, F, want_P=False, want_C=True)
+            # eigenpairs of the converged Fock matrix, warm-started from the last SCF eigenbasis
+            e_mo_n, _, Cm = engine.op_eig_density(plan, F, want_P=False, want_C=True,
+                                                  Cguess=Clast if self.warm_start else None)  # fmt: skip
             N = 4 * plan.molsize
             e_mo = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
             e_mo[:, : plan.nmax] = e_mo_n
             lumo = plan.nocc.unsqueeze(1)
             e_gap = (e_mo.gather(1, lumo) - e_mo.gather(1, lumo - 1)).reshape(-1)
-            molecule.molecular_orbitals = _orbitals_dense(plan, Cm)
+            molecule.molecular_orbitals = engine.op_orbitals_dense(plan, Cm)
         else:
             e_mo, e_gap = None, None
         EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)
@@ -101,25 +103,6 @@ class Energy(torch.nn.Module):
         if all_terms:
             return Hf, Etot, Eelec, Enuc, Eiso, EnucAB, e_gap, e_mo, Pd, None, notconv
         return Eelec, EnucAB, Pd, notconv
-
-
-def _orbitals_dense(plan, Cm):
-    """(nmol, nmax, nmax) eigenvector matrices, identity on the padding (diag.py:110-241 `v`)."""
-    nmol, nmax = plan.nmol, plan.nmax
-    V = torch.zeros((nmol, nmax, nmax), dtype=torch.float64, device=plan.device)
-    idx = torch.arange(nmax, device=plan.device)
-    V[:, idx, idx] = 1.0
-    mat0 = plan.t["mol_mat0"]
-    norb = plan.norb
-    for n in torch.unique(norb).tolist():
-        sel = torch.nonzero(norb == n, as_tuple=False).squeeze(1)
-        off = mat0[sel].unsqueeze(1) + torch.arange(n * n, device=plan.device).unsqueeze(0)
-        blk = Cm[off].reshape(-1, n, n)
-        V[sel, :n, :n] = blk
-        if n < nmax:
-            V[sel.unsqueeze(1), idx[n:].unsqueeze(0), idx[n:].unsqueeze(0)] = 1.0
-            V[sel, :n, n:] = 0.0
-    return V
 
 
 def _ground_dipole(molecule, Pd):

@@ -41,6 +41,38 @@ SEQM_HD Dual3 operator/(double a, const Dual3& b) {
 SEQM_HD Dual3& operator+=(Dual3& a, const Dual3& b) { a.v += b.v; a.d0 += b.d0; a.d1 += b.d1; a.d2 += b.d2; return a; }
 SEQM_HD Dual3& operator-=(Dual3& a, const Dual3& b) { a.v -= b.v; a.d0 -= b.d0; a.d1 -= b.d1; a.d2 -= b.d2; return a; }
 
+// one-derivative dual: value + d/dr (used by the adjoint force kernel for the radial derivatives)
+struct Dual1 {
+  double v, d;
+  SEQM_HD Dual1() : v(0.0), d(0.0) {}
+  SEQM_HD Dual1(double a) : v(a), d(0.0) {}
+  SEQM_HD Dual1(double a, double b) : v(a), d(b) {}
+};
+SEQM_HD Dual1 operator+(const Dual1& a, const Dual1& b) { return Dual1(a.v + b.v, a.d + b.d); }
+SEQM_HD Dual1 operator-(const Dual1& a, const Dual1& b) { return Dual1(a.v - b.v, a.d - b.d); }
+SEQM_HD Dual1 operator-(const Dual1& a) { return Dual1(-a.v, -a.d); }
+SEQM_HD Dual1 operator*(const Dual1& a, const Dual1& b) { return Dual1(a.v * b.v, a.d * b.v + a.v * b.d); }
+SEQM_HD Dual1 operator/(const Dual1& a, const Dual1& b) {
+  double inv = 1.0 / b.v, q = a.v * inv;
+  return Dual1(q, (a.d - q * b.d) * inv);
+}
+SEQM_HD Dual1 operator+(const Dual1& a, double b) { return Dual1(a.v + b, a.d); }
+SEQM_HD Dual1 operator+(double b, const Dual1& a) { return Dual1(a.v + b, a.d); }
+SEQM_HD Dual1 operator-(const Dual1& a, double b) { return Dual1(a.v - b, a.d); }
+SEQM_HD Dual1 operator-(double b, const Dual1& a) { return Dual1(b - a.v, -a.d); }
+SEQM_HD Dual1 operator*(const Dual1& a, double b) { return Dual1(a.v * b, a.d * b); }
+SEQM_HD Dual1 operator*(double b, const Dual1& a) { return Dual1(a.v * b, a.d * b); }
+SEQM_HD Dual1 operator/(const Dual1& a, double b) { double i = 1.0 / b; return Dual1(a.v * i, a.d * i); }
+SEQM_HD Dual1 operator/(double a, const Dual1& b) {
+  double inv = 1.0 / b.v, q = a * inv;
+  return Dual1(q, -q * inv * b.d);
+}
+SEQM_HD Dual1& operator+=(Dual1& a, const Dual1& b) { a.v += b.v; a.d += b.d; return a; }
+SEQM_HD Dual1 sq_root(const Dual1& x) { double s = sqrt(x.v); return Dual1(s, 0.5 / s * x.d); }
+SEQM_HD Dual1 inv_sqrt(const Dual1& x) { double s = 1.0 / sqrt(x.v); return Dual1(s, -0.5 * s / x.v * x.d); }
+SEQM_HD Dual1 e_xp(const Dual1& x) { double e = exp(x.v); return Dual1(e, e * x.d); }
+SEQM_HD double val(const Dual1& x) { return x.v; }
+
 // scalar helpers, overloaded for double and Dual3
 SEQM_HD double sq_root(double x) { return sqrt(x); }
 SEQM_HD Dual3 sq_root(const Dual3& x) {

@@ -179,8 +179,177 @@ SEQM_GLOBAL void pair_sum_kernel(seqm_batch_t b, const double* __restrict__ vals
 
 // Hellmann-Feynman pair gradient dE_pair/dR_i at fixed density (what anal_grad.py:16-225 assembles):
 //   E_pair = 2 sum P_AB o (beta S) + sum_A P o e1b + sum_B P o e2a + Coulomb + exchange + core-core
+// evaluated in REVERSE mode: all density contractions collapse into one coefficient matrix C (E_2e = C : w), the
+// adjoints dE/dri (via C rotated into the local frame) and dE/drot (via dE/dT) are formed in plain doubles, and
+// only three small pieces are differentiated forward: the 22 local integrals, the 5 Slater overlaps and the
+// core-core function in r (Dual1), and the 3x3 quaternion rotation in the bond direction (Dual3).
+// The forward-mode-everywhere version of this kernel (Dual3 through w = T^t L T) is kept as
+// pair_gradient_forward_kernel: same numbers, 3.5x the local-memory traffic; tests compare the two.
+SEQM_HD int cls_of(int kl) { return pack_class(kl); }
+
 SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* __restrict__ P,
                                       double* __restrict__ gpair) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
+    const int i = b.pair_i[p], j = b.pair_j[p];
+    const MolView v = mol_view(b, b.atom_mol[i]);
+    const double* Pm = P + v.mat0;
+    const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
+    const int ni = orb_cnt(v, i - v.a0), nj = orb_cnt(v, j - v.a0);
+    const bool hi = ni == 4, hj = nj == 4;
+    PairGeom<double> g;
+    pair_geom(xyz, i, j, g);
+    const double dist = g.r * SEQM_A0;
+    const Dual1 r1(g.r, 1.0);
+    double dEdr = 0.0, dEde[3] = {0.0, 0.0, 0.0};
+
+    // ---- resonance integrals: Q_mu,nu = P_mu,nu (beta_mu^A + beta_nu^B)
+    if (g.r <= SEQM_OVERLAP_CUTOFF) {
+      const double bsi = par(b, SEQM_P_BS, i), bpi = par(b, SEQM_P_BP, i);
+      const double bsj = par(b, SEQM_P_BS, j), bpj = par(b, SEQM_P_BP, j);
+      const int na = (int)par(b, SEQM_P_QN, i), nb = (int)par(b, SEQM_P_QN, j);
+      const double zsa = par(b, SEQM_P_ZS, i), zpa = par(b, SEQM_P_ZP, i);
+      const double zsb = par(b, SEQM_P_ZS, j), zpb = par(b, SEQM_P_ZP, j);
+      const Dual1 ss = sto_overlap(c_ovl, na, nb, 0, zsa, zsb, r1);
+      dEdr += Pm[oi * n + oj] * (bsi + bsj) * ss.d;
+      if (hi) {
+        const Dual1 os = sto_overlap(c_ovl, na, nb, 1, zpa, zsb, r1);
+        for (int k = 0; k < 3; ++k) {
+          const double q = Pm[(oi + k + 1) * n + oj] * (bpi + bsj);
+          dEdr += q * os.d * g.e[k];
+          dEde[k] += q * os.v;
+        }
+      }
+      if (hj) {
+        const Dual1 so = sto_overlap(c_ovl, na, nb, 2, zsa, zpb, r1);
+        for (int k = 0; k < 3; ++k) {
+          const double q = Pm[oi * n + oj + k + 1] * (bsi + bpj);
+          dEdr += q * so.d * g.e[k];
+          dEde[k] += q * so.v;
+        }
+      }
+      if (hi && hj) {
+        const Dual1 oo = sto_overlap(c_ovl, na, nb, 3, zpa, zpb, r1);
+        const Dual1 pp = sto_overlap(c_ovl, na, nb, 4, zpa, zpb, r1);
+        const double bb = bpi + bpj;
+        double tr = 0.0, qee = 0.0;
+        for (int k = 0; k < 3; ++k) {
+          tr += Pm[(oi + k + 1) * n + oj + k + 1];
+          double row = 0.0;
+          for (int l = 0; l < 3; ++l) {
+            const double qs = Pm[(oi + k + 1) * n + oj + l + 1] + Pm[(oi + l + 1) * n + oj + k + 1];
+            row += qs * g.e[l];
+            qee += Pm[(oi + k + 1) * n + oj + l + 1] * g.e[k] * g.e[l];
+          }
+          dEde[k] += bb * (oo.v - pp.v) * row;
+        }
+        dEdr += bb * ((oo.d - pp.d) * qee + pp.d * tr);
+      }
+    }
+
+    // ---- two-electron + core-attraction terms: E_2e = sum C[kl][mn] w[kl][mn]
+    const int nA = hi ? 10 : 1, nB = hj ? 10 : 1;
+    const int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
+    double Cm[10][10];
+    {
+      double pa[10], pb[10];
+      for (int kl = 0; kl < 10; ++kl) {
+        int mu = 0;
+        while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
+        const int nu = kl - mu * (mu + 1) / 2;
+        const double wt = (mu == nu) ? 1.0 : 2.0;
+        pa[kl] = (kl < nA) ? wt * Pm[(oi + mu) * n + oi + nu] : 0.0;
+        pb[kl] = (kl < nB) ? wt * Pm[(oj + mu) * n + oj + nu] : 0.0;
+      }
+      const double ti = par(b, SEQM_P_TORE, i), tj = par(b, SEQM_P_TORE, j);
+      for (int kl = 0; kl < nA; ++kl)
+        for (int mn = 0; mn < nB; ++mn) Cm[kl][mn] = pa[kl] * pb[mn];
+      for (int kl = 0; kl < nA; ++kl) Cm[kl][0] -= tj * pa[kl];
+      for (int mn = 0; mn < nB; ++mn) Cm[0][mn] -= ti * pb[mn];
+      for (int mu = 0; mu < ni; ++mu)
+        for (int nu = 0; nu < ni; ++nu)
+          for (int la = 0; la < nj; ++la)
+            for (int sg = 0; sg < nj; ++sg)
+              Cm[pack2(mu, nu)][pack2(la, sg)] -= 0.5 * Pm[(oi + mu) * n + oj + la] * Pm[(oi + nu) * n + oj + sg];
+    }
+    Dual1 ri[22];
+    local_integrals(r1, load_multipole(b, i), load_multipole(b, j), nint, ri);
+    if (nint == 1) {
+      dEdr += Cm[0][0] * ri[0].d;
+    } else {
+      double vdir[3] = {-g.e[0], -g.e[1], -g.e[2]};
+      double rot[3][3], Tm[10][10];
+      rotation_rows(vdir, rot);
+      pair_transform(rot, Tm);
+      // U2 = T C (rows: local pair index, cols: molecular mn) ; U1 = T C^t
+      double U1[10][10], U2[10][10], GT[10][10];
+      for (int a = 0; a < 10; ++a)
+        for (int c = 0; c < 10; ++c) { U1[a][c] = 0.0; U2[a][c] = 0.0; GT[a][c] = 0.0; }
+      for (int KL = 0; KL < nA; ++KL)
+        for (int kl = 0; kl < nA; ++kl) {
+          if (cls_of(KL) != cls_of(kl)) continue;
+          const double t = Tm[KL][kl];
+          for (int c = 0; c < nB; ++c) U2[KL][c] += t * Cm[kl][c];
+        }
+      for (int MN = 0; MN < nB; ++MN)
+        for (int mn = 0; mn < nB; ++mn) {
+          if (cls_of(MN) != cls_of(mn)) continue;
+          const double t = Tm[MN][mn];
+          for (int c = 0; c < nA; ++c) U1[MN][c] += t * Cm[c][mn];
+        }
+      for (int e = 0; e < SEQM_NL; ++e) {
+        const LEntry le = l_entry(e);
+        if (le.k >= nint || le.mn >= nB) continue;
+        const int cK = cls_of(le.kl), cM = cls_of(le.mn);
+        double cl = 0.0;  // (T C T^t)[KL][MN]
+        for (int c = 0; c < nB; ++c)
+          if (cls_of(c) == cM) cl += U2[le.kl][c] * Tm[le.mn][c];
+        dEdr += cl * ri[le.k].d;
+        const double lv = ri[le.k].v;
+        for (int c = 0; c < nA; ++c)
+          if (cls_of(c) == cK) GT[le.kl][c] += lv * U1[le.mn][c];
+        for (int c = 0; c < nB; ++c)
+          if (cls_of(c) == cM) GT[le.mn][c] += lv * U2[le.kl][c];
+      }
+      // dE/drot from dE/dT
+      double Gr[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int a = 0; a < 3; ++a)
+        for (int k = 0; k < 3; ++k) Gr[a][k] += GT[pack2(a + 1, 0)][pack2(k + 1, 0)];
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c <= a; ++c)
+          for (int k = 0; k < 3; ++k)
+            for (int l = 0; l <= k; ++l) {
+              const double gt = GT[pack2(a + 1, c + 1)][pack2(k + 1, l + 1)];
+              Gr[a][k] += gt * rot[c][l];
+              Gr[c][l] += gt * rot[a][k];
+              if (a != c) {
+                Gr[c][k] += gt * rot[a][l];
+                Gr[a][l] += gt * rot[c][k];
+              }
+            }
+      // d rot / d v by forward mode on the 3x3 rotation only ; e = -v
+      Dual3 vd[3] = {Dual3(vdir[0], 1.0, 0.0, 0.0), Dual3(vdir[1], 0.0, 1.0, 0.0), Dual3(vdir[2], 0.0, 0.0, 1.0)};
+      Dual3 rd[3][3];
+      rotation_rows(vd, rd);
+      for (int a = 0; a < 3; ++a)
+        for (int k = 0; k < 3; ++k) {
+          dEde[0] -= Gr[a][k] * rd[a][k].d0;
+          dEde[1] -= Gr[a][k] * rd[a][k].d1;
+          dEde[2] -= Gr[a][k] * rd[a][k].d2;
+        }
+    }
+    // ---- core-core repulsion (depends on r only)
+    dEdr += core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), r1, ri[0]).d;
+    // ---- chain rule: X = R_j - R_i, r = |X|/a0, e = X/|X| ; gradient with respect to R_i is -dE/dX
+    const double ede = dEde[0] * g.e[0] + dEde[1] * g.e[1] + dEde[2] * g.e[2];
+    for (int c = 0; c < 3; ++c)
+      gpair[3 * (long long)p + c] = -(dEdr * g.e[c] * (1.0 / SEQM_A0) + (dEde[c] - ede * g.e[c]) / dist);
+  }
+}
+
+// Forward-mode reference implementation of the same quantity (Dual3 through the whole pair code).
+SEQM_GLOBAL void pair_gradient_forward_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* __restrict__ P,
+                                              double* __restrict__ gpair) {
+
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
     const int i = b.pair_i[p], j = b.pair_j[p];
     const MolView v = mol_view(b, b.atom_mol[i]);

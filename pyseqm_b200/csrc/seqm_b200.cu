@@ -193,6 +193,16 @@ SEQM_GLOBAL void unpack_kernel(seqm_batch_t b, const double* __restrict__ packed
   for (int t = threadIdx.x; t < n * n; t += blockDim.x)
     D[(long long)dense_index(v, t / n) * N + dense_index(v, t % n)] = packed[v.mat0 + t];
 }
+// packed eigenvector matrices -> (nmol, nmax, nmax) with the identity on the padding (diag.py:110-241 `v`)
+SEQM_GLOBAL void orbitals_dense_kernel(seqm_batch_t b, const double* __restrict__ C, double* __restrict__ V) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n, N = b.nmax;
+  double* Vm = V + (long long)v.m * N * N;
+  for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
+    const int i = t / N, j = t - i * N;
+    Vm[t] = (i < n && j < n) ? C[v.mat0 + i * n + j] : ((i == j) ? 1.0 : 0.0);
+  }
+}
 SEQM_GLOBAL void initial_density_kernel(seqm_batch_t b, double* __restrict__ P) {
   const MolView v = mol_view(b, blockIdx.x);
   const int n = v.n;
@@ -392,6 +402,24 @@ int seqm_unpack(const seqm_batch_t* b, const double* packed, double* dense, void
   SEQM_LAUNCH(unpack_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, packed, dense);
   return seqm_check_launch("unpack_kernel");
 }
+int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  SEQM_LAUNCH(orbitals_dense_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, C, V);
+  return seqm_check_launch("orbitals_dense_kernel");
+}
+int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
+                          void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (b->npairs > 0) {
+    SEQM_LAUNCH(pair_gradient_forward_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, pair_scratch);
+    rc = seqm_check_launch("pair_gradient_forward_kernel");
+    if (rc) return rc;
+  }
+  SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad);
+  return seqm_check_launch("atom_gradient_kernel");
+}
 int seqm_initial_density(const seqm_batch_t* b, double* P, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
@@ -434,7 +462,7 @@ static int zero_nnot(const ScfWork& W, void* stream) {
 }
 
 int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
-             double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, void* stream) {
+             double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, double* C_last, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
   if (o->converger < 0 || o->converger > 2) {
@@ -535,12 +563,15 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   if (n_iter_out) *n_iter_out = printed;
 #ifndef SEQM_HOSTEMU
   cudaError_t e = cudaMemcpyAsync(Eelec, W.Eel_new, sizeof(double) * b->nmol, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && C_last && have_C)
+    e = cudaMemcpyAsync(C_last, W.C, sizeof(double) * (size_t)b->mat_total, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) {
-    seqm_set_error("Eelec copy: %s", cudaGetErrorString(e));
+    seqm_set_error("result copy: %s", cudaGetErrorString(e));
     return SEQM_ERR_CUDA;
   }
 #else
   memcpy(Eelec, W.Eel_new, sizeof(double) * b->nmol);
+  if (C_last && have_C) memcpy(C_last, W.C, sizeof(double) * (size_t)b->mat_total);
 #endif
 #undef CHK
   return SEQM_OK;

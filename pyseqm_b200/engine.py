@@ -196,11 +196,18 @@ def op_nuclear_energy(plan, xyz, w):
     return EAB[: plan.npairs], En
 
 
-def op_gradient(plan, xyz, P):
+def op_gradient(plan, xyz, P, forward_mode=False):
     scratch = torch.zeros((max(plan.npairs, 1), 3), dtype=torch.float64, device=plan.device)
     g = torch.zeros((plan.nat, 3), dtype=torch.float64, device=plan.device)
-    plan.lib.check(plan.lib.dll.seqm_gradient(plan.ref, ptr(xyz), ptr(P), ptr(scratch), ptr(g), stream_of(g)), "seqm_gradient")
+    fn = plan.lib.dll.seqm_gradient_forward if forward_mode else plan.lib.dll.seqm_gradient
+    plan.lib.check(fn(plan.ref, ptr(xyz), ptr(P), ptr(scratch), ptr(g), stream_of(g)), "seqm_gradient")
     return g
+
+
+def op_orbitals_dense(plan, Cm):
+    V = torch.empty((plan.nmol, plan.nmax, plan.nmax), dtype=torch.float64, device=plan.device)
+    plan.lib.check(plan.lib.dll.seqm_orbitals_dense(plan.ref, ptr(Cm), ptr(V), stream_of(V)), "seqm_orbitals_dense")
+    return V
 
 
 def op_pack(plan, dense):
@@ -224,7 +231,7 @@ def op_initial_density(plan):
     return P
 
 
-def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_start=True):
+def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_start=True, want_C=False):
     """Runs the SCF loop; P (packed) is updated in place.  Returns (F, Eelec, notconverged, n_iter)."""
     o = SeqmScfOpts()
     o.eps = float(eps)
@@ -242,9 +249,12 @@ def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_star
     E = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
     nc = torch.ones(plan.nmol, dtype=torch.int32, device=plan.device)
     nit = C.c_int32(0)
+    Clast = plan.new_mat() if (want_C and not sp2[0]) else None
     plan.lib.check(
         plan.lib.dll.seqm_scf(plan.ref, C.byref(o), ptr(H), ptr(w), ptr(P), ptr(F), ptr(E), ptr(nc), ptr(ws),
-                              C.byref(nit), stream_of(P)),
+                              C.byref(nit), ptr(Clast), stream_of(P)),
         "seqm_scf",
     )  # fmt: skip
+    if want_C:
+        return F, E, nc.to(torch.bool), int(nit.value), Clast
     return F, E, nc.to(torch.bool), int(nit.value)
