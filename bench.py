@@ -101,6 +101,39 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}  # fmt: skip
 
 
+def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist):
+    """replica-steps/s of XL-BOMD NVE (eigensolver density branch, the one the reference can run) on `nrep`
+    coronene replicas per GPU; the t = 0 SCF is excluded, as in SURVEY 8(d)."""
+    import torch
+
+    xyz = os.path.join(ROOT, "tests", "golden", "xyz", "coronene.xyz")
+    s, c = seqm.read_xyz([xyz] * nrep)
+    sp = {"method": "AM1", "scf_eps": 1.0e-7, "scf_converger": [2], "sp2": [False]}
+    torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))
+    mol = seqm.Molecule(const, sp, torch.as_tensor(c, device=dev), torch.as_tensor(s, device=dev))
+    md = seqm.XL_BOMD(xl_bomd_params={"k": 6}, seqm_parameters=sp, timestep=0.4, Temp=300.0)
+    md.initialize(mol)
+    for i in range(3):
+        md._do_integrator_step(i, mol, dict())
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(3, 3 + nsteps):
+        md._do_integrator_step(i, mol, dict())
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    Ek = md._kinetic_energy(mol)
+    return {"metric": "XL-BOMD MD steps/s (replica-steps/s)", "value": nrep * world * nsteps / float(t), "unit": "replica-steps/s",
+            "ms_per_md_step": float(t) / nsteps * 1e3, "replicas_per_gpu": nrep, "steps": nsteps, "molecule": "coronene C24H12 (108 orbitals)",
+            "method": "AM1, k=6, dt=0.4 fs, 300 K, density by the Jacobi eigensolver (reference branch xlbomd.py:361)",
+            "finite": bool(torch.isfinite(mol.Etot).all() and torch.isfinite(Ek).all())}  # fmt: skip
+
+
 def _oracle_chunk(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import seqm_oracle as so
@@ -163,6 +196,8 @@ def main():
     ap.add_argument("--nmol", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--xl-replicas", type=int, default=1024, help="coronene replicas for the XL-BOMD line (0 = skip)")
+    ap.add_argument("--xl-steps", type=int, default=20)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -320,6 +355,11 @@ def main():
         if roofline["fock_kernel_hbm"]["achieved"]:
             roofline["fock_kernel_hbm"]["frac"] = roofline["fock_kernel_hbm"]["achieved"] / hbm_peak
 
+    # ---- second headline metric: XL-BOMD MD steps/s (configs[2]: coronene replicas, AM1, k = 6, dt = 0.4 fs) ------
+    xl = None
+    if args.xl_replicas > 0:
+        xl = xl_bomd_rate(seqm, dev, const, args.xl_replicas, args.xl_steps, world, dist if world > 1 else None)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -338,7 +378,7 @@ def main():
                     "includes": "pinned-host species+coordinates H2D, Molecule() (parser, parameter gather), forward, "
                                 "D2H of Etot, Hf, force, notconverged"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "kernel_breakdown": breakdown, "scf_iterations": n_iter, "not_converged": nnot,
+            "kernel_breakdown": breakdown, "scf_iterations": n_iter, "not_converged": nnot, "xl_bomd": xl,
         }  # fmt: skip
         print(json.dumps(line))
     if world > 1:

@@ -108,6 +108,14 @@ int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* 
 int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
                   void* stream);
 
+/* XL-BOMD (seqm/dynamics/xlbomd.py:73-570, non-KSA branch): shadow electronic energy
+ * sum D o F(P) - 1/2 (F(P) - Hcore) o P  (elec_energy_xl, energy.py:76-88) and its nuclear gradient at fixed
+ * density D and field P (what ForceXL obtains by autograd through hcore + fock, xlbomd.py:536-551). */
+int seqm_elec_energy_xl(const seqm_batch_t* b, const double* D, const double* P, const double* F, const double* H,
+                        double* Eelec, void* stream);
+int seqm_gradient_xl(const seqm_batch_t* b, const double* xyz, const double* D, const double* P, double* pair_scratch,
+                     double* grad, void* stream);
+
 /* the same gradient by forward-mode differentiation of the whole pair code (slower; cross-check of seqm_gradient) */
 int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
                           void* stream);

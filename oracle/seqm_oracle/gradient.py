@@ -16,8 +16,10 @@ from .tables import Tables
 DELTA = 1.0e-5  # Angstrom, anal_grad.py:13
 
 
-def _pair_energy(P, par, mp, method, xij, rij, PAi, PBj, Dab, pki, pkj):
-    """Energy terms that depend on the geometry of each pair, at fixed density blocks."""
+def _pair_energy(P, par, mp, method, xij, rij, PAi, PBj, Dab, pki, pkj, xl=None):
+    """Energy terms that depend on the geometry of each pair, at fixed density blocks.
+    xl = (field blocks) switches to the XL-BOMD shadow energy sum D o F(P) - 1/2 (F(P)-h) o P:
+    one-electron terms with D, two-electron terms with (D - P/2) x P  (energy.py:76-88)."""
     T = Tables.get()
     w, e1b, e2a, _, _ = two_center_integrals_geom(P.ni, P.nj, P.idxi, P.idxj, xij, rij, mp, T)
     zeta = np.stack([par["zeta_s"], par["zeta_p"]], axis=1)
@@ -27,17 +29,26 @@ def _pair_energy(P, par, mp, method, xij, rij, PAi, PBj, Dab, pki, pkj):
     E = np.sum(Dab * di * bsum, axis=(1, 2))
     sym = np.triu(np.ones((4, 4)), 1) + np.triu(np.ones((4, 4)))  # 1 on diagonal, 2 above
     E += np.sum(PAi * e1b * sym, axis=(1, 2)) + np.sum(PBj * e2a * sym, axis=(1, 2))
-    E += np.matmul(pki[:, None, :], np.matmul(w, pkj[:, :, None]))[:, 0, 0]
     w4 = w[:, PACK[:, :, None, None], PACK[None, None, :, :]]  # (p, mu, nu, lam, sig)
     wx = w4.transpose(0, 1, 3, 2, 4).reshape(-1, 16, 16)
     d16 = Dab.reshape(-1, 16)
-    E += -0.5 * np.matmul(d16[:, None, :], np.matmul(wx, d16[:, :, None]))[:, 0, 0]
+    if xl is None:
+        E += np.matmul(pki[:, None, :], np.matmul(w, pkj[:, :, None]))[:, 0, 0]
+        E += -0.5 * np.matmul(d16[:, None, :], np.matmul(wx, d16[:, :, None]))[:, 0, 0]
+    else:
+        fki, fkj, Fab = xl  # packed weighted diagonal blocks and off-diagonal block of the field P
+        xi, xj = pki - 0.5 * fki, pkj - 0.5 * fkj
+        E += np.matmul(xi[:, None, :], np.matmul(w, fkj[:, :, None]))[:, 0, 0]
+        E += np.matmul(fki[:, None, :], np.matmul(w, xj[:, :, None]))[:, 0, 0]
+        x16 = d16 - 0.5 * Fab.reshape(-1, 16)
+        E += -np.matmul(x16[:, None, :], np.matmul(wx, Fab.reshape(-1, 16)[:, :, None]))[:, 0, 0]
     E += pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, rij, w[:, 0, 0], par)
     return E
 
 
-def hf_gradient(P, par, method, Dm, mp=None):
-    """grad (nmol, molsize, 3) in eV/Angstrom; force = -grad.  (anal_grad.py:16-92, 95-225)"""
+def hf_gradient(P, par, method, Dm, mp=None, field=None):
+    """grad (nmol, molsize, 3) in eV/Angstrom; force = -grad.  (anal_grad.py:16-92, 95-225)
+    field: optional XL-BOMD field density P (then Dm is the density D solved from F(P); xlbomd.py:536-551)."""
     T = Tables.get()
     nmol, molsize = P.nmol, P.molsize
     if mp is None:
@@ -48,6 +59,12 @@ def hf_gradient(P, par, method, Dm, mp=None):
     Dab = Db[mi, ai, aj]
     pk = PA[:, PACK_ROW, PACK_COL] * WEIGHT
     args = (PA[P.idxi], PA[P.idxj], Dab, pk[P.idxi], pk[P.idxj])
+    xl = None
+    if field is not None:
+        Fb = field.reshape(nmol, molsize, 4, molsize, 4).transpose(0, 1, 3, 2, 4)
+        FA = Fb[P.atom_molid, P.atom_pos, P.atom_pos]
+        fk = FA[:, PACK_ROW, PACK_COL] * WEIGHT
+        xl = (fk[P.idxi], fk[P.idxj], Fb[mi, ai, aj])
     Xij = P.xij * (P.rij * T.a0)[:, None]  # R_j - R_i in Angstrom
     g = np.zeros((P.rij.shape[0], 3))
     for c in range(3):
@@ -57,7 +74,7 @@ def hf_gradient(P, par, method, Dm, mp=None):
             X = Xij.copy()
             X[:, c] -= s * DELTA
             d = np.sqrt(np.sum(X * X, axis=1))
-            Es.append(_pair_energy(P, par, mp, method, X / d[:, None], d / T.a0, *args))
+            Es.append(_pair_energy(P, par, mp, method, X / d[:, None], d / T.a0, *args, xl=xl))
         g[:, c] = (Es[0] - Es[1]) / (2.0 * DELTA)
     nat = P.Z.shape[0]
     ga = np.zeros((nat, 3))

@@ -3,7 +3,7 @@
 force, dm, Hf, Etot, Eelec, Enuc, Eiso, e_mo, e_gap, q (+ n_scf_iter); self.charge / self.notconverged."""
 import torch
 
-from .basics import Force
+from .basics import Force, ForceXL
 from .Molecule import reject_unsupported
 
 
@@ -13,6 +13,7 @@ class Electronic_Structure(torch.nn.Module):
         reject_unsupported(seqm_parameters)
         self.seqm_parameters = seqm_parameters
         self.conservative_force = Force(seqm_parameters)
+        self.conservative_force_xl = ForceXL(seqm_parameters)
         self.charge = None
         self.notconverged = None
 
@@ -24,14 +25,21 @@ class Electronic_Structure(torch.nn.Module):
 
     def forward(self, molecule, learned_parameters=dict(), xl_bomd_params=dict(), P0=None, err_threshold=None,
                 max_rank=None, T_el=None, dm_prop="SCF", *args, **kwargs):  # fmt: skip
-        if dm_prop != "SCF":
-            raise NotImplementedError(f"dm_prop={dm_prop!r}: only the ground-state SCF path is on the B200 yet")
         if max_rank is not None or T_el is not None:
             raise NotImplementedError("KSA / finite-temperature options are not part of the B200 SCF path")
-        (molecule.force, P, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso, molecule.e_mo,
-         molecule.e_gap, self.charge, self.notconverged) = self.conservative_force(
-            molecule, P0=P0, learned_parameters=learned_parameters, *args, **kwargs)  # fmt: skip
-        molecule.dm = P.detach()
+        kwargs.pop("cis_amp", None)
+        if dm_prop == "SCF":
+            (molecule.force, P, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso, molecule.e_mo,
+             molecule.e_gap, self.charge, self.notconverged) = self.conservative_force(
+                molecule, P0=P0, learned_parameters=learned_parameters, *args, **kwargs)  # fmt: skip
+            molecule.dm = P.detach()
+        elif dm_prop == "XL-BOMD":
+            (molecule.force, molecule.dm, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso,
+             molecule.e_mo, molecule.e_gap, molecule.Electronic_entropy, molecule.dP2dt2, molecule.Krylov_Error,
+             molecule.Fermi_occ) = self.conservative_force_xl(
+                molecule, P0, learned_parameters=learned_parameters, xl_bomd_params=xl_bomd_params)  # fmt: skip
+        else:
+            raise NotImplementedError(f"dm_prop={dm_prop!r} is not implemented by the B200 path")
         with torch.no_grad():
             molecule.q = molecule.const.tore[molecule.species] - self.atomic_charges(molecule.dm)
 

@@ -137,6 +137,8 @@ class Molecule(torch.nn.Module):
         self.verbose = True
         self.analytical_gradient = None
         self.active_state = 0
+        self.Electronic_entropy = self.Fermi_occ = self.dP2dt2 = self.Krylov_Error = None
+        self.cis_amplitudes = None
         self.n_scf_iter: Optional[int] = None  # the count the reference only prints (scf_loop.py:975-992)
 
     def _refresh_geometry(self):

@@ -93,6 +93,8 @@ class SeqmLib:
             "seqm_scf_workspace_bytes": ([B, O], C.c_int64),
             "seqm_scf": ([B, O, P, P, P, P, P, P, P, C.POINTER(C.c_int32), P, P], C.c_int),
             "seqm_gradient_forward": ([B, P, P, P, P, P], C.c_int),
+            "seqm_gradient_xl": ([B, P, P, P, P, P, P], C.c_int),
+            "seqm_elec_energy_xl": ([B, P, P, P, P, P, P], C.c_int),
             "seqm_orbitals_dense": ([B, P, P, P], C.c_int),
             "seqm_launch_count": ([], C.c_longlong),
             "seqm_fp64_peak_tflops": ([], C.c_double),

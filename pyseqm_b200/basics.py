@@ -129,6 +129,82 @@ def _ground_dipole(molecule, Pd):
     molecule.dipole = (elec + nuc) * to_debye * debye_to_AU
 
 
+class ForceXL(torch.nn.Module):
+    """XL-BOMD energy and force for a given field density P (seqm/dynamics/xlbomd.py:73-570, non-KSA branch):
+    hcore -> F(P) -> D from F (Jacobi eigensolver, or SP2 when sp2=[True, eps]) -> shadow energy
+    sum D o F - 1/2 (F - h) o P -> force at fixed D and P.  No SCF.
+
+    `forward` takes/returns the dense padded layout like the reference; `forward_packed` is the same step on
+    packed device buffers (what pyseqm_b200.MolecularDynamics.XL_BOMD uses every step)."""
+
+    def __init__(self, seqm_parameters):
+        super().__init__()
+        reject_unsupported(seqm_parameters)
+        self.seqm_parameters = seqm_parameters
+        self.Hf_flag = seqm_parameters.get("Hf_flag", True)
+        self.sp2 = seqm_parameters.get("sp2", [False])
+        self._C = None  # eigenvectors of the previous step: warm start of the next density solve
+
+    def forward_packed(self, molecule, Pp):
+        plan = molecule._plan
+        const = molecule.const
+        t0 = time.time()
+        xyz = molecule._refresh_geometry()
+        w, hab = engine.op_pair_integrals(plan, xyz)
+        H = engine.op_hcore(plan, w, hab)
+        t0 = _timing(molecule, "Hcore + STO Integrals", t0)
+        F = engine.op_fock(plan, Pp, H, w)
+        if self.sp2[0]:
+            D, _ = engine.op_sp2_density(plan, F, self.sp2[1])
+            e_mo_n = None
+        else:
+            e_mo_n, D, self._C = engine.op_eig_density(plan, F, want_P=True, want_C=True, Cguess=self._C)
+        t0 = _timing(molecule, "D*", t0)
+        Eelec = engine.op_elec_energy_xl(plan, D, Pp, F, H)
+        EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)
+        g = engine.op_gradient_xl(plan, xyz, D, Pp)
+        force = torch.zeros((plan.nmol * plan.molsize, 3), dtype=torch.float64, device=plan.device)
+        force[plan.real_atoms] = -g
+        force = force.reshape(plan.nmol, plan.molsize, 3)
+        t0 = _timing(molecule, "Force", t0)
+        Etot = Eelec + Enuc
+        Eiso, eheat = _atom_sums(plan, const)
+        Hf = Etot - Eiso + (eheat if self.Hf_flag else 0.0)
+        molecule.w = w
+        return dict(force=force, D=D, Hf=Hf, Etot=Etot, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo_n=e_mo_n)
+
+    def forward(self, molecule, P, cis_amp=None, learned_parameters=dict(), xl_bomd_params=dict(), *args, **kwargs):
+        if xl_bomd_params and "max_rank" in xl_bomd_params:
+            raise NotImplementedError("KSA-XL-BOMD (max_rank) is not part of the B200 path")
+        plan = molecule._plan
+        r = self.forward_packed(molecule, engine.op_pack(plan, P))
+        Dd = engine.op_unpack(plan, r["D"])
+        _ground_dipole(molecule, Dd)
+        N = 4 * plan.molsize
+        if r["e_mo_n"] is not None:
+            e = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
+            e[:, : plan.nmax] = r["e_mo_n"]
+            lumo = plan.nocc.unsqueeze(1)
+            e_gap = (e.gather(1, lumo) - e.gather(1, lumo - 1)).reshape(-1)
+        else:
+            e, e_gap = None, torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
+        EEnt = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
+        return (r["force"], Dd, r["Hf"], r["Etot"], r["Eelec"], r["Enuc"], r["Eiso"], e, e_gap, EEnt, None, None, None)
+
+
+def _atom_sums(plan, const):
+    """Per-molecule sums of the isolated-atom electronic energies (energy.py:8-23) and heats of formation."""
+    Z = plan.Z
+    Eiso_atom = (
+        plan.parameter("U_ss") * const.ussc[Z] + plan.parameter("U_pp") * const.uppc[Z]
+        + plan.parameter("g_ss") * const.gssc[Z] + plan.parameter("g_pp") * const.gppc[Z]
+        + plan.parameter("g_sp") * const.gspc[Z] + plan.parameter("g_p2") * const.gp2c[Z]
+        + plan.parameter("h_sp") * const.hspc[Z]
+    )  # fmt: skip
+    z = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
+    return z.clone().index_add_(0, plan.atom_mol, Eiso_atom), z.clone().index_add_(0, plan.atom_mol, const.eheat[Z])
+
+
 class Force(torch.nn.Module):
     """Force.forward (basics.py:1260-1365): all three force modes of the reference (autograd,
     analytical, semi-numerical) compute the same Hellmann-Feynman gradient; one kernel serves them."""

@@ -187,12 +187,16 @@ SEQM_GLOBAL void pair_sum_kernel(seqm_batch_t b, const double* __restrict__ vals
 // pair_gradient_forward_kernel: same numbers, 3.5x the local-memory traffic; tests compare the two.
 SEQM_HD int cls_of(int kl) { return pack_class(kl); }
 
-SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* __restrict__ P,
+// Two densities: D multiplies the one-electron terms and (D - P/2) the two-electron terms built from P, which is
+// the XL-BOMD shadow energy  E = sum D o F(P) - 1/2 (F(P) - h) o P + E_nuc  (energy.py:76-88, xlbomd.py:430-447);
+// with D == P it is the ordinary SCF energy.  (No __restrict__ on D/P: they may alias.)
+SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* D, const double* P,
                                       double* __restrict__ gpair) {
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
     const int i = b.pair_i[p], j = b.pair_j[p];
     const MolView v = mol_view(b, b.atom_mol[i]);
     const double* Pm = P + v.mat0;
+    const double* Dm = D + v.mat0;
     const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
     const int ni = orb_cnt(v, i - v.a0), nj = orb_cnt(v, j - v.a0);
     const bool hi = ni == 4, hj = nj == 4;
@@ -202,7 +206,7 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
     const Dual1 r1(g.r, 1.0);
     double dEdr = 0.0, dEde[3] = {0.0, 0.0, 0.0};
 
-    // ---- resonance integrals: Q_mu,nu = P_mu,nu (beta_mu^A + beta_nu^B)
+    // ---- resonance integrals: Q_mu,nu = D_mu,nu (beta_mu^A + beta_nu^B)
     if (g.r <= SEQM_OVERLAP_CUTOFF) {
       const double bsi = par(b, SEQM_P_BS, i), bpi = par(b, SEQM_P_BP, i);
       const double bsj = par(b, SEQM_P_BS, j), bpj = par(b, SEQM_P_BP, j);
@@ -210,11 +214,11 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
       const double zsa = par(b, SEQM_P_ZS, i), zpa = par(b, SEQM_P_ZP, i);
       const double zsb = par(b, SEQM_P_ZS, j), zpb = par(b, SEQM_P_ZP, j);
       const Dual1 ss = sto_overlap(c_ovl, na, nb, 0, zsa, zsb, r1);
-      dEdr += Pm[oi * n + oj] * (bsi + bsj) * ss.d;
+      dEdr += Dm[oi * n + oj] * (bsi + bsj) * ss.d;
       if (hi) {
         const Dual1 os = sto_overlap(c_ovl, na, nb, 1, zpa, zsb, r1);
         for (int k = 0; k < 3; ++k) {
-          const double q = Pm[(oi + k + 1) * n + oj] * (bpi + bsj);
+          const double q = Dm[(oi + k + 1) * n + oj] * (bpi + bsj);
           dEdr += q * os.d * g.e[k];
           dEde[k] += q * os.v;
         }
@@ -222,7 +226,7 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
       if (hj) {
         const Dual1 so = sto_overlap(c_ovl, na, nb, 2, zsa, zpb, r1);
         for (int k = 0; k < 3; ++k) {
-          const double q = Pm[oi * n + oj + k + 1] * (bsi + bpj);
+          const double q = Dm[oi * n + oj + k + 1] * (bsi + bpj);
           dEdr += q * so.d * g.e[k];
           dEde[k] += q * so.v;
         }
@@ -233,12 +237,12 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
         const double bb = bpi + bpj;
         double tr = 0.0, qee = 0.0;
         for (int k = 0; k < 3; ++k) {
-          tr += Pm[(oi + k + 1) * n + oj + k + 1];
+          tr += Dm[(oi + k + 1) * n + oj + k + 1];
           double row = 0.0;
           for (int l = 0; l < 3; ++l) {
-            const double qs = Pm[(oi + k + 1) * n + oj + l + 1] + Pm[(oi + l + 1) * n + oj + k + 1];
+            const double qs = Dm[(oi + k + 1) * n + oj + l + 1] + Dm[(oi + l + 1) * n + oj + k + 1];
             row += qs * g.e[l];
-            qee += Pm[(oi + k + 1) * n + oj + l + 1] * g.e[k] * g.e[l];
+            qee += Dm[(oi + k + 1) * n + oj + l + 1] * g.e[k] * g.e[l];
           }
           dEde[k] += bb * (oo.v - pp.v) * row;
         }
@@ -251,7 +255,7 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
     const int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
     double Cm[10][10];
     {
-      double pa[10], pb[10];
+      double pa[10], pb[10], da[10], db[10];  // weighted packed diagonal blocks of P and D
       for (int kl = 0; kl < 10; ++kl) {
         int mu = 0;
         while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
@@ -259,17 +263,21 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
         const double wt = (mu == nu) ? 1.0 : 2.0;
         pa[kl] = (kl < nA) ? wt * Pm[(oi + mu) * n + oi + nu] : 0.0;
         pb[kl] = (kl < nB) ? wt * Pm[(oj + mu) * n + oj + nu] : 0.0;
+        da[kl] = (kl < nA) ? wt * Dm[(oi + mu) * n + oi + nu] : 0.0;
+        db[kl] = (kl < nB) ? wt * Dm[(oj + mu) * n + oj + nu] : 0.0;
       }
       const double ti = par(b, SEQM_P_TORE, i), tj = par(b, SEQM_P_TORE, j);
       for (int kl = 0; kl < nA; ++kl)
-        for (int mn = 0; mn < nB; ++mn) Cm[kl][mn] = pa[kl] * pb[mn];
-      for (int kl = 0; kl < nA; ++kl) Cm[kl][0] -= tj * pa[kl];
-      for (int mn = 0; mn < nB; ++mn) Cm[0][mn] -= ti * pb[mn];
+        for (int mn = 0; mn < nB; ++mn)
+          Cm[kl][mn] = (da[kl] - 0.5 * pa[kl]) * pb[mn] + pa[kl] * (db[mn] - 0.5 * pb[mn]);
+      for (int kl = 0; kl < nA; ++kl) Cm[kl][0] -= tj * da[kl];
+      for (int mn = 0; mn < nB; ++mn) Cm[0][mn] -= ti * db[mn];
       for (int mu = 0; mu < ni; ++mu)
         for (int nu = 0; nu < ni; ++nu)
           for (int la = 0; la < nj; ++la)
             for (int sg = 0; sg < nj; ++sg)
-              Cm[pack2(mu, nu)][pack2(la, sg)] -= 0.5 * Pm[(oi + mu) * n + oj + la] * Pm[(oi + nu) * n + oj + sg];
+              Cm[pack2(mu, nu)][pack2(la, sg)] -=
+                  (Dm[(oi + mu) * n + oj + la] - 0.5 * Pm[(oi + mu) * n + oj + la]) * Pm[(oi + nu) * n + oj + sg];
     }
     Dual1 ri[22];
     local_integrals(r1, load_multipole(b, i), load_multipole(b, j), nint, ri);
@@ -415,4 +423,19 @@ SEQM_GLOBAL void atom_gradient_kernel(seqm_batch_t b, const double* __restrict__
     grad[3 * a + 1] = gy;
     grad[3 * a + 2] = gz;
   }
+}
+
+// elec_energy_xl (energy.py:76-88): sum D o F - 1/2 (F - h) o P, one CTA per molecule
+SEQM_GLOBAL void elec_energy_xl_kernel(seqm_batch_t b, const double* __restrict__ D, const double* __restrict__ P,
+                                       const double* __restrict__ F, const double* __restrict__ H, double* __restrict__ E) {
+  __shared__ double red[33];
+  const MolView v = mol_view(b, b.mol_order[blockIdx.x]);
+  const int nn = v.n * v.n;
+  double s = 0.0;
+  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+    const double f = F[v.mat0 + t];
+    s += D[v.mat0 + t] * f - 0.5 * (f - H[v.mat0 + t]) * P[v.mat0 + t];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) E[v.m] = s;
 }

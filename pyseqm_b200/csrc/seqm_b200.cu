@@ -382,7 +382,7 @@ int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, dou
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, pair_scratch));
+    PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, P, pair_scratch));
     rc = seqm_check_launch("pair_gradient_kernel");
     if (rc) return rc;
   }
@@ -407,6 +407,25 @@ int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void*
   if (rc) return rc;
   SEQM_LAUNCH(orbitals_dense_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, C, V);
   return seqm_check_launch("orbitals_dense_kernel");
+}
+int seqm_gradient_xl(const seqm_batch_t* b, const double* xyz, const double* D, const double* P, double* pair_scratch,
+                     double* grad, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (b->npairs > 0) {
+    PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, D, P, pair_scratch));
+    rc = seqm_check_launch("pair_gradient_kernel");
+    if (rc) return rc;
+  }
+  PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad));
+  return seqm_check_launch("atom_gradient_kernel");
+}
+int seqm_elec_energy_xl(const seqm_batch_t* b, const double* D, const double* P, const double* F, const double* H,
+                        double* Eelec, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  PROF(PK_OTHER, SEQM_STREAM(stream), SEQM_LAUNCH(elec_energy_xl_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, D, P, F, H, Eelec));
+  return seqm_check_launch("elec_energy_xl_kernel");
 }
 int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
                           void* stream) {

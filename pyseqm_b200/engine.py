@@ -204,6 +204,19 @@ def op_gradient(plan, xyz, P, forward_mode=False):
     return g
 
 
+def op_gradient_xl(plan, xyz, D, P):
+    scratch = torch.zeros((max(plan.npairs, 1), 3), dtype=torch.float64, device=plan.device)
+    g = torch.zeros((plan.nat, 3), dtype=torch.float64, device=plan.device)
+    plan.lib.check(plan.lib.dll.seqm_gradient_xl(plan.ref, ptr(xyz), ptr(D), ptr(P), ptr(scratch), ptr(g), stream_of(g)), "seqm_gradient_xl")
+    return g
+
+
+def op_elec_energy_xl(plan, D, P, F, H):
+    E = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
+    plan.lib.check(plan.lib.dll.seqm_elec_energy_xl(plan.ref, ptr(D), ptr(P), ptr(F), ptr(H), ptr(E), stream_of(E)), "seqm_elec_energy_xl")
+    return E
+
+
 def op_orbitals_dense(plan, Cm):
     V = torch.empty((plan.nmol, plan.nmax, plan.nmax), dtype=torch.float64, device=plan.device)
     plan.lib.check(plan.lib.dll.seqm_orbitals_dense(plan.ref, ptr(Cm), ptr(V), stream_of(V)), "seqm_orbitals_dense")

@@ -1,0 +1,118 @@
+"""XL-BOMD / BOMD: oracle against reference-generated trajectories (CPU), the kernels through host emulation
+(CPU) and the CUDA path (GPU).  Fixtures: tools/make_golden_md.py drove the unmodified reference's XL_BOMD
+(eigensolver branch, xlbomd.py:361) and Molecular_Dynamics_Basic step by step."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+CASES = ["md_xl_bomd_methane_k6", "md_xl_bomd_mixed_k4", "md_basic_methanal", "md_xl_bomd_coronene_k6"]
+
+
+def load_md(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    g["seqm_parameters"] = json.loads(str(g["seqm_parameters"]))
+    g["k"] = int(g["k"])
+    return g
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_md_matches_reference(name):
+    import seqm_oracle as so
+
+    g = load_md(name)
+    out = so.run_md(g["species"], g["coordinates0"], g["velocities0"], g["seqm_parameters"], float(g["timestep"]),
+                    int(g["steps"]), None if g["k"] < 0 else g["k"])  # fmt: skip
+    assert np.abs(out["Etot"] - g["Etot"]).max() < 1e-6
+    assert np.abs(out["Ek"] - g["Ek"]).max() < 1e-6
+    assert np.abs(out["coordinates"] - g["coordinates"]).max() < 1e-7
+    assert np.abs(out["force"] - g["force"]).max() < 1e-5
+    assert np.abs(out["dm"] - g["dm"]).max() < 1e-8
+
+
+def run_product(lib, device, g):
+    import pyseqm_b200 as seqm
+
+    torch.set_default_dtype(torch.float64)
+    sp = dict(g["seqm_parameters"])
+    mol = seqm.Molecule(seqm.Constants().to(device), sp, torch.as_tensor(g["coordinates0"], device=device).clone(),
+                        torch.as_tensor(g["species"], device=device), _lib=lib)  # fmt: skip
+    mol.velocities = torch.as_tensor(g["velocities0"], device=device).clone()
+    if g["k"] > 0:
+        md = seqm.XL_BOMD(xl_bomd_params={"k": g["k"]}, seqm_parameters=sp, timestep=float(g["timestep"]), Temp=float(g["temp"]))
+    else:
+        md = seqm.Molecular_Dynamics_Basic(seqm_parameters=sp, timestep=float(g["timestep"]), Temp=float(g["temp"]))
+    md.run(mol, int(g["steps"]))
+    Etot = torch.stack(md.history["Etot"]).cpu().numpy()
+    Ek = torch.stack(md.history["Ek"]).cpu().numpy()
+    assert np.abs(Etot - g["Etot"]).max() < 1e-6
+    assert np.abs(Ek - g["Ek"]).max() < 1e-6
+    assert np.abs(mol.coordinates.detach().cpu().numpy() - g["coordinates"]).max() < 1e-8
+    assert np.abs(mol.force.cpu().numpy() - g["force"]).max() < 1e-5
+    assert np.abs(mol.dm.cpu().numpy() - g["dm"]).max() < 1e-8
+    return mol, md
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_hostemu_md(name):
+    from helpers import hostemu_lib
+
+    run_product(hostemu_lib(), torch.device("cpu"), load_md(name))
+
+
+def test_hostemu_xl_forward_public_api():
+    """Electronic_Structure.forward(dm_prop='XL-BOMD', P0=P) with the dense padded field, as the reference's
+    XL_BOMD.one_step calls it (MolecularDynamics.py:1487-1496), against the oracle."""
+    import seqm_oracle as so
+    from helpers import hostemu_lib, run_molecule
+
+    g = load_md("md_xl_bomd_mixed_k4")
+    sp = g["seqm_parameters"]
+    ref0 = so.single_point(g["species"], g["coordinates0"], sp)
+    x1 = g["coordinates0"] + 0.01 * np.random.default_rng(0).normal(size=g["coordinates0"].shape) * (g["species"] > 0)[:, :, None]
+    ref = so.xl_forward(g["species"], x1, sp, ref0["dm"])
+    import pyseqm_b200 as seqm
+
+    lib = hostemu_lib()
+    mol = seqm.Molecule(seqm.Constants(), dict(sp), torch.as_tensor(x1), torch.as_tensor(g["species"]), _lib=lib)
+    es = seqm.Electronic_Structure(dict(sp))
+    es(mol, P0=torch.as_tensor(ref0["dm"]).clone(), dm_prop="XL-BOMD", xl_bomd_params={"k": 4})
+    assert np.abs(mol.Etot.numpy() - ref["Etot"]).max() < 1e-6
+    assert np.abs(mol.dm.numpy() - ref["dm"]).max() < 1e-8
+    assert np.abs(mol.force.numpy() - ref["force"]).max() < 1e-5
+    assert np.abs(mol.e_gap.numpy() - ref["e_gap"]).max() < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_md(name):
+    from helpers import cuda_lib
+
+    run_product(cuda_lib(), torch.device("cuda:0"), load_md(name))
+
+
+@pytest.mark.gpu
+def test_gpu_xl_bomd_energy_conservation_replicas():
+    """64 coronene replicas, 40 XL-BOMD steps: every replica conserves E(total) within the reference's drift tolerance and the
+    replicas stay independent (identical replicas give identical trajectories)."""
+    import pyseqm_b200 as seqm
+    from helpers import cuda_lib
+
+    torch.set_default_dtype(torch.float64)
+    dev = torch.device("cuda:0")
+    s, c = seqm.read_xyz([os.path.join(GOLDEN, "xyz", "coronene.xyz")] * 64)
+    sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2]}
+    mol = seqm.Molecule(seqm.Constants().to(dev), sp, torch.as_tensor(c, device=dev), torch.as_tensor(s, device=dev), _lib=cuda_lib())
+    torch.manual_seed(0)
+    md = seqm.XL_BOMD(xl_bomd_params={"k": 6}, seqm_parameters=sp, timestep=0.4, Temp=300.0)
+    md.set_dof(mol)
+    md.initialize_velocity(mol)
+    mol.velocities[1] = mol.velocities[0]  # two identical replicas
+    md.run(mol, 40)
+    E = (torch.stack(md.history["Etot"]) + torch.stack(md.history["Ek"])).cpu().numpy()
+    assert np.abs(E - E[0]).max() < 5e-2  # the reference's own drift tolerance (tests/unit/test_md_suite.py:232)
+    assert np.abs(E[:, 0] - E[:, 1]).max() < 1e-9
