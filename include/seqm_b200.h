@@ -68,7 +68,8 @@ typedef struct seqm_batch {
 
 int seqm_abi_version(void);
 const char* seqm_last_error(void);
-/* largest orbital count a single molecule may have in this build (shared-memory resident solvers) */
+/* largest orbital count for the shared-memory resident solvers (Jacobi eigensolver, in-SM SP2, in-SM DIIS);
+ * larger molecules run the global-memory Fock / GEMM-SP2 / GEMM-DIIS path and need sp2=[True, eps] */
 int seqm_max_orbitals(void);
 
 /* cal_par.py:11-28,112-169,198-257 + two_elec_two_center_int.py:116-247: dd, qq, rho0, rho1, rho2 per atom */
@@ -94,6 +95,13 @@ int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* 
 /* SP2() -- SP2.py:9-85 at each molecule's own size; P packed; niter optional [nmol] */
 int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter,
                      const int32_t* active, void* stream);
+
+/* SP2 for molecules of any size (n > seqm_max_orbitals(), e.g. C380 with 1520 orbitals): X^2 by the library's
+ * register-tiled FP64 GEMM, one molecule at a time; workspace of seqm_sp2_large_workspace_bytes() bytes;
+ * niter_host: optional HOST array [nmol].  Blocks the host (one 64-byte read-back per SP2 iteration). */
+int64_t seqm_sp2_large_workspace_bytes(const seqm_batch_t* b);
+int seqm_sp2_density_large(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter_host,
+                           void* workspace, void* stream);
 
 /* elec_energy() -- energy.py:26-53 */
 int seqm_elec_energy(const seqm_batch_t* b, const double* P, const double* H, const double* F, double* Eelec,

@@ -84,6 +84,8 @@ class SeqmLib:
             "seqm_fock": ([B, P, P, P, P, P, P], C.c_int),
             "seqm_eig_density": ([B, P, P, P, P, P, P, P], C.c_int),
             "seqm_sp2_density": ([B, P, P, C.c_double, P, P, P], C.c_int),
+            "seqm_sp2_large_workspace_bytes": ([B], C.c_int64),
+            "seqm_sp2_density_large": ([B, P, P, C.c_double, C.POINTER(C.c_int32), P, P], C.c_int),
             "seqm_elec_energy": ([B, P, P, P, P, P, P], C.c_int),
             "seqm_nuclear_energy": ([B, P, P, P, P, P], C.c_int),
             "seqm_gradient": ([B, P, P, P, P, P], C.c_int),

@@ -39,6 +39,11 @@ class Energy(torch.nn.Module):
             raise NotImplementedError("pass learned parameters (dict of (nat,) tensors) to Molecule(...), not to forward()")
         plan = molecule._plan
         const = molecule.const
+        if plan.large and not self.sp2[0]:
+            raise NotImplementedError(
+                f"a molecule with {plan.nmax} orbitals exceeds the shared-memory resident eigensolver "
+                f"({plan.lib.dll.seqm_max_orbitals()} orbitals): use the SP2 density, sp2=[True, eps]"
+            )
         t0 = time.time()
         xyz = molecule._refresh_geometry()
         # hcore(): pair integrals + Hcore assembly
@@ -61,7 +66,22 @@ class Energy(torch.nn.Module):
         self.notconverged = notconv
         molecule.w = w
         molecule._gam = w[:, 0, 0]
-        if self.eig:
+        if self.eig and plan.large:
+            # final eigenpairs of a large molecule: one cuSOLVER call outside the SCF hot loop
+            Fd = engine.op_unpack(plan, F)
+            N = 4 * plan.molsize
+            e_mo = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
+            V = torch.zeros((plan.nmol, plan.nmax, plan.nmax), dtype=torch.float64, device=plan.device)
+            for m in range(plan.nmol):
+                nh, ny = int(plan.nheavy[m]), int(plan.nhyd[m])
+                idx = torch.cat([torch.arange(4 * nh, device=plan.device), 4 * nh + 4 * torch.arange(ny, device=plan.device)])
+                ev, vec = torch.linalg.eigh(Fd[m][idx][:, idx])
+                e_mo[m, : idx.numel()] = ev
+                V[m, : idx.numel(), : idx.numel()] = vec
+            lumo = plan.nocc.unsqueeze(1)
+            e_gap = (e_mo.gather(1, lumo) - e_mo.gather(1, lumo - 1)).reshape(-1)
+            molecule.molecular_orbitals = V
+        elif self.eig:
             # eigenpairs of the converged Fock matrix, warm-started from the last SCF eigenbasis
             e_mo_n, _, Cm = engine.op_eig_density(plan, F, want_P=False, want_C=True,
                                                   Cguess=Clast if self.warm_start else None)  # fmt: skip

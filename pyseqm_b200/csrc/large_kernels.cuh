@@ -1,0 +1,292 @@
+// large_kernels.cuh -- path for molecules whose matrices do not fit one SM's shared memory (n > SEQM_MAX_ORB),
+// e.g. the C380 fullerene (n = 1520, BASELINE configs[3]).  The density comes from SP2 purification
+// (SP2.py:9-85), which is a chain of dense symmetric X^2 products: a register-tiled FP64 GEMM on the CUDA cores.
+// (tcgen05 has no FP64 kind and B200's FP64 DMMA rate equals its FMA rate, so the tensor path buys nothing.)
+//   dgemm_kernel            C = A B, row-major, 128x128x8 CTA tile, 8x8 per thread, double-buffered shared tiles
+//   fock_large_*            Fock build with P, H, F in global memory (grid over all pairs / atoms of the batch)
+//   sp2_* / commutator_*    element-wise pieces of SP2 and of the DIIS residual around the GEMM
+#pragma once
+#include "common.cuh"
+
+#define SEQM_GEMM_BM 128
+#define SEQM_GEMM_BN 128
+#define SEQM_GEMM_BK 8
+
+// C[M x N] = A[M x K] * B[K x N], all row-major with leading dimensions lda/ldb/ldc.
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) dgemm_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
+                                                       const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc) {
+#ifndef SEQM_HOSTEMU
+  __shared__ double sA[2][SEQM_GEMM_BK][SEQM_GEMM_BM + 4];  // A tile stored k-major (transposed) for conflict-free reads
+  __shared__ double sB[2][SEQM_GEMM_BK][SEQM_GEMM_BN + 4];
+  const int tid = threadIdx.x;
+  const int nbx = (N + SEQM_GEMM_BN - 1) / SEQM_GEMM_BN;
+  const int bm = (blockIdx.x / nbx) * SEQM_GEMM_BM, bn = (blockIdx.x % nbx) * SEQM_GEMM_BN;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 8 x 8 outputs (rows ty + 16 i, cols tx + 16 j)
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  // global -> register staging: A tile 128 x 8 (1024 doubles, 4 per thread), B tile 8 x 128 (4 per thread)
+  double ra[4], rb[4];
+  const int a_row = tid >> 1, a_col = (tid & 1) * 4;   // thread loads 4 consecutive k of one A row
+  const int b_row = tid >> 5, b_col = (tid & 31) * 4;  // thread loads 4 consecutive columns of one B row
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = bm + a_row, c = k0 + a_col + q;
+      ra[q] = (r < M && c < K) ? A[(long long)r * lda + c] : 0.0;
+      const int rr = k0 + b_row, cc = bn + b_col + q;
+      rb[q] = (rr < K && cc < N) ? B[(long long)rr * ldb + cc] : 0.0;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sA[buf][a_col + q][a_row] = ra[q];
+      sB[buf][b_row][b_col + q] = rb[q];
+    }
+  };
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += SEQM_GEMM_BK) {
+    const bool more = (k0 + SEQM_GEMM_BK) < K;
+    if (more) load_tiles(k0 + SEQM_GEMM_BK);
+#pragma unroll
+    for (int kk = 0; kk < SEQM_GEMM_BK; ++kk) {
+      double av[8], bv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) av[i] = sA[buf][kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = sB[buf][kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] += av[i] * bv[j];
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = bm + ty + 16 * i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = bn + tx + 16 * j;
+      if (c < N) C[(long long)r * ldc + c] = acc[i][j];
+    }
+  }
+#else
+  // host emulation: one "thread" per CTA tile
+  const int nbx = (N + SEQM_GEMM_BN - 1) / SEQM_GEMM_BN;
+  const int bm = (blockIdx.x / nbx) * SEQM_GEMM_BM, bn = (blockIdx.x % nbx) * SEQM_GEMM_BN;
+  for (int r = bm; r < bm + SEQM_GEMM_BM && r < M; ++r)
+    for (int c = bn; c < bn + SEQM_GEMM_BN && c < N; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < K; ++k) s += A[(long long)r * lda + k] * B[(long long)k * ldb + c];
+      C[(long long)r * ldc + c] = s;
+    }
+#endif
+}
+
+// ---- Fock build with everything in global memory -------------------------------------------------------
+// off-diagonal blocks: one work item per (pair, mu, lambda)
+SEQM_GLOBAL void fock_large_offdiag_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,
+                                           const double* __restrict__ w, double* __restrict__ F,
+                                           const int32_t* __restrict__ active) {
+  const long long total = (long long)b.npairs * 16;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(t >> 4), mu = (int)((t >> 2) & 3), la = (int)(t & 3);
+    const int gi = b.pair_i[p], gj = b.pair_j[p];
+    const int m = b.atom_mol[gi];
+    if (active && !active[m]) continue;
+    const MolView v = mol_view(b, m);
+    const int i = gi - v.a0, j = gj - v.a0;
+    const int ni = orb_cnt(v, i), nj = orb_cnt(v, j);
+    if (mu >= ni || la >= nj) continue;
+    const int n = v.n, oi = orb_off(v, i), oj = orb_off(v, j);
+    const double* Pm = P + v.mat0;
+    const double* wp = w + (long long)p * 100;
+    double k = 0.0;
+    for (int nu = 0; nu < ni; ++nu)
+      for (int sg = 0; sg < nj; ++sg)
+        k += Pm[(long long)(oi + nu) * n + oj + sg] * wp[pack2(mu, nu) * 10 + pack2(la, sg)];
+    const long long r = oi + mu, c = oj + la;
+    const double f = H[v.mat0 + r * n + c] - 0.5 * k;
+    F[v.mat0 + r * n + c] = f;
+    F[v.mat0 + c * n + r] = f;
+  }
+}
+// diagonal blocks: one WARP-sized group per (atom, packed kl) would be ideal; a thread per item loops over the
+// partner atoms (380 for C380), which is ample parallelism (nat*10 items) for the large path
+SEQM_GLOBAL void fock_large_diag_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,
+                                        const double* __restrict__ w, double* __restrict__ F,
+                                        const int32_t* __restrict__ active) {
+  const long long total = (long long)b.nat * 10;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int ga = (int)(t / 10), kl = (int)(t % 10);
+    const int m = b.atom_mol[ga];
+    if (active && !active[m]) continue;
+    const MolView v = mol_view(b, m);
+    const int a = ga - v.a0;
+    if (a >= v.nheavy && kl > 0) continue;
+    int mu = 0;
+    while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
+    const int nu = kl - mu * (mu + 1) / 2;
+    const int n = v.n, oa = orb_off(v, a);
+    const double* Pm = P + v.mat0;
+#define PM(r, c) Pm[(long long)(r) * n + (c)]
+    const double gss = par(b, SEQM_P_GSS, ga), gsp = par(b, SEQM_P_GSP, ga), gpp = par(b, SEQM_P_GPP, ga);
+    const double gp2 = par(b, SEQM_P_GP2, ga), hsp = par(b, SEQM_P_HSP, ga);
+    const double Pss = PM(oa, oa);
+    double Ppt = 0.0;
+    if (a < v.nheavy) Ppt = PM(oa + 1, oa + 1) + PM(oa + 2, oa + 2) + PM(oa + 3, oa + 3);
+    double g;
+    if (mu == 0)
+      g = 0.5 * Pss * gss + Ppt * (gsp - 0.5 * hsp);
+    else if (nu == 0)
+      g = PM(oa, oa + mu) * (1.5 * hsp - 0.5 * gsp);
+    else if (mu == nu) {
+      const double Pk = PM(oa + mu, oa + mu);
+      g = Pss * (gsp - 0.5 * hsp) + 0.5 * Pk * gpp + (Ppt - Pk) * (1.25 * gp2 - 0.25 * gpp);
+    } else
+      g = PM(oa + nu, oa + mu) * (0.75 * gpp - 1.25 * gp2);
+    for (int o = 0; o < v.na; ++o) {
+      if (o == a) continue;
+      const int oo = orb_off(v, o), no = orb_cnt(v, o);
+      const bool first = a < o;
+      const double* wp = w + (long long)(v.p0 + (first ? pair_local(v, a, o) : pair_local(v, o, a))) * 100;
+      const int sk = first ? 10 : 1, sm = first ? 1 : 10;
+      double j = PM(oo, oo) * wp[kl * sk];
+      if (no == 4) {
+        for (int x = 1; x < 4; ++x) {
+          j += 2.0 * PM(oo, oo + x) * wp[kl * sk + pack2(x, 0) * sm];
+          for (int y = 1; y <= x; ++y) j += (x == y ? 1.0 : 2.0) * PM(oo + y, oo + x) * wp[kl * sk + pack2(x, y) * sm];
+        }
+      }
+      g += j;
+    }
+#undef PM
+    const long long r = oa + mu, c = oa + nu;
+    const double f = H[v.mat0 + r * n + c] + g;
+    F[v.mat0 + r * n + c] = f;
+    F[v.mat0 + c * n + r] = f;
+  }
+}
+
+// ---- SP2 pieces (one molecule at a time; state in a small device struct) ---------------------------------
+struct Sp2State {
+  double h1, hN, tr, tr2, errm0, errm1, nocc;
+  int take_sq, done, iters, pad;
+};
+// Gershgorin bounds: one CTA, rows strided over threads
+SEQM_GLOBAL void sp2_bounds_kernel(int n, const double* __restrict__ Fm, double nocc, Sp2State* st) {
+  __shared__ double red[33];
+  double lo = 1.0e300, hi = -1.0e300;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double r = 0.0;
+    for (int j = 0; j < n; ++j) r += fabs(Fm[(long long)i * n + j]);
+    const double aii = Fm[(long long)i * n + i];
+    r -= fabs(aii);
+    lo = fmin(lo, aii - r);
+    hi = fmax(hi, aii + r);
+  }
+  const double hN = block_max(hi, red);
+  const double h1 = -block_max(-lo, red);
+  if (threadIdx.x == 0) {
+    st->h1 = h1;
+    st->hN = hN;
+    st->nocc = nocc;
+    st->done = 0;
+    st->iters = 0;
+  }
+}
+SEQM_GLOBAL void sp2_init_kernel(int n, const double* __restrict__ Fm, double* __restrict__ X, const Sp2State* st) {
+  const double h1 = st->h1, hN = st->hN;
+  const long long nn = (long long)n * n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / n), j = (int)(t % n);
+    X[t] = (((i == j) ? hN : 0.0) - Fm[t]) / (hN - h1);
+  }
+}
+// traces of X and X2 (one CTA), then the SP2 branch decision and convergence bookkeeping (SP2.py:55-83)
+SEQM_GLOBAL void sp2_trace_kernel(int n, const double* __restrict__ X, const double* __restrict__ X2, Sp2State* st,
+                                  double eps, int first) {
+  __shared__ double red[33];
+  double a = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    a += X[(long long)i * n + i];
+    if (X2) c += X2[(long long)i * n + i];
+  }
+  a = block_sum(a, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    if (first) {  // trace of X0
+      st->tr = a;
+      st->errm0 = fabs(a - st->nocc);
+      st->errm1 = st->errm0;
+    } else if (X2) {  // decide the branch from tr X and tr X^2
+      st->tr2 = c;
+      st->take_sq = (fabs(c - st->nocc) < fabs(2.0 * st->tr - c - st->nocc)) ? 1 : 0;
+    } else {  // after the update: re-summed trace of the new X, error history, stop test
+      st->tr = a;
+      st->errm1 = st->errm0;
+      st->errm0 = fabs(a - st->nocc);
+      st->iters += 1;
+      if ((st->errm0 < eps && st->errm1 < eps) || st->iters >= 10000) st->done = 1;
+    }
+  }
+}
+SEQM_GLOBAL void sp2_update_kernel(int n, double* __restrict__ X, const double* __restrict__ X2, const Sp2State* st) {
+  const int sq = st->take_sq;
+  const long long nn = (long long)n * n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x)
+    X[t] = sq ? X2[t] : 2.0 * X[t] - X2[t];
+}
+SEQM_GLOBAL void scale_copy_kernel(long long nn, const double* __restrict__ X, double* __restrict__ out, double s) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x)
+    out[t] = s * X[t];
+}
+
+// ---- DIIS residual for a large molecule: R = FP - (FP)^t from the GEMM result G = F P ----------------------
+SEQM_GLOBAL void commutator_kernel(int n, const double* __restrict__ G, double* __restrict__ R, double* __restrict__ rmax_out) {
+  __shared__ double red[33];
+  double rmax = 0.0;
+  const long long nn = (long long)n * n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / n), j = (int)(t % n);
+    const double r = G[t] - G[(long long)j * n + i];
+    R[t] = r;
+    rmax = fmax(rmax, fabs(r));
+  }
+  rmax = block_max(rmax, red);
+  if (threadIdx.x == 0) {
+    // max over CTAs through an ordered-int atomic max (values are non-negative doubles)
+#ifndef SEQM_HOSTEMU
+    atomicMax(reinterpret_cast<unsigned long long*>(rmax_out), (unsigned long long)__double_as_longlong(rmax));
+#else
+    if (rmax > *rmax_out) *rmax_out = rmax;
+#endif
+  }
+}
+// dots[q] = sum_{i<j} R[i][j] * Rq[i][j] for the cF stored residuals (one CTA per q)
+SEQM_GLOBAL void residual_dots_kernel(int n, const double* __restrict__ R, const double* __restrict__ hist, long long stride,
+                                      double* __restrict__ emat_row) {
+  __shared__ double red[33];
+  const int q = blockIdx.x;
+  const double* Rq = hist + (long long)q * stride;
+  double s = 0.0;
+  const long long nn = (long long)n * n;
+  for (long long t = threadIdx.x; t < nn; t += blockDim.x) {
+    const int i = (int)(t / n), j = (int)(t % n);
+    if (j > i) s += R[t] * Rq[t];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) emat_row[q] = s;
+}

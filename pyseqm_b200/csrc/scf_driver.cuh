@@ -5,6 +5,7 @@
 #pragma once
 #include "eig_kernels.cuh"
 #include "fock_kernels.cuh"
+#include "large_kernels.cuh"
 
 #define SEQM_NFOCK 10
 #define SEQM_EM (SEQM_NFOCK + 1)
@@ -23,6 +24,9 @@ struct ScfWork {  // carved out of the caller's workspace
   int32_t* active;
   ScfCtrl* ctrl;
   int has_C;
+  // large-molecule path (n > SEQM_MAX_ORB): SP2 / commutator scratch for one molecule at a time
+  double *Xl, *X2l, *rmax, *part;
+  Sp2State* sp2st;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -60,6 +64,14 @@ static size_t scf_carve(const seqm_batch_t* b, const seqm_scf_opts_t* o, unsigne
   w.Eel_run = (double*)take(nm);
   w.active = (int32_t*)take(sizeof(int32_t) * (size_t)b->nmol);
   w.ctrl = (ScfCtrl*)take(sizeof(ScfCtrl));
+  if (b->nmax > SEQM_MAX_ORB) {
+    const size_t big = sizeof(double) * (size_t)b->nmax * b->nmax;
+    w.Xl = (double*)take(big);
+    w.X2l = (double*)take(big);
+    w.rmax = (double*)take(sizeof(double));
+    w.part = (double*)take(sizeof(double) * 3 * 4096);
+    w.sp2st = (Sp2State*)take(sizeof(Sp2State));
+  }
   if (W) *W = w;
   return off;
 }
@@ -358,6 +370,27 @@ SEQM_GLOBAL void adaptive_apply_kernel(seqm_batch_t b, ScfWork W, double* __rest
   }
 }
 
+// get_error bookkeeping of one molecule (scf_loop.py:106-147), executed by a single thread
+SEQM_D void finalize_error(const seqm_batch_t& b, const ScfWork& W, int mol, double e, double d2, double dmax,
+                           int32_t* notconv, double eps, int use_diis) {
+  const MolView v = mol_view(b, mol);
+  const double err = e - W.Eel_run[mol];
+  W.err[mol] = err;
+  bool bad = fabs(err) > eps;
+  if (use_diis) bad = bad || (W.diis_err[mol] > 50.0 * eps);
+  if (!bad) {
+    W.dm_err[mol] = sqrt(d2) / (double)(4 * v.nheavy + 4 * v.nhyd);
+    W.dm_elem[mol] = dmax;
+  }
+  const bool nc = bad || (W.dm_err[mol] > 2.0 * eps) || (W.dm_elem[mol] > 15.0 * eps);
+  W.Eel_new[mol] = e;
+  notconv[mol] = nc ? 1 : 0;
+  if (nc) {
+    W.Eel_run[mol] = e;
+    seqm_atomic_add(&W.ctrl->nnot, 1);
+  }
+}
+
 // get_error (scf_loop.py:106-147) fused with elec_energy of the new density; one CTA per molecule.
 SEQM_GLOBAL void energy_error_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ P, const double* __restrict__ H,
                                      const double* __restrict__ F, int32_t* __restrict__ notconv, double eps,
@@ -378,23 +411,60 @@ SEQM_GLOBAL void energy_error_kernel(seqm_batch_t b, ScfWork W, const double* __
   e = 0.5 * block_sum(e, red);
   d2 = block_sum(d2, red);
   dmax = block_max(dmax, red);
-  if (threadIdx.x == 0) {
-    const double err = e - W.Eel_run[mol];
-    W.err[mol] = err;
-    bool bad = fabs(err) > eps;
-    if (use_diis) bad = bad || (W.diis_err[mol] > 50.0 * eps);
-    if (!bad) {
-      W.dm_err[mol] = sqrt(d2) / (double)(4 * v.nheavy + 4 * v.nhyd);
-      W.dm_elem[mol] = dmax;
-    }
-    const bool nc = bad || (W.dm_err[mol] > 2.0 * eps) || (W.dm_elem[mol] > 15.0 * eps);
-    W.Eel_new[mol] = e;
-    notconv[mol] = nc ? 1 : 0;
-    if (nc) {
-      W.Eel_run[mol] = e;
-      seqm_atomic_add(&W.ctrl->nnot, 1);
-    }
+  if (threadIdx.x == 0) finalize_error(b, W, mol, e, d2, dmax, notconv, eps, use_diis);
+}
+
+// ---- large molecules: the same three element-wise SCF pieces with a grid per molecule ----------------------
+SEQM_GLOBAL void extrapolate_large_kernel(long long nn, const double* __restrict__ coeff, const double* __restrict__ hist,
+                                          double* __restrict__ F, int cF) {
+  double c[SEQM_NFOCK];
+  for (int k = 0; k < cF; ++k) c[k] = coeff[k];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < cF; ++k) s += c[k] * hist[(long long)k * nn + t];
+    F[t] = s;
   }
+}
+SEQM_GLOBAL void mix_large_kernel(long long nn, double* __restrict__ P, double* __restrict__ Pold,
+                                  const double* __restrict__ Pnew, double a) {
+  const double oma = 1.0 - a;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x) {
+    const double p = P[t];
+    Pold[t] = p;
+    P[t] = (a == 0.0) ? Pnew[t] : a * p + oma * Pnew[t];
+  }
+}
+// per-CTA partial sums (fixed order, no atomics): part[cta] = {sum P(H+F), sum dP^2, max |dP|}
+SEQM_GLOBAL void energy_partial_kernel(long long nn, const double* __restrict__ P, const double* __restrict__ H,
+                                       const double* __restrict__ F, const double* __restrict__ Pold, double* __restrict__ part) {
+  __shared__ double red[33];
+  double e = 0.0, d2 = 0.0, dmax = 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x) {
+    const double p = P[t];
+    e += p * (H[t] + F[t]);
+    const double d = p - Pold[t];
+    d2 += d * d;
+    dmax = fmax(dmax, fabs(d));
+  }
+  e = block_sum(e, red);
+  d2 = block_sum(d2, red);
+  dmax = block_max(dmax, red);
+  if (threadIdx.x == 0) {
+    part[3 * blockIdx.x] = e;
+    part[3 * blockIdx.x + 1] = d2;
+    part[3 * blockIdx.x + 2] = dmax;
+  }
+}
+SEQM_GLOBAL void energy_finalize_kernel(seqm_batch_t b, ScfWork W, int mol, const double* __restrict__ part, int nparts,
+                                        int32_t* __restrict__ notconv, double eps, int use_diis) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double e = 0.0, d2 = 0.0, dmax = 0.0;
+  for (int k = 0; k < nparts; ++k) {
+    e += part[3 * k];
+    d2 += part[3 * k + 1];
+    dmax = fmax(dmax, part[3 * k + 2]);
+  }
+  finalize_error(b, W, mol, 0.5 * e, d2, dmax, notconv, eps, use_diis);
 }
 SEQM_GLOBAL void commit_active_kernel(seqm_batch_t b, ScfWork W, const int32_t* __restrict__ notconv) {
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < b.nmol; m += gridDim.x * blockDim.x)

@@ -12,10 +12,10 @@
 
 // ---- optional per-kernel timing (CUDA events on the launch stream; used by bench.py for the roofline) ----
 enum { PK_PAIR = 0, PK_HCORE, PK_FOCK, PK_JACOBI, PK_SP2, PK_DIIS_STORE, PK_DIIS_SOLVE, PK_DIIS_EXTRAP, PK_MIX,
-       PK_ENERGY_ERR, PK_NUC, PK_GRAD, PK_OTHER, PK_COUNT };
+       PK_ENERGY_ERR, PK_NUC, PK_GRAD, PK_OTHER, PK_GEMM, PK_COUNT };
 static const char* g_pk_names[PK_COUNT] = {"pair_integrals", "hcore", "fock", "jacobi_density", "sp2", "diis_store",
                                            "diis_solve", "diis_extrapolate", "mix", "energy_error", "nuclear_energy",
-                                           "gradient", "other"};
+                                           "gradient", "other", "dgemm"};
 static int g_prof_on = 0;
 #ifndef SEQM_HOSTEMU
 #define SEQM_PROF_MAX 32768
@@ -85,11 +85,106 @@ static int check_batch(const seqm_batch_t* b) {
     seqm_set_error("method %d not supported by this build (MNDO=0, AM1=1, PM3=2)", b->method);
     return SEQM_ERR_UNSUPPORTED;
   }
+  return ensure_device();
+}
+static int check_small(const seqm_batch_t* b, const char* what) {
   if (b->nmax > SEQM_MAX_ORB) {
-    seqm_set_error("molecule with %d orbitals exceeds the shared-memory resident limit of %d", b->nmax, SEQM_MAX_ORB);
+    seqm_set_error("%s: a molecule with %d orbitals exceeds the shared-memory resident limit of %d (large molecules: "
+                   "density by SP2 only, sp2=[True, eps])", what, b->nmax, SEQM_MAX_ORB);
     return SEQM_ERR_TOO_LARGE;
   }
-  return ensure_device();
+  return SEQM_OK;
+}
+
+static int grid1d(long long n, int block);
+// ---- large-molecule helpers (host side) ------------------------------------------------------------------
+struct HostMol { long long mat0; int n, nocc; };
+static int fetch_host_mols(const seqm_batch_t* b, HostMol* hm, cudaStream_t st) {
+  long long* m0 = new long long[b->nmol + 1];
+  int *nh = new int[b->nmol], *ny = new int[b->nmol], *no = new int[b->nmol];
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemcpyAsync(m0, b->mol_mat0, sizeof(long long) * (b->nmol + 1), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(nh, b->mol_nheavy, sizeof(int) * b->nmol, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ny, b->mol_nhyd, sizeof(int) * b->nmol, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(no, b->mol_nocc, sizeof(int) * b->nmol, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { seqm_set_error("fetch_host_mols: %s", cudaGetErrorString(e)); return SEQM_ERR_CUDA; }
+#else
+  (void)st;
+  memcpy(m0, b->mol_mat0, sizeof(long long) * (b->nmol + 1));
+  memcpy(nh, b->mol_nheavy, sizeof(int) * b->nmol);
+  memcpy(ny, b->mol_nhyd, sizeof(int) * b->nmol);
+  memcpy(no, b->mol_nocc, sizeof(int) * b->nmol);
+#endif
+  for (int m = 0; m < b->nmol; ++m) { hm[m].mat0 = m0[m]; hm[m].n = 4 * nh[m] + ny[m]; hm[m].nocc = no[m]; }
+  delete[] m0; delete[] nh; delete[] ny; delete[] no;
+  return SEQM_OK;
+}
+static int fetch_host_ints(const int32_t* dev, int32_t* host, int n, cudaStream_t st) {
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { seqm_set_error("fetch_host_ints: %s", cudaGetErrorString(e)); return SEQM_ERR_CUDA; }
+#else
+  (void)st;
+  memcpy(host, dev, sizeof(int32_t) * n);
+#endif
+  return SEQM_OK;
+}
+static int launch_gemm(int n, const double* A, const double* B, double* C, cudaStream_t st) {
+  const int nb = (n + SEQM_GEMM_BM - 1) / SEQM_GEMM_BM;
+  PROF(PK_GEMM, st, SEQM_LAUNCH(dgemm_kernel, nb * nb, 256, 0, st, n, n, n, A, n, B, n, C, n));
+  return seqm_check_launch("dgemm_kernel");
+}
+// SP2 purification of one large molecule: X, X2 scratch of n*n doubles, state on the device; P = 2 X.
+static int sp2_large_one(int n, int nocc, const double* Fm, double* Pm, double eps, double* X, double* X2, Sp2State* stt,
+                         int* iters_out, cudaStream_t st) {
+  if (eps > 1.0e-3) eps = 1.0e-3;
+  if (eps < 1.0e-7) eps = 1.0e-7;
+  const long long nn = (long long)n * n;
+  const int ge = grid1d(nn, 256);
+  SEQM_LAUNCH(sp2_bounds_kernel, 1, 1024, 0, st, n, Fm, (double)nocc, stt);
+  SEQM_LAUNCH(sp2_init_kernel, ge, 256, 0, st, n, Fm, X, (const Sp2State*)stt);
+  SEQM_LAUNCH(sp2_trace_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)nullptr, stt, eps, 1);
+  int rc = seqm_check_launch("sp2 setup");
+  if (rc) return rc;
+  for (int it = 0; it < 10000; ++it) {
+    rc = launch_gemm(n, X, X, X2, st);
+    if (rc) return rc;
+    PROF(PK_SP2, st, SEQM_LAUNCH(sp2_trace_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)X2, stt, eps, 0));
+    PROF(PK_SP2, st, SEQM_LAUNCH(sp2_update_kernel, ge, 256, 0, st, n, X, (const double*)X2, (const Sp2State*)stt));
+    PROF(PK_SP2, st, SEQM_LAUNCH(sp2_trace_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)nullptr, stt, eps, 0));
+    rc = seqm_check_launch("sp2 iteration");
+    if (rc) return rc;
+    Sp2State h;
+#ifndef SEQM_HOSTEMU
+    cudaError_t e = cudaMemcpyAsync(&h, stt, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { seqm_set_error("sp2 state read-back: %s", cudaGetErrorString(e)); return SEQM_ERR_CUDA; }
+#else
+    h = *stt;
+#endif
+    if (h.done) {
+      if (iters_out) *iters_out = h.iters;
+      break;
+    }
+  }
+  SEQM_LAUNCH(scale_copy_kernel, ge, 256, 0, st, nn, (const double*)X, Pm, 2.0);
+  return seqm_check_launch("scale_copy_kernel");
+}
+
+static int threads_for(int nmax);
+static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, const double* w, double* F,
+                       const int32_t* active, cudaStream_t st) {
+  if (b->nmax > SEQM_MAX_ORB) {  // matrices in global memory, grid over all pairs / atoms
+    if (b->npairs > 0)
+      PROF(PK_FOCK, st, SEQM_LAUNCH(fock_large_offdiag_kernel, grid1d((long long)b->npairs * 16, 256), 256, 0, st, *b, P, H, w, F, active));
+    PROF(PK_FOCK, st, SEQM_LAUNCH(fock_large_diag_kernel, grid1d((long long)b->nat * 10, 128), 128, 0, st, *b, P, H, w, F, active));
+    return seqm_check_launch("fock_large kernels");
+  }
+  const size_t smem = sizeof(double) * (size_t)b->nmax * b->nmax;
+  PROF(PK_FOCK, st, SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, st, *b, P, H, w, F, active));
+  return seqm_check_launch("fock_kernel");
 }
 static int diis_grid(int nmol) {
 #ifdef SEQM_HOSTEMU
@@ -334,14 +429,14 @@ int seqm_fock(const seqm_batch_t* b, const double* P, const double* H, const dou
               const int32_t* active, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
-  const size_t smem = sizeof(double) * (size_t)b->nmax * b->nmax;
-  PROF(PK_FOCK, SEQM_STREAM(stream), SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, P, H, w, F, active));
-  return seqm_check_launch("fock_kernel");
+  return launch_fock(b, P, H, w, F, active, SEQM_STREAM(stream));
 }
 
 int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const double* Cguess,
                      const int32_t* active, void* stream) {
   int rc = check_batch(b);
+  if (rc) return rc;
+  rc = check_small(b, "seqm_eig_density");
   if (rc) return rc;
   PROF(PK_JACOBI, SEQM_STREAM(stream), rc = launch_jacobi(b, F, P, evals, C, Cguess, active, SEQM_STREAM(stream)));
   return rc;
@@ -351,9 +446,36 @@ int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double e
                      void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
+  rc = check_small(b, "seqm_sp2_density");
+  if (rc) return rc;
   const size_t smem = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
   PROF(PK_SP2, SEQM_STREAM(stream), SEQM_LAUNCH(sp2_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, F, P, eps, niter, active));
   return seqm_check_launch("sp2_kernel");
+}
+
+int64_t seqm_sp2_large_workspace_bytes(const seqm_batch_t* b) {
+  return (int64_t)(2 * sizeof(double) * (size_t)b->nmax * b->nmax + 4096);
+}
+/* SP2 for molecules of any size: X^2 by the FP64 GEMM, one molecule at a time (blocks the host per iteration) */
+int seqm_sp2_density_large(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter_host,
+                           void* workspace, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  cudaStream_t st = SEQM_STREAM(stream);
+  HostMol* hm = new HostMol[b->nmol];
+  rc = fetch_host_mols(b, hm, st);
+  unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  const size_t big = (sizeof(double) * (size_t)b->nmax * b->nmax + 255) & ~(size_t)255;
+  double* X = (double*)base;
+  double* X2 = (double*)(base + big);
+  Sp2State* stt = (Sp2State*)(base + 2 * big);
+  for (int m = 0; m < b->nmol && !rc; ++m) {
+    int it = 0;
+    rc = sp2_large_one(hm[m].n, hm[m].nocc, F + hm[m].mat0, P + hm[m].mat0, eps, X, X2, stt, &it, st);
+    if (niter_host) niter_host[m] = it;
+  }
+  delete[] hm;
+  return rc;
 }
 
 int seqm_elec_energy(const seqm_batch_t* b, const double* P, const double* H, const double* F, double* Eelec,
@@ -503,8 +625,23 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   SEQM_LAUNCH(scf_init_kernel, gm, 128, 0, st, *b, W, o->converger);
   CHK("scf_init_kernel");
   // F(P0), Eelec(P0)
-  PROF(PK_FOCK, SEQM_STREAM(stream), SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)nullptr));
-  CHK("fock_kernel");
+  const bool large = b->nmax > SEQM_MAX_ORB;
+  HostMol* hm = nullptr;
+  int32_t* h_active = nullptr;
+  if (large) {
+    if (!o->use_sp2) {
+      seqm_set_error("molecules above %d orbitals need the SP2 density (sp2=[True, eps]); the batched Jacobi eigensolver "
+                     "is shared-memory resident", SEQM_MAX_ORB);
+      return SEQM_ERR_TOO_LARGE;
+    }
+    hm = new HostMol[b->nmol];
+    h_active = new int32_t[b->nmol];
+    rc = fetch_host_mols(b, hm, st);
+    if (rc) return rc;
+    for (int m = 0; m < b->nmol; ++m) h_active[m] = 1;
+  }
+  rc = launch_fock(b, P, H, w, F, (const int32_t*)nullptr, st);
+  if (rc) return rc;
   PROF(PK_OTHER, SEQM_STREAM(stream), SEQM_LAUNCH(elec_energy_kernel, b->nmol, 128, 0, st, *b, P, H, F, W.Eel_run, (const int32_t*)nullptr));
   CHK("elec_energy_kernel");
   int have_C = 0;
@@ -521,17 +658,62 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       if (nnot == 0) break;
       cF = (cF < SEQM_NFOCK) ? cF + 1 : SEQM_NFOCK;
       counter = (counter + 1) % SEQM_NFOCK;
-      PROF(PK_DIIS_STORE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF));
-      CHK("diis_store_kernel");
+      if (!large) {
+        PROF(PK_DIIS_STORE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF));
+        CHK("diis_store_kernel");
+      } else {
+        for (int m = 0; m < b->nmol; ++m) {
+          if (!h_active[m]) continue;
+          const int n = hm[m].n;
+          const long long nn = (long long)n * n, h0 = hm[m].mat0 * SEQM_NFOCK;
+          double* Fh = W.FOCK + h0 + (long long)counter * nn;
+          double* Rh = W.RES + h0 + (long long)counter * nn;
+#ifndef SEQM_HOSTEMU
+          cudaMemcpyAsync(Fh, F + hm[m].mat0, sizeof(double) * nn, cudaMemcpyDeviceToDevice, st);
+          cudaMemsetAsync(W.rmax, 0, sizeof(double), st);
+#else
+          memcpy(Fh, F + hm[m].mat0, sizeof(double) * nn);
+          *W.rmax = 0.0;
+#endif
+          rc = launch_gemm(n, F + hm[m].mat0, P + hm[m].mat0, W.Xl, st);  // G = F P ; R = G - G^t
+          if (rc) return rc;
+          PROF(PK_DIIS_STORE, st, SEQM_LAUNCH(commutator_kernel, grid1d(nn, 256), 256, 0, st, n, (const double*)W.Xl, Rh, W.rmax));
+          PROF(PK_DIIS_STORE, st, SEQM_LAUNCH(residual_dots_kernel, cF, 1024, 0, st, n, (const double*)Rh, (const double*)(W.RES + h0), nn,
+                                              W.EMAT + (long long)m * SEQM_EM * SEQM_EM + counter * SEQM_EM));
+#ifndef SEQM_HOSTEMU
+          cudaMemcpyAsync(W.diis_err + m, W.rmax, sizeof(double), cudaMemcpyDeviceToDevice, st);
+#else
+          W.diis_err[m] = *W.rmax;
+#endif
+          CHK("large diis_store");
+        }
+      }
       if (cF >= 2) {
         PROF(PK_DIIS_SOLVE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_solve_kernel, diis_grid(b->nmol), 32 * SEQM_DIIS_WARPS, 0, st, *b, W, counter, cF));
         CHK("diis_solve_kernel");
-        PROF(PK_DIIS_EXTRAP, SEQM_STREAM(stream), SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF));
+        if (!large) {
+          PROF(PK_DIIS_EXTRAP, SEQM_STREAM(stream), SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF));
+        } else {
+          for (int m = 0; m < b->nmol; ++m) {
+            if (!h_active[m]) continue;
+            const long long nn = (long long)hm[m].n * hm[m].n;
+            PROF(PK_DIIS_EXTRAP, st, SEQM_LAUNCH(extrapolate_large_kernel, grid1d(nn, 256), 256, 0, st, nn,
+                                                 (const double*)(W.coeff + (long long)m * SEQM_NFOCK),
+                                                 (const double*)(W.FOCK + hm[m].mat0 * SEQM_NFOCK), F + hm[m].mat0, cF));
+          }
+        }
         CHK("diis_extrapolate_kernel");
       }
     }
     // Pnew from F on the active molecules
-    if (o->use_sp2) {
+    if (large) {
+      for (int m = 0; m < b->nmol; ++m) {
+        if (!h_active[m]) continue;
+        rc = sp2_large_one(hm[m].n, hm[m].nocc, F + hm[m].mat0, W.Pnew + hm[m].mat0, o->sp2_eps, W.Xl, W.X2l, W.sp2st,
+                           (int*)nullptr, st);
+        if (rc) return rc;
+      }
+    } else if (o->use_sp2) {
       PROF(PK_SP2, SEQM_STREAM(stream), SEQM_LAUNCH(sp2_kernel, b->nmol, nt, smsp2, st, *b, F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, W.active));
       CHK("sp2_kernel");
     } else {
@@ -549,15 +731,36 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       CHK("adaptive_diag_kernel");
       PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_apply_kernel, b->nmol, 256, 0, st, *b, W, P));
       CHK("adaptive_apply_kernel");
-    } else {
+    } else if (!large) {
       PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, (cF < 2) ? 0.5 : 0.0));
       CHK("mix_linear_kernel");
+    } else {
+      for (int m = 0; m < b->nmol; ++m) {
+        if (!h_active[m]) continue;
+        const long long nn = (long long)hm[m].n * hm[m].n;
+        PROF(PK_MIX, st, SEQM_LAUNCH(mix_large_kernel, grid1d(nn, 256), 256, 0, st, nn, P + hm[m].mat0, W.Pold + hm[m].mat0,
+                                     (const double*)(W.Pnew + hm[m].mat0), (cF < 2) ? 0.5 : 0.0));
+      }
+      CHK("mix_large_kernel");
     }
-    PROF(PK_FOCK, SEQM_STREAM(stream), SEQM_LAUNCH(fock_kernel, b->nmol, nt, sm1, st, *b, P, H, w, F, (const int32_t*)W.active));
-    CHK("fock_kernel");
+    rc = launch_fock(b, P, H, w, F, (const int32_t*)W.active, st);
+    if (rc) return rc;
     rc = zero_nnot(W, stream);
     if (rc) return rc;
-    PROF(PK_ENERGY_ERR, SEQM_STREAM(stream), SEQM_LAUNCH(energy_error_kernel, b->nmol, 128, 0, st, *b, W, P, H, F, notconverged, o->eps, o->converger == 2));
+    if (!large) {
+      PROF(PK_ENERGY_ERR, SEQM_STREAM(stream), SEQM_LAUNCH(energy_error_kernel, b->nmol, 128, 0, st, *b, W, P, H, F, notconverged, o->eps, o->converger == 2));
+    } else {
+      for (int m = 0; m < b->nmol; ++m) {
+        if (!h_active[m]) continue;
+        const long long nn = (long long)hm[m].n * hm[m].n, m0 = hm[m].mat0;
+        int np_ = grid1d(nn, 256);
+        if (np_ > 4096) np_ = 4096;
+        PROF(PK_ENERGY_ERR, st, SEQM_LAUNCH(energy_partial_kernel, np_, 256, 0, st, nn, (const double*)(P + m0), H + m0,
+                                            (const double*)(F + m0), (const double*)(W.Pold + m0), W.part));
+        PROF(PK_ENERGY_ERR, st, SEQM_LAUNCH(energy_finalize_kernel, 1, 32, 0, st, *b, W, m, (const double*)W.part, np_,
+                                            notconverged, o->eps, o->converger == 2));
+      }
+    }
     CHK("energy_error_kernel");
     SEQM_LAUNCH(commit_active_kernel, gm, 128, 0, st, *b, W, notconverged);
     CHK("commit_active_kernel");
@@ -565,6 +768,10 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
     rc = read_ctrl(W, stream, &h);
     if (rc) return rc;
     nnot = h.nnot;
+    if (large) {
+      rc = fetch_host_ints(W.active, h_active, b->nmol, st);
+      if (rc) return rc;
+    }
     if (o->converger == 2) {
       if (h.reset) {
         counter = -1;
@@ -580,6 +787,8 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   }
   if (o->converger == 2) printed = (k > k_last) ? k_last + 1 : k;
   if (n_iter_out) *n_iter_out = printed;
+  delete[] hm;
+  delete[] h_active;
 #ifndef SEQM_HOSTEMU
   cudaError_t e = cudaMemcpyAsync(Eelec, W.Eel_new, sizeof(double) * b->nmol, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess && C_last && have_C)

@@ -124,11 +124,7 @@ class BatchPlan:
             s.cls_count[c] = len(idx)
         self.struct = s
         self.ref = C.byref(s)
-        if self.nmax > lib.dll.seqm_max_orbitals():
-            raise NotImplementedError(
-                f"a molecule with {self.nmax} orbitals exceeds this build's shared-memory resident limit "
-                f"({lib.dll.seqm_max_orbitals()}); large single molecules are not covered yet"
-            )
+        self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path
         z = torch.zeros(1, dtype=torch.float64, device=dev)
         lib.check(lib.dll.seqm_atom_multipoles(self.ref, stream_of(z)), "seqm_atom_multipoles")
 
@@ -175,6 +171,15 @@ def op_eig_density(plan, F, want_P=True, want_C=False, Cguess=None, active=None)
 
 def op_sp2_density(plan, F, eps, active=None):
     P = plan.new_mat()
+    if plan.large:
+        nb = plan.lib.dll.seqm_sp2_large_workspace_bytes(plan.ref)
+        ws = torch.zeros(nb, dtype=torch.uint8, device=plan.device)
+        nit_h = (C.c_int32 * plan.nmol)()
+        plan.lib.check(
+            plan.lib.dll.seqm_sp2_density_large(plan.ref, ptr(F), ptr(P), C.c_double(eps), nit_h, ptr(ws), stream_of(F)),
+            "seqm_sp2_density_large",
+        )
+        return P, torch.tensor(list(nit_h), dtype=torch.int32)
     nit = torch.zeros(plan.nmol, dtype=torch.int32, device=plan.device)
     plan.lib.check(
         plan.lib.dll.seqm_sp2_density(plan.ref, ptr(F), ptr(P), C.c_double(eps), ptr(nit), ptr(active), stream_of(F)),
