@@ -34,13 +34,13 @@ enum seqm_par_row {
   SEQM_P_GP2, SEQM_P_HSP, SEQM_P_ALPHA,
   SEQM_P_K1, SEQM_P_K2, SEQM_P_K3, SEQM_P_K4, SEQM_P_L1, SEQM_P_L2, SEQM_P_L3, SEQM_P_L4,
   SEQM_P_M1, SEQM_P_M2, SEQM_P_M3, SEQM_P_M4,
-  SEQM_P_TORE, SEQM_P_QN,
+  SEQM_P_TORE, SEQM_P_QN, SEQM_P_RHOCORE, SEQM_P_ATNUM,
   /* filled by seqm_atom_multipoles(): */
   SEQM_P_DD, SEQM_P_QQ, SEQM_P_RHO0, SEQM_P_RHO1, SEQM_P_RHO2,
   SEQM_NPAR
 };
 
-enum seqm_method { SEQM_MNDO = 0, SEQM_AM1 = 1, SEQM_PM3 = 2 };
+enum seqm_method { SEQM_MNDO = 0, SEQM_AM1 = 1, SEQM_PM3 = 2, SEQM_PM6_SP = 3 };
 
 typedef struct seqm_batch {
   int32_t nmol, nat, npairs, method;
@@ -64,6 +64,11 @@ typedef struct seqm_batch {
    * mol_order[cls_begin[c] .. cls_begin[c]+cls_count[c]) because mol_order is sorted by descending n. */
   int32_t cls_begin[12];
   int32_t cls_count[12];
+  /* PM6_SP pairwise core-core parameters alpha[Zi*pw_dim+Zj], chi[...] (PWCCT_PM6_SP_MOPAC.csv; parameters.py:49-88);
+   * NULL for the other methods */
+  const double* pw_alpha;
+  const double* pw_chi;
+  int32_t pw_dim;
 } seqm_batch_t;
 
 int seqm_abi_version(void);

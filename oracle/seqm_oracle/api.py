@@ -9,7 +9,7 @@ from .density import density_from_fock
 from .energy import elec_energy, isolated_atom_energy, molecule_sums, pair_nuclear_energy
 from .gradient import hf_gradient
 from .hamiltonian import build_fock, build_hcore, initial_density
-from .integrals import atom_multipoles
+from .integrals import atom_multipoles, rho0_eff
 from .parser import parse
 from .scf import run_scf
 from .tables import Tables, method_parameters
@@ -46,8 +46,8 @@ def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True):
     """Returns a dict with the result contract of SURVEY 8(a15)."""
     T = Tables.get()
     method = seqm_parameters["method"]
-    if method not in ("MNDO", "AM1", "PM3"):
-        raise NotImplementedError(f"oracle covers MNDO/AM1/PM3, not {method}")
+    if method not in ("MNDO", "AM1", "PM3", "PM6_SP"):
+        raise NotImplementedError(f"oracle covers MNDO/AM1/PM3/PM6_SP, not {method}")
     eps = float(seqm_parameters["scf_eps"])
     conv = seqm_parameters.get("scf_converger", [2])
     sp2 = seqm_parameters.get("sp2", [False])
@@ -61,7 +61,7 @@ def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True):
     F = build_fock(P, par, H, w, D)
     _, e_mo, V = density_from_fock(F, P.nHeavy, P.nHydro, P.nocc, want_eig=True)
     Eelec = elec_energy(D, F, H)
-    EnucAB = pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, P.rij, w[:, 0, 0], par)
+    EnucAB = pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, P.rij, w[:, 0, 0], par, rho0=rho0_eff(par, mp))
     Enuc = molecule_sums(EnucAB, P.pair_molid, P.nmol)
     Etot = Eelec + Enuc
     Eiso = molecule_sums(isolated_atom_energy(P.Z, par), P.atom_molid, P.nmol)

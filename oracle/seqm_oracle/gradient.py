@@ -10,7 +10,7 @@ by tests/test_oracle_golden.py.
 import numpy as np
 
 from .energy import pair_nuclear_energy
-from .integrals import PACK, PACK_COL, PACK_ROW, WEIGHT, atom_multipoles, overlap_sp, two_center_integrals_geom
+from .integrals import PACK, PACK_COL, PACK_ROW, WEIGHT, atom_multipoles, overlap_sp, rho0_eff, two_center_integrals_geom
 from .tables import Tables
 
 DELTA = 1.0e-5  # Angstrom, anal_grad.py:13
@@ -42,7 +42,7 @@ def _pair_energy(P, par, mp, method, xij, rij, PAi, PBj, Dab, pki, pkj, xl=None)
         E += np.matmul(fki[:, None, :], np.matmul(w, xj[:, :, None]))[:, 0, 0]
         x16 = d16 - 0.5 * Fab.reshape(-1, 16)
         E += -np.matmul(x16[:, None, :], np.matmul(wx, Fab.reshape(-1, 16)[:, :, None]))[:, 0, 0]
-    E += pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, rij, w[:, 0, 0], par)
+    E += pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, rij, w[:, 0, 0], par, rho0=rho0_eff(par, mp))
     return E
 
 

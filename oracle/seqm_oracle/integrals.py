@@ -77,6 +77,15 @@ def atom_multipoles(Z, par):
     return dd, qq, rho0, rho1, rho2
 
 
+def rho0_eff(par, mp):
+    """rho_0 per atom with rho_core substituted where it is non-zero (two_elec_two_center_int.py:273-281)."""
+    rho0 = mp[2]
+    rc = par.get("rho_core")
+    if rc is None:
+        return rho0
+    return np.where(rc != 0.0, rc, rho0)
+
+
 # --- point-charge multipole configurations -------------------------------------------------------
 # each entry: list of (coefficient, x, y, z) in units of the charge separation D (z = bond axis)
 def _cfg(kind, D1, D2):

@@ -11,7 +11,7 @@ from .density import density_from_fock, sp2_density
 from .energy import elec_energy_xl, isolated_atom_energy, molecule_sums, pair_nuclear_energy
 from .gradient import hf_gradient
 from .hamiltonian import build_fock, build_hcore
-from .integrals import atom_multipoles
+from .integrals import atom_multipoles, rho0_eff
 from .parser import parse
 from .tables import Tables, method_parameters
 
@@ -56,7 +56,7 @@ def xl_forward(species, coordinates, seqm_parameters, field):
         ar = np.arange(P.nmol)
         e_gap = e[ar, P.nocc] - e[ar, P.nocc - 1]
     Eelec = elec_energy_xl(D, field, F, H)
-    EnucAB = pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, P.rij, w[:, 0, 0], par)
+    EnucAB = pair_nuclear_energy(method, P.ni, P.nj, P.idxi, P.idxj, P.rij, w[:, 0, 0], par, rho0=rho0_eff(par, mp))
     Enuc = molecule_sums(EnucAB, P.pair_molid, P.nmol)
     Etot = Eelec + Enuc
     Eiso = molecule_sums(isolated_atom_energy(P.Z, par), P.atom_molid, P.nmol)

@@ -52,4 +52,12 @@ def method_parameters(method, Z):
     for j, c in enumerate(cols):
         out[c] = tab[Z, j].copy()
     out["_ngauss"] = _NGAUSS.get(method, 0)
+    if "pairwise_alpha_chi" in d:  # PWCCT (parameters.py:49-88)
+        zm = max(max(t[0], t[1]) for t in d["pairwise_alpha_chi"])
+        alp = np.zeros((zm + 1, zm + 1))
+        chi = np.zeros((zm + 1, zm + 1))
+        for zi, zj, a, c in d["pairwise_alpha_chi"]:
+            alp[zi, zj] = a
+            chi[zi, zj] = c
+        out["_alp"], out["_chi"] = alp, chi
     return out

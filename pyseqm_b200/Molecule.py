@@ -11,7 +11,7 @@ import torch
 from . import engine
 from ._lib import get_lib
 
-SUPPORTED_METHODS = ("MNDO", "AM1", "PM3")
+SUPPORTED_METHODS = ("MNDO", "AM1", "PM3", "PM6_SP")
 
 
 def check_input(species):
@@ -102,7 +102,7 @@ class Molecule(torch.nn.Module):
             raise NotImplementedError("pair_outer_cutoff that removes pairs is not supported by the B200 path yet")
         # per-atom parameter dict (Molecule.py:86-115)
         names = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha"]
-        ng = {"MNDO": 0, "AM1": 4, "PM3": 2}[self.method]
+        ng = {"MNDO": 0, "AM1": 4, "PM3": 2, "PM6_SP": 4}[self.method]
         for g in range(1, ng + 1):
             names += [f"Gaussian{g}_K", f"Gaussian{g}_L", f"Gaussian{g}_M"]
         self.parameters = {k: plan.parameter(k) for k in names}
@@ -112,8 +112,11 @@ class Molecule(torch.nn.Module):
             self.parameters[k] = zeros
         self.parameters["Kbeta"] = None
         zmax = int(species.max())
-        self.alp = torch.zeros((zmax + 1, zmax + 1), dtype=torch.float64, device=dev)
-        self.chi = torch.zeros_like(self.alp)
+        if plan.pw is not None:
+            self.alp, self.chi = plan.pw[0], plan.pw[1]
+        else:
+            self.alp = torch.zeros((zmax + 1, zmax + 1), dtype=torch.float64, device=dev)
+            self.chi = torch.zeros_like(self.alp)
         self.norb = self.nHydro + 4 * self.nHeavy
         non_zero = species != 0
         self.num_atoms = non_zero.sum(dim=1).to(coordinates.dtype)

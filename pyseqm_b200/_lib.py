@@ -19,10 +19,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
 # rows of the per-atom parameter table (enum seqm_par_row)
 PAR_ROWS = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha",
             "Gaussian1_K", "Gaussian2_K", "Gaussian3_K", "Gaussian4_K", "Gaussian1_L", "Gaussian2_L", "Gaussian3_L",
-            "Gaussian4_L", "Gaussian1_M", "Gaussian2_M", "Gaussian3_M", "Gaussian4_M", "tore", "qn",
+            "Gaussian4_L", "Gaussian1_M", "Gaussian2_M", "Gaussian3_M", "Gaussian4_M", "tore", "qn", "rho_core", "atomic_num",
             "dd", "qq", "rho0", "rho1", "rho2"]  # fmt: skip
 NPAR = len(PAR_ROWS)
-METHOD_ID = {"MNDO": 0, "AM1": 1, "PM3": 2}
+METHOD_ID = {"MNDO": 0, "AM1": 1, "PM3": 2, "PM6_SP": 3}
 
 
 class SeqmBatchStruct(C.Structure):
@@ -33,6 +33,7 @@ class SeqmBatchStruct(C.Structure):
         ("mol_nheavy", C.c_void_p), ("mol_nhyd", C.c_void_p), ("mol_nocc", C.c_void_p), ("mol_order", C.c_void_p),
         ("atom_Z", C.c_void_p), ("atom_mol", C.c_void_p), ("pair_i", C.c_void_p), ("pair_j", C.c_void_p),
         ("atom_par", C.c_void_p), ("cls_begin", C.c_int32 * 12), ("cls_count", C.c_int32 * 12),
+        ("pw_alpha", C.c_void_p), ("pw_chi", C.c_void_p), ("pw_dim", C.c_int32),
     ]  # fmt: skip
 
 JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 60)

@@ -342,20 +342,47 @@ SEQM_HD void overlap_block(const OverlapTables& tab, int na, int nb, bool heavyA
 }
 
 // ---- core-core repulsion ------------------------------------------------------------------------
-// method: 0 MNDO, 1 AM1 (4 gaussians), 2 PM3 (2 gaussians).  r in bohr, gam = (ss|ss).
+// method: 0 MNDO, 1 AM1 (4 gaussians), 2 PM3 (2 gaussians), 3 PM6_SP (4 gaussians + pairwise alpha/chi terms).
+// r in bohr, gam = (ss|ss).  energy.py:91-174.
 struct CorePar {
-  double tore, alpha, gK[4], gL[4], gM[4];
+  double tore, alpha, gK[4], gL[4], gM[4], rho0eff, atnum;
 };
 template <class T>
-SEQM_HD T core_core(int method, int ni, int nj, const CorePar& A, const CorePar& B, const T& r, const T& gam) {
+SEQM_HD T core_core(int method, int ni, int nj, const CorePar& A, const CorePar& B, const T& r, const T& gam, double alp,
+                    double chi) {
   const T ra = r * SEQM_A0;
-  const bool xh = ((ni == 7) || (ni == 8)) && (nj == 1);
-  T t2 = e_xp(-(A.alpha * ra));
-  if (xh) t2 = t2 * ra;
-  const T t3 = e_xp(-(B.alpha * ra));
-  T E = (A.tore * B.tore) * gam * (1.0 + t2 + t3);
+  T E;
+  if (method == 3) {
+    // PM6 core-core (energy.py:140-171): Voityuk-type unpolarisable-core term + scaled (ss|ss)-like interaction
+    const double za3 = pow(A.atnum, 1.0 / 3.0) + pow(B.atnum, 1.0 / 3.0);
+    const T q = za3 / ra;
+    const T q2 = q * q, q4 = q2 * q2;
+    const T unpol = 1.0e-8 * (q4 * q4 * q4);
+    const double rs = A.rho0eff + B.rho0eff;
+    const T g0 = (A.tore * B.tore * SEQM_EV) * inv_sqrt(r * r + rs * rs);
+    const bool xh = (ni == 6 || ni == 7 || ni == 8) && (nj == 1);
+    T scale;
+    if (xh) {
+      scale = 1.0 + (2.0 * chi) * e_xp(-(alp * (ra * ra)));
+    } else {
+      const T ra2 = ra * ra;
+      scale = 1.0 + (2.0 * chi) * e_xp(-(alp * (ra + 0.0003 * (ra2 * ra2 * ra2))));
+    }
+    E = unpol + g0 * scale;
+    if (ni == 6 && nj == 6) E = E + g0 * (9.28 * e_xp(-(5.98 * ra)));
+    if (ni == 14 && nj == 8) {
+      const T d = r - 2.9;
+      E = E - g0 * (0.0007 * e_xp(-(d * d)));
+    }
+  } else {
+    const bool xh = ((ni == 7) || (ni == 8)) && (nj == 1);
+    T t2 = e_xp(-(A.alpha * ra));
+    if (xh) t2 = t2 * ra;
+    const T t3 = e_xp(-(B.alpha * ra));
+    E = (A.tore * B.tore) * gam * (1.0 + t2 + t3);
+  }
   if (method != 0) {
-    const int ng = (method == 1) ? 4 : 2;
+    const int ng = (method == 2) ? 2 : 4;
     T g = T(0.0);
     for (int k = 0; k < ng; ++k) {
       const T da = ra - A.gM[k], db = ra - B.gM[k];

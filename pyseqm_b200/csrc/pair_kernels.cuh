@@ -39,7 +39,18 @@ SEQM_HD CorePar load_core(const seqm_batch_t& b, int a) {
     c.gL[k] = par(b, SEQM_P_L1 + k, a);
     c.gM[k] = par(b, SEQM_P_M1 + k, a);
   }
+  const double rc = par(b, SEQM_P_RHOCORE, a);
+  c.rho0eff = (rc != 0.0) ? rc : par(b, SEQM_P_RHO0, a);  // two_elec_two_center_int.py:273-281
+  c.atnum = par(b, SEQM_P_ATNUM, a);
   return c;
+}
+SEQM_HD void pair_pw(const seqm_batch_t& b, int i, int j, double& alp, double& chi) {
+  alp = chi = 0.0;
+  if (b.pw_alpha) {
+    const long long k = (long long)b.atom_Z[i] * b.pw_dim + b.atom_Z[j];
+    alp = b.pw_alpha[k];
+    chi = b.pw_chi[k];
+  }
 }
 
 // Geometry of a pair as scalars of type T.  For T = Dual3 the derivative slots are d/dR_i.
@@ -163,8 +174,10 @@ SEQM_GLOBAL void nuclear_energy_kernel(seqm_batch_t b, const double* __restrict_
     const int i = b.pair_i[p], j = b.pair_j[p];
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
+    double alp, chi;
+    pair_pw(b, i, j, alp, chi);
     EnucAB[p] = core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), g.r,
-                          w[(long long)p * 100]);
+                          w[(long long)p * 100], alp, chi);
   }
 }
 // per-molecule sum of a per-pair quantity (pairs of a molecule are contiguous): deterministic, no atomics
@@ -346,7 +359,11 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
         }
     }
     // ---- core-core repulsion (depends on r only)
-    dEdr += core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), r1, ri[0]).d;
+    {
+      double alp, chi;
+      pair_pw(b, i, j, alp, chi);
+      dEdr += core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), r1, ri[0], alp, chi).d;
+    }
     // ---- chain rule: X = R_j - R_i, r = |X|/a0, e = X/|X| ; gradient with respect to R_i is -dE/dX
     const double ede = dEde[0] * g.e[0] + dEde[1] * g.e[1] + dEde[2] * g.e[2];
     for (int c = 0; c < 3; ++c)
@@ -399,7 +416,11 @@ SEQM_GLOBAL void pair_gradient_forward_kernel(seqm_batch_t b, const double* __re
         for (int nu = 0; nu < ni; ++nu)
           for (int sg = 0; sg < nj; ++sg)
             E += (-0.5 * Pm[(oi + mu) * n + oj + la] * Pm[(oi + nu) * n + oj + sg]) * w[pack2(mu, nu)][pack2(la, sg)];
-    E += core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), g.r, w[0][0]);
+    {
+      double alp, chi;
+      pair_pw(b, i, j, alp, chi);
+      E += core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), g.r, w[0][0], alp, chi);
+    }
     gpair[3 * (long long)p] = E.d0;
     gpair[3 * (long long)p + 1] = E.d1;
     gpair[3 * (long long)p + 2] = E.d2;

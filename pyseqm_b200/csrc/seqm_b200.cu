@@ -81,8 +81,8 @@ static int check_batch(const seqm_batch_t* b) {
     seqm_set_error("empty batch");
     return SEQM_ERR_ARG;
   }
-  if (b->method < 0 || b->method > 2) {
-    seqm_set_error("method %d not supported by this build (MNDO=0, AM1=1, PM3=2)", b->method);
+  if (b->method < 0 || b->method > 3 || (b->method == 3 && !b->pw_alpha)) {
+    seqm_set_error("method %d not supported by this build (MNDO=0, AM1=1, PM3=2, PM6_SP=3 with pairwise tables)", b->method);
     return SEQM_ERR_UNSUPPORTED;
   }
   return ensure_device();

@@ -33,7 +33,16 @@ def method_table(method):
         tab = torch.zeros((zmax + 1, len(d["columns"])), dtype=torch.float64)
         for k, v in d["rows"].items():
             tab[int(k)] = torch.tensor(v, dtype=torch.float64)
-        _TABLE_CACHE[key] = (tab, d["columns"])
+        pw = None
+        if "pairwise_alpha_chi" in d:  # PWCCT (parameters.py:49-88): alpha[Zi, Zj], chi[Zi, Zj]
+            zm = max(max(t[0], t[1]) for t in d["pairwise_alpha_chi"])
+            a = torch.zeros((zm + 1, zm + 1), dtype=torch.float64)
+            c = torch.zeros_like(a)
+            for zi, zj, al, ch in d["pairwise_alpha_chi"]:
+                a[zi, zj] = al
+                c[zi, zj] = ch
+            pw = (a, c)
+        _TABLE_CACHE[key] = (tab, d["columns"], pw)
     return _TABLE_CACHE[key]
 
 
@@ -98,7 +107,7 @@ class BatchPlan:
         self.atom_mol, self.atom_local = atom_mol, local
         self.pair_i, self.pair_j = pair_i, pair_j
         # per-atom parameter table
-        tab, cols = method_table(method)
+        tab, cols, pw = method_table(method)
         tabd = tab.to(dev)
         par = torch.zeros((NPAR, self.nat), dtype=torch.float64, device=dev)
         for r, name in enumerate(PAR_ROWS[:24]):
@@ -108,6 +117,19 @@ class BatchPlan:
                 par[r] = tabd[Z, cols.index(name)]
         par[24] = tore[Z]
         par[25] = torch.tensor(el["qn"], dtype=torch.float64, device=dev)[Z]
+        if "rho_core" in cols:
+            par[26] = tabd[Z, cols.index("rho_core")]
+        par[27] = torch.tensor(el["atomic_num"], dtype=torch.float64, device=dev)[Z]
+        self.pw = None
+        if pw is not None:
+            zmax = int(species.max())
+            dim = max(zmax + 1, 2)
+            a = torch.zeros((dim, dim), dtype=torch.float64)
+            c = torch.zeros_like(a)
+            k = min(dim, pw[0].shape[0])
+            a[:k, :k] = pw[0][:k, :k]
+            c[:k, :k] = pw[1][:k, :k]
+            self.pw = (a.to(dev).contiguous(), c.to(dev).contiguous(), dim)
         self.par = par.contiguous()
         s = SeqmBatchStruct()
         s.nmol, s.nat, s.npairs, s.method = nmol, self.nat, self.npairs, METHOD_ID[method]
@@ -115,6 +137,8 @@ class BatchPlan:
         for k, v in self.t.items():
             setattr(s, k, v.data_ptr())
         s.atom_par = self.par.data_ptr()
+        if self.pw is not None:
+            s.pw_alpha, s.pw_chi, s.pw_dim = self.pw[0].data_ptr(), self.pw[1].data_ptr(), self.pw[2]
         # eigensolver size classes over the descending-n processing order (host arrays inside the struct)
         n_sorted = norb[order].cpu().tolist()
         cls = [next((c for c, q in enumerate(JACOBI_NP) if 2 * q >= n), -1) for n in n_sorted]

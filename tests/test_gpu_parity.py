@@ -28,7 +28,7 @@ def test_cuda_library_is_the_one_loaded(lib):
     assert lib.dll.seqm_abi_version() == 1
 
 
-@pytest.mark.parametrize("method", ["AM1", "PM3", "MNDO"])
+@pytest.mark.parametrize("method", ["AM1", "PM3", "MNDO", "PM6_SP"])
 def test_operator_level(lib, dev, method):
     check_operator_level(lib, dev, method)
 
@@ -36,7 +36,8 @@ def test_operator_level(lib, dev, method):
 @pytest.mark.parametrize(
     "name",
     ["cfg1_AM1_c2", "cfg1_AM1_c1", "cfg1_AM1_c0", "cfg1_PM3_c2", "cfg1_PM3_c1", "cfg1_PM3_c0", "cfg1_MNDO_c2",
-     "cfg1_MNDO_c1", "cfg1_MNDO_c0", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48",
+     "cfg1_MNDO_c1", "cfg1_MNDO_c0", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48", "cfg1_PM6_SP_c2", "cfg1_PM6_SP_c1",
+     "cfg2_PM6_SP_24",
      "cfg3_coronene_AM1"],
 )  # fmt: skip
 def test_single_point_golden(lib, dev, name):

@@ -78,11 +78,20 @@ def operator_level(species, coords, method):
 def main():
     cfg1 = [os.path.join(XYZ, f) for f in ("methane.xyz", "benzene.xyz", "toluene.xyz")]
     species, coords = read_xyz(cfg1)
-    for method in ("AM1", "PM3", "MNDO"):
+    only = os.environ.get("GOLDEN_ONLY")  # e.g. GOLDEN_ONLY=PM6_SP regenerates just that method
+    for method in ("AM1", "PM3", "MNDO", "PM6_SP"):
+        if only and method != only:
+            continue
         for tag, conv, eps in (("c2", [2], 1e-7), ("c1", [1], 1e-6), ("c0", [0, 0.3], 1e-7)):
             sp = {"method": method, "scf_eps": eps, "scf_converger": conv, "sp2": [False], "analytical_gradient": [True]}
             extra = operator_level(species, coords, method) if tag == "c2" else None
             save(f"cfg1_{method}_{tag}", species, coords, sp, extra)
+    if only:
+        if only == "PM6_SP":
+            s4, c4 = synthetic.qm9_like_batch(24, seed=2)
+            sp = {"method": "PM6_SP", "scf_eps": 1e-7, "scf_converger": [2], "sp2": [False], "analytical_gradient": [True]}
+            save("cfg2_PM6_SP_24", s4, c4, sp, drop=("e_mo",))
+        return
     # default (autograd) forces and the SP2 density route
     sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2], "sp2": [False]}
     save("cfg1_AM1_autograd", species, coords, sp, drop=("dm", "e_mo"))
