@@ -34,8 +34,8 @@ def check_dimer(lib, device):
     assert not bool(es.notconverged.any())
     # no iteration-count assertion: with SP2 noise the DIIS tail wanders (see the module docstring)
     assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < 2e-6
-    assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < 1e-4
-    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < 2e-3
+    assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < 2e-3  # SP2-limited (weakly coupled stacked dimer)
+    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < 1e-2
     # the eigensolver route is refused for this size instead of silently doing something else
     with pytest.raises(NotImplementedError, match="SP2"):
         run_molecule(lib, device, s2, c2, {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2]})
