@@ -69,6 +69,10 @@ typedef struct seqm_batch {
   const double* pw_alpha;
   const double* pw_chi;
   int32_t pw_dim;
+  /* pair indices grouped by class (H-H | X-H | X-X) so that the pair kernels run divergence-free with compile-time
+   * block sizes: pair_perm[pair_cls_off[c] .. pair_cls_off[c+1]) are the pairs of class c (HOST offsets) */
+  int32_t pair_cls_off[4];
+  const int32_t* pair_perm;
 } seqm_batch_t;
 
 int seqm_abi_version(void);

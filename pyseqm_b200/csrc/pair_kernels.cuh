@@ -82,9 +82,7 @@ SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<Dual3>& g) {
 // w of one pair in the molecular frame (only the entries that exist for the pair class are non-zero)
 // Only the entries that exist for the pair class are written: [0][0] (H-H), [0..9][0] (X-H), all (X-X).
 template <class T>
-SEQM_HD void pair_w(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T w[10][10]) {
-  const bool hi = b.atom_Z[i] > 1, hj = b.atom_Z[j] > 1;
-  const int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
+SEQM_HD void pair_w(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T w[10][10], int nint) {
   T ri[22];
   local_integrals(g.r, load_multipole(b, i), load_multipole(b, j), nint, ri);
   if (nint == 1) {
@@ -106,15 +104,20 @@ SEQM_HD void pair_overlap(const seqm_batch_t& b, int i, int j, const PairGeom<T>
                 par(b, SEQM_P_ZP, i), par(b, SEQM_P_ZS, j), par(b, SEQM_P_ZP, j), g.r, g.e, S);
 }
 
+// CLS: 0 H-H, 1 X-H, 2 X-X -- the kernel walks the class's pair list, so every warp is divergence-free and the
+// block sizes (1 | 10 orbital products, 1 | 4 | 22 local integrals) are compile-time constants.
+template <int CLS>
 SEQM_GLOBAL void pair_integrals_kernel(seqm_batch_t b, const double* __restrict__ xyz, double* __restrict__ w,
                                        double* __restrict__ hab) {
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
+  constexpr int nA = (CLS >= 1) ? 10 : 1, nB = (CLS == 2) ? 10 : 1, nint = (CLS == 2) ? 22 : ((CLS == 1) ? 4 : 1);
+  const int q0 = b.pair_cls_off[CLS], q1 = b.pair_cls_off[CLS + 1];
+  for (int q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x) {
+    const int p = b.pair_perm[q];
     const int i = b.pair_i[p], j = b.pair_j[p];
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
     double wl[10][10];
-    pair_w(b, i, j, g, wl);
-    const int nA = (b.atom_Z[i] > 1) ? 10 : 1, nB = (b.atom_Z[j] > 1) ? 10 : 1;
+    pair_w(b, i, j, g, wl, nint);
     double* wp = w + (long long)p * 100;
     for (int k = 0; k < 10; ++k)
       for (int l = 0; l < 10; ++l) wp[k * 10 + l] = (k < nA && l < nB) ? wl[k][l] : 0.0;
@@ -203,16 +206,19 @@ SEQM_HD int cls_of(int kl) { return pack_class(kl); }
 // Two densities: D multiplies the one-electron terms and (D - P/2) the two-electron terms built from P, which is
 // the XL-BOMD shadow energy  E = sum D o F(P) - 1/2 (F(P) - h) o P + E_nuc  (energy.py:76-88, xlbomd.py:430-447);
 // with D == P it is the ordinary SCF energy.  (No __restrict__ on D/P: they may alias.)
+template <int CLS>
 SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* D, const double* P,
                                       double* __restrict__ gpair) {
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < b.npairs; p += gridDim.x * blockDim.x) {
+  constexpr bool hi = (CLS >= 1), hj = (CLS == 2);
+  constexpr int ni = hi ? 4 : 1, nj = hj ? 4 : 1;
+  const int q0 = b.pair_cls_off[CLS], q1 = b.pair_cls_off[CLS + 1];
+  for (int q = q0 + blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += gridDim.x * blockDim.x) {
+    const int p = b.pair_perm[q];
     const int i = b.pair_i[p], j = b.pair_j[p];
     const MolView v = mol_view(b, b.atom_mol[i]);
     const double* Pm = P + v.mat0;
     const double* Dm = D + v.mat0;
     const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
-    const int ni = orb_cnt(v, i - v.a0), nj = orb_cnt(v, j - v.a0);
-    const bool hi = ni == 4, hj = nj == 4;
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
     const double dist = g.r * SEQM_A0;
@@ -264,8 +270,8 @@ SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__
     }
 
     // ---- two-electron + core-attraction terms: E_2e = sum C[kl][mn] w[kl][mn]
-    const int nA = hi ? 10 : 1, nB = hj ? 10 : 1;
-    const int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
+    constexpr int nA = hi ? 10 : 1, nB = hj ? 10 : 1;
+    constexpr int nint = (hi && hj) ? 22 : (hi ? 4 : 1);
     double Cm[10][10];
     {
       double pa[10], pb[10], da[10], db[10];  // weighted packed diagonal blocks of P and D
@@ -394,7 +400,7 @@ SEQM_GLOBAL void pair_gradient_forward_kernel(seqm_batch_t b, const double* __re
           E += (Pm[(oi + mu) * n + oj + nu] * ((mu ? bpi : bsi) + (nu ? bpj : bsj))) * S[mu][nu];
     }
     Dual3 w[10][10];
-    pair_w(b, i, j, g, w);
+    pair_w(b, i, j, g, w, (ni == 4 && nj == 4) ? 22 : (ni == 4 ? 4 : 1));
     const int nA = (ni == 4) ? 10 : 1, nB = (nj == 4) ? 10 : 1;
     double pa[10], pb[10];  // weighted packed diagonal-block densities
     for (int kl = 0; kl < 10; ++kl) {

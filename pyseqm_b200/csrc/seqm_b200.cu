@@ -186,6 +186,15 @@ static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, 
   PROF(PK_FOCK, st, SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, st, *b, P, H, w, F, active));
   return seqm_check_launch("fock_kernel");
 }
+static int launch_pair_gradient(const seqm_batch_t* b, const double* xyz, const double* D, const double* P, double* gp,
+                                cudaStream_t st) {
+  const int n0 = b->pair_cls_off[1] - b->pair_cls_off[0], n1 = b->pair_cls_off[2] - b->pair_cls_off[1],
+            n2 = b->pair_cls_off[3] - b->pair_cls_off[2];
+  if (n0 > 0) PROF(PK_GRAD, st, SEQM_LAUNCH(pair_gradient_kernel<0>, grid1d(n0, 128), 128, 0, st, *b, xyz, D, P, gp));
+  if (n1 > 0) PROF(PK_GRAD, st, SEQM_LAUNCH(pair_gradient_kernel<1>, grid1d(n1, 64), 64, 0, st, *b, xyz, D, P, gp));
+  if (n2 > 0) PROF(PK_GRAD, st, SEQM_LAUNCH(pair_gradient_kernel<2>, grid1d(n2, 64), 64, 0, st, *b, xyz, D, P, gp));
+  return seqm_check_launch("pair_gradient_kernel");
+}
 static int diis_grid(int nmol) {
 #ifdef SEQM_HOSTEMU
   return nmol;  // one single-thread "warp" per emulated CTA
@@ -414,7 +423,12 @@ int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, dou
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs == 0) return SEQM_OK;
-  PROF(PK_PAIR, SEQM_STREAM(stream), SEQM_LAUNCH(pair_integrals_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, w, hab));
+  cudaStream_t st = SEQM_STREAM(stream);
+  const int n0 = b->pair_cls_off[1] - b->pair_cls_off[0], n1 = b->pair_cls_off[2] - b->pair_cls_off[1],
+            n2 = b->pair_cls_off[3] - b->pair_cls_off[2];
+  if (n0 > 0) PROF(PK_PAIR, st, SEQM_LAUNCH(pair_integrals_kernel<0>, grid1d(n0, 128), 128, 0, st, *b, xyz, w, hab));
+  if (n1 > 0) PROF(PK_PAIR, st, SEQM_LAUNCH(pair_integrals_kernel<1>, grid1d(n1, 64), 64, 0, st, *b, xyz, w, hab));
+  if (n2 > 0) PROF(PK_PAIR, st, SEQM_LAUNCH(pair_integrals_kernel<2>, grid1d(n2, 64), 64, 0, st, *b, xyz, w, hab));
   return seqm_check_launch("pair_integrals_kernel");
 }
 
@@ -504,8 +518,7 @@ int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, dou
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, P, pair_scratch));
-    rc = seqm_check_launch("pair_gradient_kernel");
+    rc = launch_pair_gradient(b, xyz, P, P, pair_scratch, SEQM_STREAM(stream));
     if (rc) return rc;
   }
   PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad));
@@ -535,8 +548,7 @@ int seqm_gradient_xl(const seqm_batch_t* b, const double* xyz, const double* D, 
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(pair_gradient_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, D, P, pair_scratch));
-    rc = seqm_check_launch("pair_gradient_kernel");
+    rc = launch_pair_gradient(b, xyz, D, P, pair_scratch, SEQM_STREAM(stream));
     if (rc) return rc;
   }
   PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad));

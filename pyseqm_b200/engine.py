@@ -139,6 +139,13 @@ class BatchPlan:
         s.atom_par = self.par.data_ptr()
         if self.pw is not None:
             s.pw_alpha, s.pw_chi, s.pw_dim = self.pw[0].data_ptr(), self.pw[1].data_ptr(), self.pw[2]
+        # pair classes: 0 H-H, 1 X-H, 2 X-X (rows are sorted by descending Z, so Z_i >= Z_j for every pair)
+        pcls = (Z[pair_i] > 1).to(torch.int64) + (Z[pair_j] > 1).to(torch.int64)
+        self.pair_perm = torch.argsort(pcls, stable=True).to(torch.int32).contiguous()
+        cnt = torch.bincount(pcls, minlength=3).cpu().tolist()
+        s.pair_cls_off[0], s.pair_cls_off[1] = 0, cnt[0]
+        s.pair_cls_off[2], s.pair_cls_off[3] = cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]
+        s.pair_perm = self.pair_perm.data_ptr()
         # eigensolver size classes over the descending-n processing order (host arrays inside the struct)
         n_sorted = norb[order].cpu().tolist()
         cls = [next((c for c, q in enumerate(JACOBI_NP) if 2 * q >= n), -1) for n in n_sorted]
