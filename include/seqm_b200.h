@@ -73,6 +73,9 @@ typedef struct seqm_batch {
    * block sizes: pair_perm[pair_cls_off[c] .. pair_cls_off[c+1]) are the pairs of class c (HOST offsets) */
   int32_t pair_cls_off[4];
   const int32_t* pair_perm;
+  /* doubles of shared-memory Coulomb scratch the pair-centric Fock kernel needs for the largest molecule:
+   * max over molecules of 20 nXX + 11 nXH + 2 nHH (pairs by class); 0 = use the two-pass kernel */
+  int32_t fock_scratch;
 } seqm_batch_t;
 
 int seqm_abi_version(void);

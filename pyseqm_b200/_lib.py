@@ -34,7 +34,7 @@ class SeqmBatchStruct(C.Structure):
         ("atom_Z", C.c_void_p), ("atom_mol", C.c_void_p), ("pair_i", C.c_void_p), ("pair_j", C.c_void_p),
         ("atom_par", C.c_void_p), ("cls_begin", C.c_int32 * 12), ("cls_count", C.c_int32 * 12),
         ("pw_alpha", C.c_void_p), ("pw_chi", C.c_void_p), ("pw_dim", C.c_int32),
-        ("pair_cls_off", C.c_int32 * 4), ("pair_perm", C.c_void_p),
+        ("pair_cls_off", C.c_int32 * 4), ("pair_perm", C.c_void_p), ("fock_scratch", C.c_int32),
     ]  # fmt: skip
 
 JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 60)

@@ -6,6 +6,14 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SEQM_SYNCWARP
+#ifndef SEQM_HOSTEMU
+#define SEQM_SYNCWARP() __syncwarp()
+#else
+#define SEQM_SYNCWARP() do { } while (0)
+#endif
+#endif
+
 SEQM_GLOBAL void fock_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,
                              const double* __restrict__ w, double* __restrict__ F, const int32_t* __restrict__ active) {
   const int m = b.mol_order[blockIdx.x];
@@ -79,6 +87,163 @@ SEQM_GLOBAL void fock_kernel(seqm_batch_t b, const double* __restrict__ P, const
     Fm[(oa + mu) * n + oa + nu] = f;
     Fm[(oa + nu) * n + oa + mu] = f;
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pair-centric Fock build: every pair's w is read from HBM exactly once (and only the entries its class has:
+// 1 for H-H, column 0 for X-H, all 100 for X-X).  Pass 1 walks the pairs by class -- X-X pairs one WARP per pair
+// (w staged in a per-warp shared tile, lanes own the 16 exchange + 10 + 10 Coulomb outputs), X-H and H-H pairs one
+// thread per pair -- writes the exchange blocks F_AB and parks the Coulomb vectors J_A, J_B in shared memory;
+// pass 2 sums them per atom in a fixed order (no atomics) together with the one-centre terms.
+// shared: sP[n*n] | sJ[fock_scratch] | wbuf[warps][100]
+SEQM_D void tri_decode(int t, int m, int& i, int& j) {  // t-th pair (i<j) of m items, row-major
+  i = 0;
+  while (t >= m - 1 - i) {
+    t -= m - 1 - i;
+    ++i;
+  }
+  j = i + 1 + t;
+}
+SEQM_D int tri_index(int i, int j, int m) { return i * (2 * m - i - 1) / 2 + (j - i - 1); }
+
+SEQM_GLOBAL void fock_pair_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,
+                                  const double* __restrict__ w, double* __restrict__ F, const int32_t* __restrict__ active) {
+  const int m = b.mol_order[blockIdx.x];
+  if (active && !active[m]) return;
+  const MolView v = mol_view(b, m);
+  const int n = v.n, nh = v.nheavy, ny = v.nhyd;
+  const int nXX = nh * (nh - 1) / 2, nXH = nh * ny, nHH = ny * (ny - 1) / 2;
+  SEQM_DYN_SMEM(double, sP);
+  double* JXA = sP + ((n * n + 1) & ~1);  // [nXX][10] onto the first atom
+  double* JXB = JXA + 10 * nXX;           // [nXX][10] onto the second atom
+  double* JHA = JXB + 10 * nXX;           // [nXH][10] onto the heavy atom
+  double* JHB = JHA + 10 * nXH;           // [nXH]     onto the hydrogen
+  double* JHH = JHB + nXH;                // [nHH][2]
+  double* wbuf = sP + ((n * n + 1) & ~1) + b.fock_scratch;
+  const double* Pm = P + v.mat0;
+  const double* Hm = H + v.mat0;
+  double* Fm = F + v.mat0;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int t = tid; t < n * n; t += nthr) sP[t] = Pm[t];
+  SEQM_SYNC();
+  // ---- pass 1a: X-X pairs, one warp per pair
+  {
+    const int L = (nthr >= 32) ? 32 : 1;
+    const int lane = tid % L, wid = tid / L, nw = nthr / L;
+    double* wb = wbuf + wid * 100;
+    for (int t = wid; t < nXX; t += nw) {
+      int i, j;
+      tri_decode(t, nh, i, j);
+      const double* wp = w + (long long)(v.p0 + pair_local(v, i, j)) * 100;
+      for (int q = lane; q < 100; q += L) wb[q] = wp[q];
+      SEQM_SYNCWARP();
+      const int oi = 4 * i, oj = 4 * j;
+      for (int o = lane; o < 36; o += L) {
+        if (o < 16) {  // exchange
+          const int mu = o >> 2, la = o & 3;
+          double k = 0.0;
+          for (int nu = 0; nu < 4; ++nu)
+            for (int sg = 0; sg < 4; ++sg) k += sP[(oi + nu) * n + oj + sg] * wb[pack2(mu, nu) * 10 + pack2(la, sg)];
+          const int r = oi + mu, c = oj + la;
+          const double f = Hm[r * n + c] - 0.5 * k;
+          Fm[r * n + c] = f;
+          Fm[c * n + r] = f;
+        } else {
+          const bool ontoA = o < 26;
+          const int q = ontoA ? o - 16 : o - 26;      // packed index of the output
+          const int oo = ontoA ? oj : oi;             // the density comes from the OTHER atom
+          double s = 0.0;
+          for (int x = 0; x < 4; ++x)
+            for (int y = 0; y <= x; ++y) {
+              const int pk = pack2(x, y);
+              const double d = (x == y ? 1.0 : 2.0) * sP[(oo + y) * n + oo + x];
+              s += d * (ontoA ? wb[q * 10 + pk] : wb[pk * 10 + q]);
+            }
+          (ontoA ? JXA : JXB)[t * 10 + q] = s;
+        }
+      }
+      SEQM_SYNCWARP();
+    }
+  }
+  // ---- pass 1b: X-H pairs (column 0 of w only), one thread per pair
+  for (int t = tid; t < nXH; t += nthr) {
+    const int i = t / ny, hj = t - i * ny, j = nh + hj;
+    const double* wp = w + (long long)(v.p0 + pair_local(v, i, j)) * 100;
+    const int oi = 4 * i, oj = 4 * nh + hj;
+    double wc[10];
+    for (int kl = 0; kl < 10; ++kl) wc[kl] = wp[kl * 10];
+    const double pjj = sP[oj * n + oj];
+    double jb = 0.0;
+    for (int x = 0; x < 4; ++x)
+      for (int y = 0; y <= x; ++y) {
+        const int pk = pack2(x, y);
+        jb += (x == y ? 1.0 : 2.0) * sP[(oi + y) * n + oi + x] * wc[pk];
+        JHA[t * 10 + pk] = wc[pk] * pjj;
+      }
+    JHB[t] = jb;
+    for (int mu = 0; mu < 4; ++mu) {
+      double k = 0.0;
+      for (int nu = 0; nu < 4; ++nu) k += sP[(oi + nu) * n + oj] * wc[pack2(mu, nu)];
+      const int r = oi + mu;
+      const double f = Hm[r * n + oj] - 0.5 * k;
+      Fm[r * n + oj] = f;
+      Fm[oj * n + r] = f;
+    }
+  }
+  // ---- pass 1c: H-H pairs
+  for (int t = tid; t < nHH; t += nthr) {
+    int hi, hj;
+    tri_decode(t, ny, hi, hj);
+    const int i = nh + hi, j = nh + hj;
+    const double w00 = w[(long long)(v.p0 + pair_local(v, i, j)) * 100];
+    const int oi = 4 * nh + hi, oj = 4 * nh + hj;
+    JHH[2 * t] = w00 * sP[oj * n + oj];
+    JHH[2 * t + 1] = w00 * sP[oi * n + oi];
+    const double f = Hm[oi * n + oj] - 0.5 * sP[oi * n + oj] * w00;
+    Fm[oi * n + oj] = f;
+    Fm[oj * n + oi] = f;
+  }
+  SEQM_SYNC();
+  // ---- pass 2: diagonal blocks = Hcore + one-centre + sum of the parked Coulomb vectors (fixed order)
+  for (int t = tid; t < v.na * 10; t += nthr) {
+    const int a = t / 10, kl = t % 10;
+    if (a >= nh && kl > 0) continue;
+    int mu = 0;
+    while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
+    const int nu = kl - mu * (mu + 1) / 2;
+    const int oa = orb_off(v, a), ga = v.a0 + a;
+    const double gss = par(b, SEQM_P_GSS, ga), gsp = par(b, SEQM_P_GSP, ga), gpp = par(b, SEQM_P_GPP, ga);
+    const double gp2 = par(b, SEQM_P_GP2, ga), hsp = par(b, SEQM_P_HSP, ga);
+    const double Pss = sP[oa * n + oa];
+    double Ppt = 0.0;
+    if (a < nh) Ppt = sP[(oa + 1) * n + oa + 1] + sP[(oa + 2) * n + oa + 2] + sP[(oa + 3) * n + oa + 3];
+    double g;
+    if (mu == 0)
+      g = 0.5 * Pss * gss + Ppt * (gsp - 0.5 * hsp);
+    else if (nu == 0)
+      g = sP[oa * n + oa + mu] * (1.5 * hsp - 0.5 * gsp);
+    else if (mu == nu) {
+      const double Pk = sP[(oa + mu) * n + oa + mu];
+      g = Pss * (gsp - 0.5 * hsp) + 0.5 * Pk * gpp + (Ppt - Pk) * (1.25 * gp2 - 0.25 * gpp);
+    } else
+      g = sP[(oa + nu) * n + oa + mu] * (0.75 * gpp - 1.25 * gp2);
+    if (a < nh) {
+      for (int o = 0; o < a; ++o) g += JXB[tri_index(o, a, nh) * 10 + kl];
+      for (int o = a + 1; o < nh; ++o) g += JXA[tri_index(a, o, nh) * 10 + kl];
+      for (int hh = 0; hh < ny; ++hh) g += JHA[(a * ny + hh) * 10 + kl];
+    } else {
+      const int ha = a - nh;
+      for (int o = 0; o < nh; ++o) g += JHB[o * ny + ha];
+      for (int o = 0; o < ha; ++o) g += JHH[2 * tri_index(o, ha, ny) + 1];
+      for (int o = ha + 1; o < ny; ++o) g += JHH[2 * tri_index(ha, o, ny)];
+    }
+    const double f = Hm[(oa + mu) * n + oa + nu] + g;
+    Fm[(oa + mu) * n + oa + nu] = f;
+    Fm[(oa + nu) * n + oa + mu] = f;
+  }
+}
+static inline size_t fock_pair_smem_bytes(int nmax, int scratch, int threads) {
+  return sizeof(double) * ((size_t)((nmax * nmax + 1) & ~1) + scratch + (size_t)(threads / 32 + 1) * 100);
 }
 
 SEQM_GLOBAL void elec_energy_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,

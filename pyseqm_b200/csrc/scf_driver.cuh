@@ -151,11 +151,6 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
   if (threadIdx.x == 0) W.diis_err[mol] = rmax;
 }
 
-#ifndef SEQM_HOSTEMU
-#define SEQM_SYNCWARP() __syncwarp()
-#else
-#define SEQM_SYNCWARP() do { } while (0)
-#endif
 #define SEQM_DIIS_WARPS 4
 
 // DIIS step 2 (scf_loop.py:1009-1031): pseudo-inverse solve of the (cF+1)x(cF+1) Pulay system, one WARP per

@@ -66,6 +66,7 @@ static int ensure_device() {
 #undef SEQM_ATTR
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e != cudaSuccess) {
     seqm_set_error("cudaFuncSetAttribute(max dynamic shared memory %d): %s", dyn, cudaGetErrorString(e));
@@ -182,8 +183,14 @@ static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, 
     PROF(PK_FOCK, st, SEQM_LAUNCH(fock_large_diag_kernel, grid1d((long long)b->nat * 10, 128), 128, 0, st, *b, P, H, w, F, active));
     return seqm_check_launch("fock_large kernels");
   }
+  const int nt = threads_for(b->nmax);
+  const size_t sm_pair = fock_pair_smem_bytes(b->nmax, b->fock_scratch, nt);
+  if (b->fock_scratch > 0 && sm_pair <= (size_t)(g_smem_optin - 2048)) {  // pair-centric: w read once
+    PROF(PK_FOCK, st, SEQM_LAUNCH(fock_pair_kernel, b->nmol, nt, sm_pair, st, *b, P, H, w, F, active));
+    return seqm_check_launch("fock_pair_kernel");
+  }
   const size_t smem = sizeof(double) * (size_t)b->nmax * b->nmax;
-  PROF(PK_FOCK, st, SEQM_LAUNCH(fock_kernel, b->nmol, threads_for(b->nmax), smem, st, *b, P, H, w, F, active));
+  PROF(PK_FOCK, st, SEQM_LAUNCH(fock_kernel, b->nmol, nt, smem, st, *b, P, H, w, F, active));
   return seqm_check_launch("fock_kernel");
 }
 static int launch_pair_gradient(const seqm_batch_t* b, const double* xyz, const double* D, const double* P, double* gp,

@@ -146,6 +146,8 @@ class BatchPlan:
         s.pair_cls_off[0], s.pair_cls_off[1] = 0, cnt[0]
         s.pair_cls_off[2], s.pair_cls_off[3] = cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]
         s.pair_perm = self.pair_perm.data_ptr()
+        nxx, nxh, nhh = nheavy * (nheavy - 1) // 2, nheavy * nhyd, nhyd * (nhyd - 1) // 2
+        s.fock_scratch = int((20 * nxx + 11 * nxh + 2 * nhh).max())
         # eigensolver size classes over the descending-n processing order (host arrays inside the struct)
         n_sorted = norb[order].cpu().tolist()
         cls = [next((c for c, q in enumerate(JACOBI_NP) if 2 * q >= n), -1) for n in n_sorted]
