@@ -134,34 +134,24 @@ def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist):
             "finite": bool(torch.isfinite(mol.Etot).all() and torch.isfinite(Ek).all())}  # fmt: skip
 
 
-def _oracle_chunk(args):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import seqm_oracle as so
-
-    species, coords = args
-    out = so.single_point(species, coords, SP)
-    return out["Etot"]
-
-
 def cpu_reference_rate(sample, cores, steps=1, warmup=0):
-    """The oracle (numpy port of the reference's CPU path) on `sample` molecules over `cores` processes."""
-    import multiprocessing as mp
-
+    """The oracle (numpy port of the reference's CPU path) on the first `sample` molecules of the rank-0 batch, one
+    process, numpy's BLAS on all host threads -- the same execution model as the reference's own CPU path (torch
+    intra-op threads over one big batch), which it matches in speed (~23 molecule-SCF/s on 8 cores for this batch)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
+    import seqm_oracle as so
 
     species, coords, _ = workload(4096, 0)
     species, coords = species[:sample], coords[:sample]
-    chunks = [(species[i::cores], coords[i::cores]) for i in range(cores) if species[i::cores].shape[0] > 0]
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     times = []
-    with mp.get_context("fork").Pool(len(chunks)) as pool:
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            res = pool.map(_oracle_chunk, chunks)
-            dt = time.perf_counter() - t0
-            if it >= warmup:
-                times.append(dt)
-    assert all(np.all(np.isfinite(r)) for r in res)
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = so.single_point(species, coords, SP)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    assert np.all(np.isfinite(out["Etot"])) and not out["notconverged"].any()
     dt = sum(times) / len(times)
     return sample / dt, dt
 
@@ -171,16 +161,16 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = min(4096, max(64, 8 * cores))
-    rate, dt = cpu_reference_rate(sample, cores, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    sample = min(1024, 32 * cores)
+    rate, dt = cpu_reference_rate(sample, cores, steps=max(1, min(args.steps, 3)), warmup=0)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_dict(4096, args.gpus, workload(4096, 0)[2]),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"first {sample} molecules of the rank-0 batch, {cores} processes x 1 thread, "
-                                   "oracle/seqm_oracle (numpy restatement of the reference CPU path; the reference is "
-                                   "Python and cannot travel to the GPU box)"},
+                         "sample": f"first {sample} molecules of the rank-0 batch in one process, numpy BLAS on {cores} host "
+                                   "threads, oracle/seqm_oracle (numpy restatement of the reference CPU path; the reference "
+                                   "is Python and cannot travel to the GPU box)"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }  # fmt: skip
     print(json.dumps(line))
@@ -363,11 +353,11 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = args.cpu_sample or min(4096, max(64, 8 * cores))
+        sample = args.cpu_sample or min(1024, 32 * cores)
         rate, dt = cpu_reference_rate(sample, cores)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"first {sample} molecules of the same batch in {dt:.1f} s, {cores} processes x 1 "
-                                  "thread, oracle/seqm_oracle (numpy restatement of the reference CPU path)"}  # fmt: skip
+                        "sample": f"first {sample} molecules of the same batch in {dt:.1f} s, one process, numpy BLAS on "
+                                  f"{cores} host threads, oracle/seqm_oracle (numpy restatement of the reference CPU path)"}  # fmt: skip
 
     if rank == 0:
         line = {
