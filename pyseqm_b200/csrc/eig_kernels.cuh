@@ -119,11 +119,27 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t
     double* S = A;  // C0 staged in shared memory, standard layout, row stride n
     for (int t = tid; t < n * n; t += nthr) S[t] = C0[t];
     SEQM_SYNC();
-    for (int t = tid; t < n * n; t += nthr) {
-      const int i = t / n, j = t - i * n;
-      double acc = 0.0;
-      for (int k = 0; k < n; ++k) acc += Fm[i * n + k] * S[k * n + j];
-      G[t] = acc;  // T = F C0
+    {  // T = F C0 in 2x2 register blocks (halves the loads per FMA)
+      const int nb = (n + 1) >> 1;
+      for (int t = tid; t < nb * nb; t += nthr) {
+        const int i = 2 * (t / nb), j = 2 * (t % nb);
+        const int i1 = (i + 1 < n) ? i + 1 : i, j1 = (j + 1 < n) ? j + 1 : j;
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double f0 = Fm[i * n + k], f1 = Fm[i1 * n + k];
+          const double s0 = S[k * n + j], s1 = S[k * n + j1];
+          a00 += f0 * s0;
+          a01 += f0 * s1;
+          a10 += f1 * s0;
+          a11 += f1 * s1;
+        }
+        G[i * n + j] = a00;
+        if (j1 != j) G[i * n + j1] = a01;
+        if (i1 != i) {
+          G[i1 * n + j] = a10;
+          if (j1 != j) G[i1 * n + j1] = a11;
+        }
+      }
     }
 #ifndef SEQM_HOSTEMU
 #pragma unroll
@@ -136,12 +152,27 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t
       for (int c = 0; c < M; ++c) Vh[i * M + c] = (i < n && c < n) ? S[i * n + c] : ((i == c) ? 1.0 : 0.0);
 #endif
     SEQM_SYNC();
-    for (int t = tid; t < n * n; t += nthr) {
-      const int i = t / n, j = t - i * n;
-      if (j < i) continue;
-      double acc = 0.0;
-      for (int k = 0; k < n; ++k) acc += S[k * n + i] * G[k * n + j];
-      G2[t] = acc;  // upper triangle of C0^t T
+    {  // upper triangle of C0^t T, 2x2 register blocks
+      const int nb = (n + 1) >> 1;
+      for (int t = tid; t < nb * nb; t += nthr) {
+        const int bi = t / nb, bj = t % nb;
+        if (bj < bi) continue;
+        const int i = 2 * bi, j = 2 * bj;
+        const int i1 = (i + 1 < n) ? i + 1 : i, j1 = (j + 1 < n) ? j + 1 : j;
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double c0 = S[k * n + i], c1 = S[k * n + i1];
+          const double g0 = G[k * n + j], g1 = G[k * n + j1];
+          a00 += c0 * g0;
+          a01 += c0 * g1;
+          a10 += c1 * g0;
+          a11 += c1 * g1;
+        }
+        G2[i * n + j] = a00;
+        if (j1 != j) G2[i * n + j1] = a01;
+        if (i1 != i && j1 != j) G2[i1 * n + j1] = a11;
+        if (i1 != i && bj > bi) G2[i1 * n + j] = a10;
+      }
     }
     SEQM_SYNC();
     for (int t = tid; t < M * M; t += nthr) {
@@ -340,17 +371,30 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t
   if (Pout) {
     double* Pm = Pout + v.mat0;
     const int nocc = v.nocc;
-    for (int t = tid; t < n * n; t += nthr) {
-      const int i = t / n, j = t - i * n;
-      if (j < i) continue;
-      double acc = 0.0;
+    const int nb = (n + 1) >> 1;  // 2x2 register blocks over the upper block triangle
+    for (int t = tid; t < nb * nb; t += nthr) {
+      const int bi = t / nb, bj = t % nb;
+      if (bj < bi) continue;
+      const int i = 2 * bi, j = 2 * bj;
+      const int i1 = (i + 1 < n) ? i + 1 : i, j1 = (j + 1 < n) ? j + 1 : j;
+      double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
       for (int r = 0; r < nocc; ++r) {
         const int c = perm[r];
-        acc += V[i * M + c] * V[j * M + c];
+        const double x0 = V[i * M + c], x1 = V[i1 * M + c], y0 = V[j * M + c], y1 = V[j1 * M + c];
+        a00 += x0 * y0;
+        a01 += x0 * y1;
+        a10 += x1 * y0;
+        a11 += x1 * y1;
       }
-      acc *= 2.0;
-      Pm[i * n + j] = acc;
-      Pm[j * n + i] = acc;
+      a00 *= 2.0; a01 *= 2.0; a10 *= 2.0; a11 *= 2.0;
+      Pm[i * n + j] = a00;
+      Pm[j * n + i] = a00;
+      if (j1 != j) { Pm[i * n + j1] = a01; Pm[j1 * n + i] = a01; }
+      if (i1 != i) {
+        Pm[i1 * n + j] = a10;
+        Pm[j * n + i1] = a10;
+        if (j1 != j) { Pm[i1 * n + j1] = a11; Pm[j1 * n + i1] = a11; }
+      }
     }
   }
 }
