@@ -130,16 +130,37 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
   double dots[SEQM_NFOCK];
   for (int j = 0; j < SEQM_NFOCK; ++j) dots[j] = 0.0;
   double rmax = 0.0;
-  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
-    const int i = t / n, j = t % n;
-    if (j <= i) continue;
-    double s = 0.0;
-    for (int k = 0; k < n; ++k) s += sF[i * n + k] * sP[k * n + j] - sP[i * n + k] * sF[k * n + j];
-    Rh[i * n + j] = s;
-    Rh[j * n + i] = -s;
-    rmax = fmax(rmax, fabs(s));
-    for (int q = 0; q < cF; ++q)
-      dots[q] += s * ((q == counter) ? s : W.RES[h0 + (long long)q * nn + i * n + j]);
+  // R = F P - P F on the strict upper triangle (R is antisymmetric), 2x2 register blocks
+  const int nb = (n + 1) >> 1;
+  for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
+    const int bi = t / nb, bj = t % nb;
+    if (bj < bi) continue;
+    const int i = 2 * bi, j = 2 * bj;
+    const int i1 = (i + 1 < n) ? i + 1 : i, j1 = (j + 1 < n) ? j + 1 : j;
+    double r00 = 0.0, r01 = 0.0, r10 = 0.0, r11 = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double fi0 = sF[i * n + k], fi1 = sF[i1 * n + k], pi0 = sP[i * n + k], pi1 = sP[i1 * n + k];
+      const double pj0 = sP[k * n + j], pj1 = sP[k * n + j1], fj0 = sF[k * n + j], fj1 = sF[k * n + j1];
+      r00 += fi0 * pj0 - pi0 * fj0;
+      r01 += fi0 * pj1 - pi0 * fj1;
+      r10 += fi1 * pj0 - pi1 * fj0;
+      r11 += fi1 * pj1 - pi1 * fj1;
+    }
+    // the (up to) four elements of the block that lie strictly above the diagonal
+    const int ri[4] = {i, i, i1, i1}, rj[4] = {j, j1, j, j1};
+    const double rv[4] = {r00, r01, r10, r11};
+    for (int e = 0; e < 4; ++e) {
+      const int a = ri[e], c = rj[e];
+      if (c <= a) continue;
+      if ((e == 1 || e == 3) && j1 == j) continue;  // clamped duplicate column
+      if ((e == 2 || e == 3) && i1 == i) continue;  // clamped duplicate row
+      const double sv = rv[e];
+      Rh[a * n + c] = sv;
+      Rh[c * n + a] = -sv;
+      rmax = fmax(rmax, fabs(sv));
+      for (int q = 0; q < cF; ++q)
+        dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + a * n + c]);
+    }
   }
   for (int t = threadIdx.x; t < n; t += blockDim.x) Rh[t * n + t] = 0.0;
   rmax = block_max(rmax, red);
