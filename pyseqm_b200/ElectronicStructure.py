@@ -7,6 +7,26 @@ from .basics import Force, ForceXL
 from .Molecule import reject_unsupported
 
 
+def orbital_charge_table(v, nHeavy, nHydro, molsize):
+    """Literal restatement of scf_loop.py:2346-2387 (closed shell): with v2 = v**2,
+       charge[i, :norb, :nH]      = v2[i][:norb, :4 nH].reshape(norb, 4, nH).sum(1)
+       charge[i, :norb, nH:nH+ny] = v2[i][:norb, 4 nH : 4 nH + ny]
+    grouped by (nHeavy, nHydro) so that each group is one batched tensor expression."""
+    nmol = v.shape[0]
+    out = torch.zeros((nmol, 4 * molsize, molsize), dtype=v.dtype, device=v.device)
+    key = nHeavy * 1000 + nHydro
+    for k in torch.unique(key).tolist():
+        nh, ny = k // 1000, k % 1000
+        sel = torch.nonzero(key == k, as_tuple=False).squeeze(1)
+        norb = 4 * nh + ny
+        v2 = v[sel][:, :norb, :norb] ** 2
+        if nh > 0:
+            out[sel, :norb, :nh] = v2[:, :, : 4 * nh].reshape(-1, norb, 4, nh).sum(dim=2)
+        if ny > 0:
+            out[sel, :norb, nh : nh + ny] = v2[:, :, 4 * nh : 4 * nh + ny]
+    return out
+
+
 class Electronic_Structure(torch.nn.Module):
     def __init__(self, seqm_parameters, *args, **kwargs):
         super().__init__()
@@ -14,8 +34,21 @@ class Electronic_Structure(torch.nn.Module):
         self.seqm_parameters = seqm_parameters
         self.conservative_force = Force(seqm_parameters)
         self.conservative_force_xl = ForceXL(seqm_parameters)
-        self.charge = None
+        self._charge = None
+        self._charge_src = None
         self.notconverged = None
+
+    @property
+    def charge(self):
+        """Per-orbital atomic "charge" table (nmol, 4*molsize, molsize) of scf_loop.py:2346-2387, evaluated lazily
+        from the eigenvectors of the last forward (it is a by-product nobody on the hot path consumes)."""
+        if self._charge is None and self._charge_src is not None:
+            self._charge = orbital_charge_table(*self._charge_src)
+        return self._charge
+
+    @charge.setter
+    def charge(self, value):
+        self._charge = value
 
     @staticmethod
     def atomic_charges(P, n_orbital=4):
@@ -30,9 +63,13 @@ class Electronic_Structure(torch.nn.Module):
         kwargs.pop("cis_amp", None)
         if dm_prop == "SCF":
             (molecule.force, P, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso, molecule.e_mo,
-             molecule.e_gap, self.charge, self.notconverged) = self.conservative_force(
+             molecule.e_gap, _, self.notconverged) = self.conservative_force(
                 molecule, P0=P0, learned_parameters=learned_parameters, *args, **kwargs)  # fmt: skip
             molecule.dm = P.detach()
+            self._charge = None
+            self._charge_src = None
+            if molecule.molecular_orbitals is not None:
+                self._charge_src = (molecule.molecular_orbitals, molecule.nHeavy, molecule.nHydro, molecule.molsize)
         elif dm_prop == "XL-BOMD":
             (molecule.force, molecule.dm, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso,
              molecule.e_mo, molecule.e_gap, molecule.Electronic_entropy, molecule.dP2dt2, molecule.Krylov_Error,

@@ -148,13 +148,16 @@ class BatchPlan:
         s.pair_perm = self.pair_perm.data_ptr()
         nxx, nxh, nhh = nheavy * (nheavy - 1) // 2, nheavy * nhyd, nhyd * (nhyd - 1) // 2
         s.fock_scratch = int((20 * nxx + 11 * nxh + 2 * nhh).max())
-        # eigensolver size classes over the descending-n processing order (host arrays inside the struct)
-        n_sorted = norb[order].cpu().tolist()
-        cls = [next((c for c, q in enumerate(JACOBI_NP) if 2 * q >= n), -1) for n in n_sorted]
-        for c in range(len(JACOBI_NP)):
-            idx = [k for k, x in enumerate(cls) if x == c]
-            s.cls_begin[c] = idx[0] if idx else 0
-            s.cls_count[c] = len(idx)
+        # eigensolver size classes over the descending-n processing order (host arrays inside the struct):
+        # class c = smallest NP with 2*NP >= n; molecules beyond the last class (large path) belong to none
+        bounds = torch.tensor([2 * q for q in JACOBI_NP], device=dev)
+        cls = torch.bucketize(norb, bounds)  # == len(JACOBI_NP) for n > 2*NP_max
+        cnt = torch.bincount(cls, minlength=len(JACOBI_NP) + 1).cpu().tolist()
+        begin = cnt[len(JACOBI_NP)]  # mol_order is descending in n: the too-large molecules come first
+        for c in range(len(JACOBI_NP) - 1, -1, -1):
+            s.cls_begin[c] = begin
+            s.cls_count[c] = cnt[c]
+            begin += cnt[c]
         self.struct = s
         self.ref = C.byref(s)
         self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path

@@ -49,3 +49,18 @@ def test_user_P0_is_updated_in_place(lib):
     assert mol.dm.data_ptr() == P0.data_ptr()
     assert mol.n_scf_iter <= 3  # restart from the converged density
     assert np.abs(mol.Etot.numpy() - g["Etot"]).max() < 1e-6
+
+
+def test_lazy_orbital_charge_table(lib):
+    """esdriver.charge (scf_loop.py:2346-2387) is built lazily from the eigenvectors; every row of the
+    orthogonal eigenvector matrix carries unit weight in total."""
+    from conftest import load_golden
+
+    g = load_golden("cfg1_AM1_c2")
+    mol, es = run_molecule(lib, CPU, g["species"], g["coordinates"], g["seqm_parameters"])
+    c = es.charge
+    assert tuple(c.shape) == (3, 4 * mol.molsize, mol.molsize)
+    norb = (4 * mol.nHeavy + mol.nHydro).tolist()
+    for m in range(3):
+        assert np.abs(c[m, : norb[m]].sum(dim=1).numpy() - 1.0).max() < 1e-12
+        assert float(c[m, norb[m] :].abs().max()) == 0.0
