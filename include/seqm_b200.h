@@ -60,7 +60,7 @@ typedef struct seqm_batch {
   const int32_t* pair_j;    /* [npairs] */
   double* atom_par;         /* [SEQM_NPAR * nat] */
   /* HOST arrays: eigensolver size classes.  Class c holds the molecules with n <= 2*np_c orbitals
-   * (np_c = 4,8,...,32,40,48,56,60) that do not fit class c-1; they occupy the contiguous range
+   * (np_c = 4,8,...,32,40,48,56,64) that do not fit class c-1; they occupy the contiguous range
    * mol_order[cls_begin[c] .. cls_begin[c]+cls_count[c]) because mol_order is sorted by descending n. */
   int32_t cls_begin[12];
   int32_t cls_count[12];

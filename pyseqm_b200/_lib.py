@@ -37,7 +37,7 @@ class SeqmBatchStruct(C.Structure):
         ("pair_cls_off", C.c_int32 * 4), ("pair_perm", C.c_void_p), ("fock_scratch", C.c_int32),
     ]  # fmt: skip
 
-JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 60)
+JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64)
 
 
 class SeqmScfOpts(C.Structure):

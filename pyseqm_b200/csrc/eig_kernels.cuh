@@ -35,22 +35,24 @@ struct alignas(16) seqm_d2 { double x, y; };
 //   * A lives in shared memory in two column planes (even columns | odd columns, row stride LD padded so
 //     that the row segments touched by one warp fall in disjoint banks): every access of both the even and
 //     the odd step is a conflict-free 64-bit access with unit lane stride.
-//   * V never touches shared memory during the sweeps: thread (row i, quarter s) keeps m/4 consecutive
-//     entries of row i in registers; the one pair that straddles two quarters in odd steps is exchanged with
-//     two 64-bit shuffles inside the 4-lane group.
+//   * V never touches shared memory during the sweeps: thread (row i, segment s) keeps m/SR consecutive
+//     entries of row i in registers (SR = 4 threads per row, 8 for the classes with NP >= 40); the one pair that
+//     straddles two segments in odd steps is exchanged with two 64-bit shuffles inside the SR-lane group.
 //   * per pair l the transform is x' = a x + b y, y' = b x - a y with (a,b) = (sin, cos) [rotate + swap],
 //     (0,1) [swap only, |a_pq| below threshold] or (1,0) for the wrap pair (m-1,0) of odd steps (identity up
 //     to the sign of slot 0, which is irrelevant for an eigenbasis).
 // Slots n..m-1 are decoupled dummies whose diagonal lies above the Gershgorin bound; they rank last.
-// blockDim.x must be 4*m (V ownership); tiles are strided over all threads.
+// blockDim.x must be SR*m (V ownership); tiles are strided over all threads.
 // shared: A[m*LD] | cs[NP] (double2) | scr[40] | dg[m] | perm[m] (int)
 // ---------------------------------------------------------------------------------------------------
 template <int NP>
 struct JacobiCfg {
   static constexpr int M = 2 * NP;
   static constexpr int LD = M + ((NP / 2) % 8);
-  static constexpr int SEG = NP / 2;  // V entries per thread (4 threads per row)
-  static constexpr int THREADS = 4 * M;
+  static constexpr int SR = (NP >= 40) ? 8 : 4;  // threads per row of V (more for the big classes: 1 CTA/SM there,
+                                                 // so the CTA itself must bring enough warps to hide latency)
+  static constexpr int SEG = M / SR;             // V entries per thread
+  static constexpr int THREADS = SR * M;
   static constexpr size_t SMEM = sizeof(double) * ((size_t)M * LD + 2 * NP + 40 + M) + sizeof(int) * (M + 4);
 };
 
@@ -86,11 +88,11 @@ SEQM_HD void jacobi_tile_offsets(int k, int l, int* oe, int* oo) {
 }
 
 template <int NP>
-SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
                                      double* __restrict__ evals, double* __restrict__ Cout,
                                      const double* __restrict__ Cguess, const int32_t* __restrict__ active) {
   typedef JacobiCfg<NP> K;
-  constexpr int M = K::M, LD = K::LD, SEG = K::SEG;
+  constexpr int M = K::M, LD = K::LD, SEG = K::SEG, SR = K::SR;
   const int mol = b.mol_order[first + blockIdx.x];
   if (active && !active[mol]) return;
   const MolView v = mol_view(b, mol);
@@ -106,7 +108,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t
   const bool warm = (Cguess != nullptr);
 #ifndef SEQM_HOSTEMU
   double vr[SEG];  // V[row][seg*SEG .. seg*SEG+SEG-1]
-  const int vrow = tid >> 2, vseg = tid & 3;
+  const int vrow = tid / SR, vseg = tid % SR;
 #else
   static double Vh[128 * 128];  // host emulation keeps V in memory (one "thread" plays all owners)
 #endif
@@ -311,8 +313,8 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t
       } else {
         const int lane = tid & 31;
         const double first_old = vr[0], last_old = vr[SEG - 1];
-        const double y_next = __shfl_sync(0xffffffffu, first_old, (lane & ~3) | ((lane + 1) & 3));
-        const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~3) | ((lane + 3) & 3));
+        const double y_next = __shfl_sync(0xffffffffu, first_old, (lane & ~(SR - 1)) | ((lane + 1) & (SR - 1)));
+        const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~(SR - 1)) | ((lane + SR - 1) & (SR - 1)));
 #pragma unroll
         for (int j = 0; j < SEG / 2 - 1; ++j) {
           const seqm_d2 c = cs[vseg * (SEG / 2) + j];
@@ -400,8 +402,8 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(4 * 2 * NP) jacobi_fixed_kernel(seqm_batch_t
 }
 
 // size classes: a molecule with n orbitals runs in the smallest NP with 2*NP >= n
-#define SEQM_JACOBI_CLASSES(X) X(4) X(8) X(12) X(16) X(20) X(24) X(28) X(32) X(40) X(48) X(56) X(60)
-static const int g_jacobi_np[] = {4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 60};
+#define SEQM_JACOBI_CLASSES(X) X(4) X(8) X(12) X(16) X(20) X(24) X(28) X(32) X(40) X(48) X(56) X(64)
+static const int g_jacobi_np[] = {4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64};
 static const int g_jacobi_ncls = 12;
 static inline int jacobi_class_of(int n) {
   for (int c = 0; c < g_jacobi_ncls; ++c)
