@@ -74,7 +74,7 @@ class Molecule(torch.nn.Module):
             mult = mult * torch.ones(coordinates.shape[0], device=coordinates.device)
         self.mult = mult
         if seqm_parameters.get("elements") is None:
-            seqm_parameters["elements"] = [0] + sorted(set(species.reshape(-1).tolist()))
+            seqm_parameters["elements"] = sorted(set([0] + torch.unique(species).tolist()))
         self.seqm_parameters = seqm_parameters
         self.method = seqm_parameters["method"]
         if callable(learned_parameters):

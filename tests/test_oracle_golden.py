@@ -13,23 +13,34 @@ from conftest import GOLDEN, TOL_DM, TOL_E, TOL_F, load_golden
 XYZ = os.path.join(GOLDEN, "xyz")
 
 CASES = [f"cfg1_{m}_{c}" for m in ("AM1", "PM3", "MNDO", "PM6_SP") for c in ("c2", "c1", "c0")] + [
-    "cfg2_PM6_SP_24",
+    "cfg2_PM6_SP_24", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2",
     "cfg1_AM1_sp2", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48", "cfg3_coronene_AM1",
 ]  # fmt: skip
+
+
+# MNDO PH3: the pseudo-inverse of a cond=1e12 EMAT (scf_loop.py:1024-1033) feeds rounding noise of the eigensolver
+# into F at the 1e-4 level, so the number of iterations to convergence is not reproducible between LAPACK builds
+CHAOTIC_DIIS = {"thirdrow_MNDO_c2"}
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_single_point_matches_reference(name):
     g = load_golden(name)
     out = so.single_point(g["species"], g["coordinates"], g["seqm_parameters"])
-    assert out["n_scf_iter"] == g["n_scf_iter"]
+    if name not in CHAOTIC_DIIS:
+        assert out["n_scf_iter"] == g["n_scf_iter"]
     assert not out["notconverged"].any() and not g["notconverged"].any()
-    for k in ("Etot", "Hf", "Eelec", "Enuc", "Eiso", "e_gap"):
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "Eiso"):
         assert np.abs(out[k] - g[k]).max() < TOL_E, k
-    assert np.abs(out["dm"] - g["dm"]).max() < TOL_DM
+    # the third-row set runs through ill-conditioned (cond up to 1e12-1e16) DIIS solves that amplify
+    # LAPACK-vs-LAPACK rounding to ~2e-7 in P (energies still agree to 1e-12): looser density check there
+    tol_dm = 1e-6 if name.startswith("thirdrow") else TOL_DM
+    assert np.abs(out["dm"] - g["dm"]).max() < tol_dm
+    tol_orb = 1e-5 if name.startswith("thirdrow") else TOL_E  # orbital energies are first order in that noise
+    assert np.abs(out["e_gap"] - g["e_gap"]).max() < tol_orb
     if "e_mo" in g:
-        assert np.abs(out["e_mo"] - g["e_mo"]).max() < TOL_E
-    assert np.abs(out["q"] - g["q"]).max() < TOL_DM
+        assert np.abs(out["e_mo"] - g["e_mo"]).max() < tol_orb
+    assert np.abs(out["q"] - g["q"]).max() < tol_dm
     assert np.abs(out["force"] - g["force"]).max() < TOL_F
 
 
