@@ -280,7 +280,8 @@ def main():
         out_nc.copy_(es.notconverged, non_blocking=True)
         torch.cuda.synchronize()
 
-    step_e2e()
+    for _ in range(max(1, min(args.warmup, 3))):
+        step_e2e()
     e2e_t = []
     for _ in range(args.steps):
         flush.fill_(1.0)
@@ -289,6 +290,7 @@ def main():
         step_e2e()
         e2e_t.append(time.perf_counter() - t0)
         barrier()
+    print("e2e step times (ms):", [round(t * 1e3, 2) for t in e2e_t], file=sys.stderr)
     t_e2e = torch.tensor([sum(e2e_t) / len(e2e_t)], device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
