@@ -36,7 +36,7 @@ class Tables:
         return cls._inst
 
 
-_NGAUSS = {"MNDO": 0, "AM1": 4, "PM3": 2, "PM6_SP": 4}
+_NGAUSS = {"MNDO": 0, "AM1": 4, "PM3": 2, "PM6_SP": 4, "PM6": 4}
 
 
 def method_parameters(method, Z):

@@ -68,7 +68,7 @@ class Electronic_Structure(torch.nn.Module):
             molecule.dm = P.detach()
             self._charge = None
             self._charge_src = None
-            if molecule.molecular_orbitals is not None:
+            if molecule.molecular_orbitals is not None and molecule.method != "PM6":  # scf_loop.py:2350: none for PM6
                 self._charge_src = (molecule.molecular_orbitals, molecule.nHeavy, molecule.nHydro, molecule.molsize)
         elif dm_prop == "XL-BOMD":
             (molecule.force, molecule.dm, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso,
@@ -78,7 +78,8 @@ class Electronic_Structure(torch.nn.Module):
         else:
             raise NotImplementedError(f"dm_prop={dm_prop!r} is not implemented by the B200 path")
         with torch.no_grad():
-            molecule.q = molecule.const.tore[molecule.species] - self.atomic_charges(molecule.dm)
+            molecule.q = molecule.const.tore[molecule.species] - self.atomic_charges(
+                molecule.dm, n_orbital=getattr(molecule, "orbital_stride", 4))
 
     def get_force(self):
         return self.force

@@ -148,7 +148,12 @@ class XL_BOMD(Molecular_Dynamics_Basic):
         super().initialize(molecule, remove_com=remove_com, learned_parameters=learned_parameters, steps=steps)
         plan = molecule._plan
         with torch.no_grad():
-            Dp = engine.op_pack(plan, molecule.dm)  # converged SCF density at t = 0
+            dm = molecule.dm
+            if molecule.orbital_stride != 4:  # method="PM6": back to the 4-slot layout the packed kernels use
+                from .Molecule import narrow_orbitals
+
+                dm = narrow_orbitals(dm, plan.molsize, molecule.orbital_stride)
+            Dp = engine.op_pack(plan, dm)  # converged SCF density at t = 0
             self._ctx = {"P": Dp.clone(), "Pt": Dp.unsqueeze(0).repeat(self.m, 1), "D": Dp}
         self.coeff = self.coeff.to(molecule.coordinates.device)
 
@@ -188,4 +193,8 @@ class XL_BOMD(Molecular_Dynamics_Basic):
         out = super().run(molecule, steps, *args, **kwargs)
         if self._ctx is not None:
             molecule.dm = engine.op_unpack(molecule._plan, self._ctx["D"])  # dense density of the last step
+            if molecule.orbital_stride != 4:
+                from .Molecule import widen_orbitals
+
+                molecule.dm = widen_orbitals(molecule.dm, molecule._plan.molsize, molecule.orbital_stride)
         return out

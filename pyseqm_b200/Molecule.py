@@ -11,7 +11,28 @@ import torch
 from . import engine
 from ._lib import get_lib
 
-SUPPORTED_METHODS = ("MNDO", "AM1", "PM3", "PM6_SP")
+SUPPORTED_METHODS = ("MNDO", "AM1", "PM3", "PM6_SP", "PM6")
+
+
+def pm6_d_shell(species):
+    """Elements that carry a d shell in the reference's PM6 (the nSuperHeavy set, seqm/basics.py:258-269)."""
+    s = species
+    return (((s > 12) & (s < 18)) | ((s > 20) & (s < 30)) | ((s > 32) & (s < 36)) | ((s > 38) & (s < 48))
+            | ((s > 50) & (s < 54)) | ((s > 70) & (s < 80)) | (s == 57))  # fmt: skip
+
+
+def widen_orbitals(P4, molsize, stride=9):
+    """(nmol, 4 molsize, 4 molsize) -> (nmol, 9 molsize, 9 molsize): the reference's PM6 layout keeps 9 orbital
+    slots per atom (s, px, py, pz, 5 d) and leaves the d slots of sp-only atoms zero (packd.py:195-218)."""
+    b = P4.shape[0]
+    out = torch.zeros((b, molsize, stride, molsize, stride), dtype=P4.dtype, device=P4.device)
+    out[:, :, :4, :, :4] = P4.view(b, molsize, 4, molsize, 4)
+    return out.view(b, stride * molsize, stride * molsize)
+
+
+def narrow_orbitals(P9, molsize, stride=9):
+    b = P9.shape[0]
+    return P9.reshape(b, molsize, stride, molsize, stride)[:, :, :4, :, :4].reshape(b, 4 * molsize, 4 * molsize).contiguous()
 
 
 def check_input(species):
@@ -80,7 +101,19 @@ class Molecule(torch.nn.Module):
         if callable(learned_parameters):
             raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
         lib = _lib if _lib is not None else get_lib()
-        plan = engine.BatchPlan(lib, species, self.method, parameters=learned_parameters, charges=charges)
+        # method="PM6" on elements without a d shell is numerically PM6_SP with the PM6 parameter file; the results
+        # are widened to the reference's 9-slot layout.  d-shell elements (a17) are not on the B200 path yet.
+        self.orbital_stride = 9 if self.method == "PM6" else 4
+        kernel_method, table = self.method, None
+        if self.method == "PM6":
+            if bool(pm6_d_shell(species).any()):
+                bad = sorted(set(species[pm6_d_shell(species)].tolist()))
+                raise NotImplementedError(
+                    f"method 'PM6' with d-shell elements Z={bad} is not implemented by the B200 path yet "
+                    "(sp-only elements are; 'PM6_SP' treats every element with an sp basis)"
+                )
+            kernel_method, table = "PM6_SP", "PM6"
+        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned_parameters, charges=charges, table=table)
         self._plan = plan
         dev = coordinates.device
         self.nmol, self.molsize = plan.nmol, plan.molsize
@@ -102,7 +135,7 @@ class Molecule(torch.nn.Module):
             raise NotImplementedError("pair_outer_cutoff that removes pairs is not supported by the B200 path yet")
         # per-atom parameter dict (Molecule.py:86-115)
         names = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha"]
-        ng = {"MNDO": 0, "AM1": 4, "PM3": 2, "PM6_SP": 4}[self.method]
+        ng = {"MNDO": 0, "AM1": 4, "PM3": 2, "PM6_SP": 4, "PM6": 4}[self.method]
         for g in range(1, ng + 1):
             names += [f"Gaussian{g}_K", f"Gaussian{g}_L", f"Gaussian{g}_M"]
         self.parameters = {k: plan.parameter(k) for k in names}

@@ -7,7 +7,7 @@ import warnings
 import torch
 
 from . import engine
-from .Molecule import reject_unsupported
+from .Molecule import narrow_orbitals, reject_unsupported, widen_orbitals
 from .seqm_functions.constants import ev_kcalpmol  # noqa: F401
 
 
@@ -51,7 +51,11 @@ class Energy(torch.nn.Module):
         H = engine.op_hcore(plan, w, hab)
         t0 = _timing(molecule, "Hcore + STO Integrals", t0)
         # density: initial guess or the caller's P0 (overwritten in place, ElectronicStructure.py:78)
-        P = engine.op_initial_density(plan) if P0 is None else engine.op_pack(plan, P0)
+        wide = molecule.orbital_stride != 4  # method="PM6": 9 orbital slots per atom in every dense tensor
+        if P0 is None:
+            P = engine.op_initial_density(plan)
+        else:
+            P = engine.op_pack(plan, narrow_orbitals(P0, plan.molsize, molecule.orbital_stride) if wide else P0)
         F, Eelec, notconv, n_iter, Clast = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
                                                          warm_start=self.warm_start, want_C=True)  # fmt: skip
         molecule.n_scf_iter = n_iter
@@ -64,12 +68,16 @@ class Energy(torch.nn.Module):
             warnings.warn("SCF for %d/%d molecules doesn't converge after %d iterations" % (nnot, plan.nmol, 1000))
         t0 = _timing(molecule, "SCF", t0)
         self.notconverged = notconv
-        molecule.w = w
+        if wide:  # (npairs, 45, 45), sp pairs first, the roles of the two atoms swapped (hcore.py:143-146)
+            molecule.w = torch.zeros((w.shape[0], 45, 45), dtype=w.dtype, device=w.device)
+            molecule.w[:, :10, :10] = w.transpose(1, 2)
+        else:
+            molecule.w = w
         molecule._gam = w[:, 0, 0]
         if self.eig and plan.large:
             # final eigenpairs of a large molecule: one cuSOLVER call outside the SCF hot loop
             Fd = engine.op_unpack(plan, F)
-            N = 4 * plan.molsize
+            N = molecule.orbital_stride * plan.molsize
             e_mo = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
             V = torch.zeros((plan.nmol, plan.nmax, plan.nmax), dtype=torch.float64, device=plan.device)
             for m in range(plan.nmol):
@@ -85,7 +93,7 @@ class Energy(torch.nn.Module):
             # eigenpairs of the converged Fock matrix, warm-started from the last SCF eigenbasis
             e_mo_n, _, Cm = engine.op_eig_density(plan, F, want_P=False, want_C=True,
                                                   Cguess=Clast if self.warm_start else None)  # fmt: skip
-            N = 4 * plan.molsize
+            N = molecule.orbital_stride * plan.molsize
             e_mo = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
             e_mo[:, : plan.nmax] = e_mo_n
             lumo = plan.nocc.unsqueeze(1)
@@ -102,11 +110,13 @@ class Energy(torch.nn.Module):
             grad = grad.reshape(plan.nmol, plan.molsize, 3)
             molecule.analytical_gradient = grad
             t0 = _timing(molecule, "Force", t0)
-        Pd = engine.op_unpack(plan, P, out=P0 if (P0 is not None and P0.is_contiguous()) else None)
+        Pd = engine.op_unpack(plan, P, out=P0 if (P0 is not None and P0.is_contiguous() and not wide) else None)
+        _ground_dipole(molecule, Pd)
+        if wide:
+            Pd = widen_orbitals(Pd, plan.molsize, molecule.orbital_stride)
         if P0 is not None and Pd is not P0:
             P0.copy_(Pd)
             Pd = P0
-        _ground_dipole(molecule, Pd)
         Etot = Eelec + Enuc
         Z = plan.Z
         Eiso_atom = (
@@ -196,6 +206,8 @@ class ForceXL(torch.nn.Module):
     def forward(self, molecule, P, cis_amp=None, learned_parameters=dict(), xl_bomd_params=dict(), *args, **kwargs):
         if xl_bomd_params and "max_rank" in xl_bomd_params:
             raise NotImplementedError("KSA-XL-BOMD (max_rank) is not part of the B200 path")
+        if molecule.orbital_stride != 4:
+            raise NotImplementedError("XL-BOMD with method='PM6' is not on the B200 path; use 'PM6_SP' for sp-only elements")
         plan = molecule._plan
         r = self.forward_packed(molecule, engine.op_pack(plan, P))
         Dd = engine.op_unpack(plan, r["D"])

@@ -49,7 +49,7 @@ def method_table(method):
 class BatchPlan:
     """Index tensors of one molecule batch (topology only; coordinates are passed per call)."""
 
-    def __init__(self, lib, species, method, parameters=None, charges=0):
+    def __init__(self, lib, species, method, parameters=None, charges=0, table=None):
         if method not in METHOD_ID:
             raise NotImplementedError(
                 f"method {method!r} is not implemented by the B200 path (supported: {sorted(METHOD_ID)})"
@@ -107,7 +107,7 @@ class BatchPlan:
         self.atom_mol, self.atom_local = atom_mol, local
         self.pair_i, self.pair_j = pair_i, pair_j
         # per-atom parameter table
-        tab, cols, pw = method_table(method)
+        tab, cols, pw = method_table(table or method)
         tabd = tab.to(dev)
         par = torch.zeros((NPAR, self.nat), dtype=torch.float64, device=dev)
         for r, name in enumerate(PAR_ROWS[:24]):

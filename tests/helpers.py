@@ -5,6 +5,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 import torch
 
 from conftest import ROOT, TOL_DM, TOL_E, TOL_F, load_golden
@@ -96,3 +97,31 @@ def check_operator_level(lib, device, method):
     idx = packed_index(int(plan.nheavy[m]), int(plan.nhyd[m]))
     assert np.abs(d[m][np.ix_(idx, idx)] - g["op_sp2_packed"][m]).max() < 1e-9
     return plan
+
+
+def check_pm6_sp_elements(lib, device):
+    """method="PM6" on elements without a d shell: the reference's 9-slot layout of dm / e_mo / w and its
+    `charge=None`, P0 accepted in that layout; d-shell elements are refused loudly."""
+    mol = check_golden_case(lib, device, "pm6_sp_elements_c2")
+    g = load_golden("pm6_sp_elements_c2")
+    ms = g["species"].shape[1]
+    assert tuple(mol.dm.shape) == (4, 9 * ms, 9 * ms) and tuple(mol.e_mo.shape) == (4, 9 * ms)
+    assert tuple(mol.w.shape) == (g["w_sp"].shape[0], 45, 45)
+    w = mol.w.cpu().numpy()
+    assert np.abs(w[:, :10, :10] - g["w_sp"]).max() < 1e-10 and np.abs(w[:, 10:, :]).max() == 0.0
+    # restart from the converged density in the wide layout, updated in place
+    P0 = torch.as_tensor(g["dm"], device=device).clone()
+    mol2, es2 = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"], P0=P0)
+    assert mol2.dm.data_ptr() == P0.data_ptr() and mol2.n_scf_iter <= 3 and es2.charge is None
+    assert np.abs(mol2.Etot.cpu().numpy() - g["Etot"]).max() < TOL_E
+    # adaptive-mixing converger on a QM9-like batch (density pinned through its diagonal)
+    g = load_golden("pm6_sp_elements_qm9_12_c1")
+    mol3, es3 = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"])
+    assert mol3.n_scf_iter == g["n_scf_iter"] and not bool(es3.notconverged.any())
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "e_gap"):
+        assert np.abs(getattr(mol3, k).cpu().numpy() - g[k]).max() < TOL_E, k
+    assert np.abs(mol3.dm.diagonal(dim1=1, dim2=2).cpu().numpy() - g["dm_diag"]).max() < TOL_DM
+    assert np.abs(mol3.force.cpu().numpy() - g["force"]).max() < TOL_F
+    with pytest.raises(NotImplementedError, match="d-shell"):
+        run_molecule(lib, device, np.array([[16, 1, 1]]), np.array([[[0.0, 0, 0], [0.96, 0.9, 0], [-0.96, 0.9, 0]]]),
+                     {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2]})

@@ -44,6 +44,12 @@ def test_single_point_golden(lib, dev, name):
     check_golden_case(lib, dev, name)
 
 
+def test_pm6_on_elements_without_d_shell(lib, dev):
+    from helpers import check_pm6_sp_elements
+
+    check_pm6_sp_elements(lib, dev)
+
+
 def test_autograd_mode_forces_of_reference(lib, dev):
     g = load_golden("cfg1_AM1_autograd")
     mol, _ = run_molecule(lib, dev, g["species"], g["coordinates"], g["seqm_parameters"])

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import check_golden_case, check_operator_level, hostemu_lib, run_molecule
+from helpers import check_golden_case, check_operator_level, check_pm6_sp_elements, hostemu_lib, run_molecule
 
 CPU = torch.device("cpu")
 
@@ -28,6 +28,10 @@ def test_operator_level(lib, method):
 )  # fmt: skip
 def test_single_point_golden(lib, name):
     check_golden_case(lib, CPU, name)
+
+
+def test_pm6_on_elements_without_d_shell(lib):
+    check_pm6_sp_elements(lib, CPU)
 
 
 def test_sp2_route(lib):
