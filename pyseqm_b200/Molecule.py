@@ -100,7 +100,6 @@ class Molecule(torch.nn.Module):
         self.method = seqm_parameters["method"]
         if callable(learned_parameters):
             raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
-        lib = _lib if _lib is not None else get_lib()
         # method="PM6" on elements without a d shell is numerically PM6_SP with the PM6 parameter file; the results
         # are widened to the reference's 9-slot layout.  d-shell elements (a17) are not on the B200 path yet.
         self.orbital_stride = 9 if self.method == "PM6" else 4
@@ -113,6 +112,7 @@ class Molecule(torch.nn.Module):
                     "(sp-only elements are; 'PM6_SP' treats every element with an sp basis)"
                 )
             kernel_method, table = "PM6_SP", "PM6"
+        lib = _lib if _lib is not None else get_lib()
         plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned_parameters, charges=charges, table=table)
         self._plan = plan
         dev = coordinates.device

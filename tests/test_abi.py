@@ -59,7 +59,10 @@ def test_option_matrix_rejections():
 
     species = torch.tensor([[6, 1, 1, 1, 1]])
     coords = torch.randn(1, 5, 3, dtype=torch.float64)
-    for bad in ({"method": "PM6"}, {"UHF": True}, {"excited_states": {"n_states": 2}}, {"scf_backward": 1},
+    with pytest.raises(NotImplementedError, match="d-shell"):  # PM6 is served only for elements without a d shell
+        seqm.Molecule(seqm.Constants(), {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2]},
+                      torch.randn(1, 3, 3, dtype=torch.float64), torch.tensor([[16, 1, 1]]))  # fmt: skip
+    for bad in ({"method": "PM7"}, {"UHF": True}, {"excited_states": {"n_states": 2}}, {"scf_backward": 1},
                 {"scf_converger": [3, 0.1]}, {"dispersion": True}):  # fmt: skip
         sp = {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2]}
         sp.update(bad)
