@@ -125,3 +125,69 @@ def check_pm6_sp_elements(lib, device):
     with pytest.raises(NotImplementedError, match="d-shell"):
         run_molecule(lib, device, np.array([[16, 1, 1]]), np.array([[[0.0, 0, 0], [0.96, 0.9, 0], [-0.96, 0.9, 0]]]),
                      {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2]})
+
+
+def check_level_b_signatures(lib, device, method):
+    """The reference's operator signatures (SURVEY 8(b) level B) against the reference's operator outputs."""
+    from pyseqm_b200.seqm_functions import _plans
+    from pyseqm_b200.seqm_functions.anal_grad import scf_analytic_grad
+    from pyseqm_b200.seqm_functions.diag import sym_eig_trunc
+    from pyseqm_b200.seqm_functions.energy import elec_energy, heat_formation, pair_nuclear_energy, total_energy
+    from pyseqm_b200.seqm_functions.fock import fock
+    from pyseqm_b200.seqm_functions.hcore import hcore
+    from pyseqm_b200.seqm_functions.pack import pack, unpack
+    from pyseqm_b200.seqm_functions.scf_loop import scf_loop
+    from pyseqm_b200.seqm_functions.SP2 import SP2
+
+    _plans.use_library(lib)
+    try:
+        g = load_golden(f"cfg1_{method}_c2")
+        sp = dict(g["seqm_parameters"])
+        const = seqm.Constants().to(device)
+        mol = seqm.Molecule(const, sp, torch.as_tensor(g["coordinates"], device=device),
+                            torch.as_tensor(g["species"], device=device), _lib=lib)  # fmt: skip
+        nmol, ms = mol.nmol, mol.molsize
+        M, w, rho0xi, rho0xj, riXH, ri = hcore(mol)
+        assert np.abs(M.cpu().numpy() - g["op_M"]).max() < 1e-12 and np.abs(w.cpu().numpy() - g["op_w"]).max() < 1e-12
+        X = torch.as_tensor(g["op_X"], device=device)
+        p = mol.parameters
+        args = (nmol, ms, X, M, mol.maskd, mol.mask, mol.idxi, mol.idxj, w, None, p["g_ss"], p["g_pp"], p["g_sp"],
+                p["g_p2"], p["h_sp"], method, p["zeta_s"], p["zeta_p"], p["zeta_d"], mol.Z, p["F0SD"], p["G2SD"])  # fmt: skip
+        F = fock(*args)
+        assert np.abs(F.cpu().numpy() - g["op_F"]).max() < 1e-11
+        # the same call with untagged clones: the plan is rebuilt from (maskd, Z, one-centre parameters)
+        args2 = list(args)
+        args2[3], args2[8] = M.clone(), w.clone()
+        assert np.abs(fock(*args2).cpu().numpy() - g["op_F"]).max() < 1e-11
+        Fg = torch.as_tensor(g["op_F"], device=device)
+        e, P, v = sym_eig_trunc(Fg, mol.nHeavy, mol.nHydro, mol.nocc)
+        assert np.abs(P.cpu().numpy() - g["op_P"]).max() < 1e-10 and np.abs(e.cpu().numpy() - g["op_e"]).max() < 1e-10
+        e1, v1 = sym_eig_trunc(Fg[1], mol.nHeavy[1], mol.nHydro[1], mol.nocc[1], eig_only=True)
+        assert np.abs(e1.cpu().numpy() - g["op_e"][1]).max() < 1e-10
+        # pack / unpack round trip and SP2 on the packed matrices (largest molecule carries no padding)
+        Fp = pack(Fg, mol.nHeavy, mol.nHydro)
+        assert tuple(Fp.shape) == (nmol, int(mol.norb.max()), int(mol.norb.max()))
+        assert np.abs(unpack(Fp, mol.nHeavy, mol.nHydro, 4 * ms).cpu().numpy() - g["op_F"]).max() == 0.0
+        Psp2 = SP2(Fp, mol.nocc, 1.0e-5)
+        m = int(np.argmax(mol.norb.cpu().numpy()))
+        assert np.abs(Psp2[m].cpu().numpy() - g["op_sp2_packed"][m]).max() < 1e-9
+        # scf_loop 12-tuple + energies + gradient == the single-point fixture
+        out = scf_loop(mol, eps=sp["scf_eps"], sp2=sp.get("sp2", [False]), scf_converger=sp["scf_converger"], eig=True)
+        Fd, e, Pd, Mh, w2, charge, _, _, _, _, notconv, v = out
+        assert mol.n_scf_iter == g["n_scf_iter"] and not bool(notconv.any())
+        assert np.abs(Pd.cpu().numpy() - g["dm"]).max() < TOL_DM and np.abs(e.cpu().numpy() - g["e_mo"]).max() < TOL_E
+        Hd = Mh.view(nmol, ms, ms, 4, 4).transpose(2, 3).reshape(nmol, 4 * ms, 4 * ms)
+        Eelec = elec_energy(Pd, Fd, Hd, molecule=mol)
+        assert np.abs(Eelec.cpu().numpy() - g["Eelec"]).max() < TOL_E
+        assert np.abs(elec_energy(Pd, Fd, Hd).cpu().numpy() - g["Eelec"]).max() < TOL_E
+        Etot, Enuc = total_energy(nmol, mol.pair_molid, pair_nuclear_energy(mol, w2), Eelec)
+        assert np.abs(Etot.cpu().numpy() - g["Etot"]).max() < TOL_E
+        from pyseqm_b200.seqm_functions.energy import elec_energy_isolated_atom
+
+        Eiso = elec_energy_isolated_atom(const, mol.Z, p["U_ss"], p["U_pp"], p["g_ss"], p["g_pp"], p["g_sp"], p["g_p2"], p["h_sp"])
+        Hf, Eiso_sum = heat_formation(const, nmol, mol.atom_molid, mol.Z, Etot, Eiso, flag=True)
+        assert np.abs(Hf.cpu().numpy() - g["Hf"]).max() < TOL_E
+        grad = scf_analytic_grad(Pd, mol)
+        assert np.abs(-grad.cpu().numpy() - g["force"]).max() < TOL_F
+    finally:
+        _plans.use_library(None)

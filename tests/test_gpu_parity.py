@@ -33,6 +33,13 @@ def test_operator_level(lib, dev, method):
     check_operator_level(lib, dev, method)
 
 
+@pytest.mark.parametrize("method", ["AM1", "PM3", "MNDO", "PM6_SP"])
+def test_reference_operator_signatures(lib, dev, method):
+    from helpers import check_level_b_signatures
+
+    check_level_b_signatures(lib, dev, method)
+
+
 @pytest.mark.parametrize(
     "name",
     ["cfg1_AM1_c2", "cfg1_AM1_c1", "cfg1_AM1_c0", "cfg1_PM3_c2", "cfg1_PM3_c1", "cfg1_PM3_c0", "cfg1_MNDO_c2",
