@@ -161,6 +161,8 @@ typedef struct seqm_scf_opts {
   double sp2_eps;
   int32_t max_iter;  /* reference: 1000 */
   int32_t warm_start;/* 1: eigensolver starts from the previous iteration's eigenvectors */
+  int32_t pipeline;  /* Pulay DIIS only. 0: auto (two half-batches out of phase on two streams when nmol >= 256),
+                      * 1: single stream, 2: always two half-batches. Results do not depend on it. */
 } seqm_scf_opts_t;
 int64_t seqm_scf_workspace_bytes(const seqm_batch_t* b, const seqm_scf_opts_t* o);
 /* C_last: optional packed buffer receiving the eigenvectors of the last density solve (a warm start for the
@@ -173,7 +175,9 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
  * per kernel kind (seqm_profile_kinds() entries, names from seqm_profile_name()). */
 /* number of kernel launches issued by this library since load (bench.py gpu_launches) */
 long long seqm_launch_count(void);
-/* eigensolver statistics since the last reset: out[0] molecules solved, out[1] Jacobi sweeps, out[2] rotation steps */
+/* eigensolver statistics since the last reset, out[8]: [0] molecules solved, [1] Jacobi sweeps, [2] solves finished by
+ * the first-order occupied-virtual correction, [3] solves without any sweep, [4..7] SM cycles summed over CTAs:
+ * warm-start transform, sweeps, epilogue, total */
 int seqm_jacobi_stats(unsigned long long* out, int reset);
 /* measured FP64 FMA peak (TFLOP/s) of the current device: roofline denominator of the FP64-bound kernels */
 double seqm_fp64_peak_tflops(void);

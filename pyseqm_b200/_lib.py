@@ -42,7 +42,8 @@ JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64)
 
 class SeqmScfOpts(C.Structure):
     _fields_ = [("eps", C.c_double), ("converger", C.c_int32), ("alpha", C.c_double), ("use_sp2", C.c_int32),
-                ("sp2_eps", C.c_double), ("max_iter", C.c_int32), ("warm_start", C.c_int32)]  # fmt: skip
+                ("sp2_eps", C.c_double), ("max_iter", C.c_int32), ("warm_start", C.c_int32),
+                ("pipeline", C.c_int32)]  # fmt: skip
 
 
 class SeqmError(RuntimeError):
@@ -117,9 +118,10 @@ class SeqmLib:
             raise SeqmError("libseqm_b200 ABI version mismatch")
 
     def jacobi_stats(self, reset=True):
-        out = (C.c_ulonglong * 4)()
+        out = (C.c_ulonglong * 8)()
         self.check(self.dll.seqm_jacobi_stats(out, 1 if reset else 0), "seqm_jacobi_stats")
-        return {"molecules": out[0], "sweeps": out[1], "rotation_steps": out[2]}
+        return {"molecules": out[0], "sweeps": out[1], "first_order_finishes": out[2], "no_sweep": out[3],
+                "cycles_transform": out[4], "cycles_sweeps": out[5], "cycles_epilogue": out[6], "cycles_total": out[7]}
 
     def profile_enable(self, on=True):
         self.dll.seqm_profile_enable(1 if on else 0)

@@ -11,11 +11,15 @@
 #include "common.cuh"
 
 #define SEQM_JACOBI_MAX_SWEEPS 60
-// debug/statistics counters: [0] molecules solved, [1] sweeps, [2] steps with at least one rotation
+// statistics counters: [0] molecules solved, [1] sweeps, [2] solves finished by the first-order correction,
+// [3] solves that needed no sweep at all, [4..7] SM clock cycles (thread 0 of every CTA) spent in: warm-start
+// transform, sweeps + convergence checks, epilogue (eigenvector store, correction, density), total
 #ifndef SEQM_HOSTEMU
-__device__ unsigned long long g_jacobi_stats[4];
+__device__ unsigned long long g_jacobi_stats[8];
+#define SEQM_CLOCK() clock64()
 #else
-static unsigned long long g_jacobi_stats[4];
+static unsigned long long g_jacobi_stats[8];
+#define SEQM_CLOCK() 0LL
 #endif
 SEQM_D void stat_add(int k, unsigned long long v) {
 #ifndef SEQM_HOSTEMU
@@ -43,7 +47,15 @@ struct alignas(16) seqm_d2 { double x, y; };
 //     to the sign of slot 0, which is irrelevant for an eigenbasis).
 // Slots n..m-1 are decoupled dummies whose diagonal lies above the Gershgorin bound; they rank last.
 // blockDim.x must be SR*m (V ownership); tiles are strided over all threads.
-// shared: A[m*LD] | cs[NP] (double2) | scr[40] | dg[m] | perm[m] (int)
+// shared: A[m*LD] | cs[NP] (double2) | scr[40] | dg[m] | perm[m] (int) | occm[m] (int)
+//
+// Inside the SCF only the density is consumed, and it depends on the occupied SUBSPACE alone.  Before every sweep
+// the occupied-virtual block of the current A is inspected (slots ranked by their diagonal); once its largest
+// element is below 1e-7 |A| and 1e-6 of the HOMO-LUMO gap the sweeps stop and the occupied vectors get the
+// first-order correction  c_i += sum_a c_a A_ai / (d_i - d_a)  (second-order error < 1e-10 in P; rotations inside
+// the occupied or the virtual space never mattered).  This replaces the last, all-tiny-rotations sweep, and in late
+// SCF iterations -- where the warm-started A is already that close -- every sweep.  The eigenvectors handed to the
+// next warm start stay the uncorrected, exactly orthogonal product of rotations.
 // ---------------------------------------------------------------------------------------------------
 template <int NP>
 struct JacobiCfg {
@@ -53,7 +65,7 @@ struct JacobiCfg {
                                                  // so the CTA itself must bring enough warps to hide latency)
   static constexpr int SEG = M / SR;             // V entries per thread
   static constexpr int THREADS = SR * M;
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)M * LD + 2 * NP + 40 + M) + sizeof(int) * (M + 4);
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)M * LD + 2 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
 };
 
 // element (r, c) of the plane-split matrix
@@ -103,9 +115,11 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(
   double* scr = reinterpret_cast<double*>(cs + NP);
   double* dg = scr + 40;
   int* perm = reinterpret_cast<int*>(dg + M);
+  int* occm = perm + M;
   const double* Fm = F + v.mat0;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const bool warm = (Cguess != nullptr);
+  const long long clk0 = SEQM_CLOCK();
 #ifndef SEQM_HOSTEMU
   double vr[SEG];  // V[row][seg*SEG .. seg*SEG+SEG-1]
   const int vrow = tid / SR, vseg = tid % SR;
@@ -197,6 +211,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(
 #endif
   }
   SEQM_SYNC();
+  const long long clk1 = SEQM_CLOCK();
   double dmax = 0.0;
   for (int t = tid; t < M * LD; t += nthr) {
     const int c = t % LD;
@@ -237,7 +252,34 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(
   if (tid == 0) { s_flag[0][0] = s_flag[0][1] = s_flag[1][0] = s_flag[1][1] = 0; }
   SEQM_SYNC();
   int nsweep = 0;
+  const bool scf_mode = (Pout != nullptr) && (evals == nullptr) && v.nocc > 0 && v.nocc < n;
+  const double tol_pert = 1.0e-7 * fmax(dmax, 1.0e-300);
+  bool pert = false;
   for (int sweep = 0; sweep < SEQM_JACOBI_MAX_SWEEPS; ++sweep) {
+    if (scf_mode && (warm || sweep > 0)) {
+      // occupied / virtual slots by rank of the current diagonal, then the largest coupling between them
+      for (int i = tid; i < M; i += nthr) dg[i] = A[SEQM_AIDX(i, i)];
+      SEQM_SYNC();
+      for (int i = tid; i < M; i += nthr) {
+        const double ei = dg[i];
+        int r = 0;
+        for (int j = 0; j < M; ++j) r += (dg[j] < ei) || (dg[j] == ei && j < i);
+        perm[r] = i;
+        occm[i] = (r < v.nocc) ? 1 : 0;
+      }
+      SEQM_SYNC();
+      double ov = 0.0;
+      for (int t = tid; t < M * M; t += nthr) {
+        const int r = t / M, c = t - r * M;
+        if (c > r && occm[r] != occm[c]) ov = fmax(ov, fabs(A[SEQM_AIDX(r, c)]));
+      }
+      ov = block_max(ov, scr);
+      const double gap = dg[perm[v.nocc]] - dg[perm[v.nocc - 1]];
+      if (ov <= tol_pert && ov <= 1.0e-6 * gap) {
+        pert = true;
+        break;
+      }
+    }
     ++nsweep;
     int* flag = s_flag[sweep & 1];
     for (int step = 0; step < M; ++step) {
@@ -343,20 +385,16 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(
     // coupling below 1e-9 eV, i.e. a density error below 1e-10, so no check sweep is needed
     if (!flag[0] || !flag[1]) break;
   }
+  const long long clk2 = SEQM_CLOCK();
   if (tid == 0) {
     stat_add(0, 1);
     stat_add(1, nsweep);
+    if (pert) stat_add(2, 1);
+    if (nsweep == 0) stat_add(3, 1);
   }
-  // eigenvalues -> dg, then reuse the A storage for V in standard layout (row stride M)
+  // eigenvalues -> dg and their ranking, then reuse the A storage for V in standard layout (row stride M)
   for (int i = tid; i < M; i += nthr) dg[i] = A[SEQM_AIDX(i, i)];
   SEQM_SYNC();
-  double* V = A;
-#ifndef SEQM_HOSTEMU
-#pragma unroll
-  for (int e = 0; e < SEG; ++e) V[vrow * M + vseg * SEG + e] = vr[e];
-#else
-  for (int t = 0; t < M * M; ++t) V[t] = Vh[t];
-#endif
   for (int i = tid; i < M; i += nthr) {
     const double ei = dg[i];
     int r = 0;
@@ -364,11 +402,40 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(
     perm[r] = i;
   }
   SEQM_SYNC();
+  const int nv = n - v.nocc;
+  double* Xg = Pout ? Pout + v.mat0 : nullptr;  // first-order mixing coefficients, [virtual q][occupied r]
+  if (pert) {
+    for (int t = tid; t < nv * v.nocc; t += nthr) {
+      const int q = t / v.nocc, r = t - q * v.nocc;
+      const int a = perm[v.nocc + q], i = perm[r];
+      const double e = (a < i) ? A[SEQM_AIDX(a, i)] : A[SEQM_AIDX(i, a)];
+      Xg[t] = e / (dg[i] - dg[a]);
+    }
+    SEQM_SYNC();
+  }
+  double* V = A;
+#ifndef SEQM_HOSTEMU
+#pragma unroll
+  for (int e = 0; e < SEG; ++e) V[vrow * M + vseg * SEG + e] = vr[e];
+#else
+  for (int t = 0; t < M * M; ++t) V[t] = Vh[t];
+#endif
+  SEQM_SYNC();
   if (evals)
     for (int r = tid; r < b.nmax; r += nthr) evals[(long long)mol * b.nmax + r] = (r < n) ? dg[perm[r]] : 0.0;
   if (Cout) {
     double* Cm = Cout + v.mat0;
     for (int t = tid; t < n * n; t += nthr) Cm[t] = V[(t / n) * M + perm[t % n]];
+  }
+  if (pert) {
+    SEQM_SYNC();  // Cout took the uncorrected vectors
+    for (int t = tid; t < n * v.nocc; t += nthr) {
+      const int row = t / v.nocc, r = t - row * v.nocc;
+      double sacc = 0.0;
+      for (int q = 0; q < nv; ++q) sacc += V[row * M + perm[v.nocc + q]] * Xg[q * v.nocc + r];
+      V[row * M + perm[r]] += sacc;
+    }
+    SEQM_SYNC();
   }
   if (Pout) {
     double* Pm = Pout + v.mat0;
@@ -398,6 +465,13 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(
         if (j1 != j) { Pm[i1 * n + j1] = a11; Pm[j1 * n + i1] = a11; }
       }
     }
+  }
+  if (tid == 0) {
+    const long long clk3 = SEQM_CLOCK();
+    stat_add(4, (unsigned long long)(clk1 - clk0));
+    stat_add(5, (unsigned long long)(clk2 - clk1));
+    stat_add(6, (unsigned long long)(clk3 - clk2));
+    stat_add(7, (unsigned long long)(clk3 - clk0));
   }
 }
 

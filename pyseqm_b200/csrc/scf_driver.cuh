@@ -10,10 +10,12 @@
 #define SEQM_NFOCK 10
 #define SEQM_EM (SEQM_NFOCK + 1)
 
-struct ScfCtrl {  // device-resident control block
+struct ScfCtrl {  // device-resident control block (one per half-batch on the pipelined DIIS path)
   int nnot;       // molecules still not converged after the last get_error
-  int reset;      // DIIS: some active molecule had cond > 1e7 this iteration
-  int pad[6];
+  int reset;      // DIIS: some active molecule had cond > 1e7 this iteration (synchronous path)
+  int counter;    // DIIS ring slot of the current iteration (pipelined path: advanced by diis_begin_kernel)
+  int cF;         // DIIS history depth of the current iteration
+  int pad[4];
 };
 
 struct ScfWork {  // carved out of the caller's workspace
@@ -23,6 +25,8 @@ struct ScfWork {  // carved out of the caller's workspace
   double *err, *dm_err, *dm_elem, *Eel_new, *Eel_run;
   int32_t* active;
   ScfCtrl* ctrl;
+  int32_t* order2;  // pipelined path: processing order of half A followed by half B
+  int* rflag;       // pipelined path: DIIS reset flags [half][iteration parity]
   int has_C;
   // large-molecule path (n > SEQM_MAX_ORB): SP2 / commutator scratch for one molecule at a time
   double *Xl, *X2l, *rmax, *part;
@@ -63,7 +67,9 @@ static size_t scf_carve(const seqm_batch_t* b, const seqm_scf_opts_t* o, unsigne
   w.Eel_new = (double*)take(nm);
   w.Eel_run = (double*)take(nm);
   w.active = (int32_t*)take(sizeof(int32_t) * (size_t)b->nmol);
-  w.ctrl = (ScfCtrl*)take(sizeof(ScfCtrl));
+  w.ctrl = (ScfCtrl*)take(2 * sizeof(ScfCtrl));
+  w.order2 = (int32_t*)take(sizeof(int32_t) * (size_t)b->nmol);
+  w.rflag = (int*)take(4 * sizeof(int));
   if (b->nmax > SEQM_MAX_ORB) {
     const size_t big = sizeof(double) * (size_t)b->nmax * b->nmax;
     w.Xl = (double*)take(big);
@@ -92,9 +98,43 @@ SEQM_GLOBAL void scf_init_kernel(seqm_batch_t b, ScfWork W, int converger) {
     if (converger == 1)
       for (int k = 0; k < b.nmax; ++k) W.old2[(long long)m * b.nmax + k] = 0.0;
     if (m == 0) {
-      W.ctrl->nnot = b.nmol;
-      W.ctrl->reset = 0;
+      for (int h = 0; h < 2; ++h) {
+        W.ctrl[h].nnot = b.nmol;
+        W.ctrl[h].reset = 0;
+        W.ctrl[h].counter = -1;
+        W.ctrl[h].cF = 0;
+      }
+      for (int i = 0; i < 4; ++i) W.rflag[i] = 0;
     }
+    // interleaved split of the descending-size processing order: both halves see the same size mix
+    const int nA = (b.nmol + 1) / 2;
+    W.order2[(m & 1) ? nA + (m >> 1) : (m >> 1)] = b.mol_order[m];
+  }
+}
+// Pipelined DIIS path, start of iteration k of one half-batch (b.mol_order / b.nmol describe the half, W.ctrl is
+// its control block): apply the batch-global reset decided in iteration k-1 (scf_loop.py:1117-1130: any active
+// molecule of EITHER half with cond > 1e7 empties everyone's history), advance the ring (scf_loop.py:993-996),
+// clear this iteration's reset flag and the not-converged counter.
+SEQM_GLOBAL void diis_begin_kernel(seqm_batch_t b, ScfWork W, int k, int half) {
+  const int prev = (k - 1) & 1;
+  const bool rst = (k > 0) && ((W.rflag[prev] | W.rflag[2 + prev]) != 0);
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rst)
+    for (int i = tid; i < b.nmol; i += gridDim.x * blockDim.x) {
+      double* E = W.EMAT + (long long)b.mol_order[i] * SEQM_EM * SEQM_EM;
+      for (int r = 0; r < SEQM_EM; ++r)
+        for (int c = 0; c < SEQM_EM; ++c) E[r * SEQM_EM + c] = (c < r) ? -1.0 : 0.0;
+    }
+  if (tid == 0) {
+    int cF = W.ctrl->cF, counter = W.ctrl->counter;
+    if (rst) {
+      counter = -1;
+      cF = 0;
+    }
+    W.ctrl->cF = (cF < SEQM_NFOCK) ? cF + 1 : SEQM_NFOCK;
+    W.ctrl->counter = (counter + 1) % SEQM_NFOCK;
+    W.ctrl->nnot = 0;
+    W.rflag[2 * half + (k & 1)] = 0;
   }
 }
 SEQM_GLOBAL void emat_reset_kernel(seqm_batch_t b, ScfWork W) {
@@ -112,6 +152,10 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
   __shared__ double red[33];
   const int mol = b.mol_order[blockIdx.x];
   if (!W.active[mol]) return;
+  if (counter < 0) {  // pipelined path: the ring state lives on the device
+    counter = W.ctrl->counter;
+    cF = W.ctrl->cF;
+  }
   const MolView v = mol_view(b, mol);
   const int n = v.n, nn = n * n;
   SEQM_DYN_SMEM(double, sm);
@@ -177,13 +221,20 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
 // DIIS step 2 (scf_loop.py:1009-1031): pseudo-inverse solve of the (cF+1)x(cF+1) Pulay system, one WARP per
 // molecule (lanes own rows/columns of the tiny matrix in shared memory; cyclic Jacobi, the lower triangle of
 // EMAT is authoritative exactly as torch.linalg.eigh(UPLO='L') reads it), condition-number reset flag.
-SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int cF) {
+SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int cF, int* reset_flag) {
   __shared__ double sA[SEQM_DIIS_WARPS][SEQM_EM * SEQM_EM];
   __shared__ double sQ[SEQM_DIIS_WARPS][SEQM_EM * SEQM_EM];
   const int L = (blockDim.x >= 32) ? 32 : 1;
   const int lane = threadIdx.x % L, wib = threadIdx.x / L, wpb = blockDim.x / L;
-  const int mol = blockIdx.x * wpb + wib;
-  if (mol >= b.nmol || !W.active[mol]) return;
+  const int slot = blockIdx.x * wpb + wib;
+  if (slot >= b.nmol) return;
+  const int mol = b.mol_order[slot];
+  if (!W.active[mol]) return;
+  if (counter < 0) {
+    counter = W.ctrl->counter;
+    cF = W.ctrl->cF;
+    if (cF < 2) return;  // scf_loop.py:1016
+  }
   const int n = cF + 1;
   double* A = sA[wib];
   double* Q = sQ[wib];
@@ -238,7 +289,7 @@ SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int c
     amax = fmax(amax, a);
     amin = fmin(amin, a);
   }
-  if (lane == 0 && amax / amin > 1.0e7) seqm_atomic_or(&W.ctrl->reset, 1);
+  if (lane == 0 && amax / amin > 1.0e7) seqm_atomic_or(reset_flag, 1);
   for (int k = lane; k < cF; k += L) {
     double s = 0.0;
     for (int i = 0; i < n; ++i) {
@@ -253,6 +304,10 @@ SEQM_GLOBAL void diis_solve_kernel(seqm_batch_t b, ScfWork W, int counter, int c
 SEQM_GLOBAL void diis_extrapolate_kernel(seqm_batch_t b, ScfWork W, double* __restrict__ F, int cF) {
   const int mol = b.mol_order[blockIdx.x];
   if (!W.active[mol]) return;
+  if (cF < 0) {
+    cF = W.ctrl->cF;
+    if (cF < 2) return;
+  }
   const MolView v = mol_view(b, mol);
   const int nn = v.n * v.n;
   const long long h0 = v.mat0 * SEQM_NFOCK;
@@ -269,6 +324,7 @@ SEQM_GLOBAL void diis_extrapolate_kernel(seqm_batch_t b, ScfWork W, double* __re
 SEQM_GLOBAL void mix_linear_kernel(seqm_batch_t b, ScfWork W, double* __restrict__ P, double a) {
   const int mol = b.mol_order[blockIdx.x];
   if (!W.active[mol]) return;
+  if (a < 0.0) a = (W.ctrl->cF < 2) ? 0.5 : 0.0;  // pipelined DIIS: alpha_direct until two Fock matrices are stored
   const MolView v = mol_view(b, mol);
   const int nn = v.n * v.n;
   const double oma = 1.0 - a;
@@ -483,6 +539,8 @@ SEQM_GLOBAL void energy_finalize_kernel(seqm_batch_t b, ScfWork W, int mol, cons
   finalize_error(b, W, mol, 0.5 * e, d2, dmax, notconv, eps, use_diis);
 }
 SEQM_GLOBAL void commit_active_kernel(seqm_batch_t b, ScfWork W, const int32_t* __restrict__ notconv) {
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < b.nmol; m += gridDim.x * blockDim.x)
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b.nmol; i += gridDim.x * blockDim.x) {
+    const int m = b.mol_order[i];
     W.active[m] = notconv[m];
+  }
 }

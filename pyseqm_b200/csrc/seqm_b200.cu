@@ -213,25 +213,28 @@ static int diis_grid(int nmol) {
 // One molecule is a long dependent chain (sweeps x steps x barrier latency), so the classes are forked onto
 // their own streams and run concurrently; the caller's stream joins them afterwards.
 #ifndef SEQM_HOSTEMU
-static cudaStream_t g_cls_stream[16];
-static cudaEvent_t g_cls_fork, g_cls_join[16];
+// two independent sets ("lanes"): the pipelined SCF runs the eigensolver of its two half-batches concurrently
+static cudaStream_t g_cls_stream[2][16];
+static cudaEvent_t g_cls_fork[2], g_cls_join[2][16];
 static int g_cls_streams_ready = 0;
 static int ensure_class_streams() {
   if (g_cls_streams_ready) return SEQM_OK;
-  for (int c = 0; c < g_jacobi_ncls; ++c) {
-    if (cudaStreamCreateWithFlags(&g_cls_stream[c], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&g_cls_join[c], cudaEventDisableTiming) != cudaSuccess) {
-      seqm_set_error("could not create eigensolver class streams");
-      return SEQM_ERR_CUDA;
+  for (int l = 0; l < 2; ++l) {
+    for (int c = 0; c < g_jacobi_ncls; ++c) {
+      if (cudaStreamCreateWithFlags(&g_cls_stream[l][c], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&g_cls_join[l][c], cudaEventDisableTiming) != cudaSuccess) {
+        seqm_set_error("could not create eigensolver class streams");
+        return SEQM_ERR_CUDA;
+      }
     }
+    if (cudaEventCreateWithFlags(&g_cls_fork[l], cudaEventDisableTiming) != cudaSuccess) return SEQM_ERR_CUDA;
   }
-  if (cudaEventCreateWithFlags(&g_cls_fork, cudaEventDisableTiming) != cudaSuccess) return SEQM_ERR_CUDA;
   g_cls_streams_ready = 1;
   return SEQM_OK;
 }
 #endif
 static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const double* Cguess,
-                         const int32_t* active, cudaStream_t st) {
+                         const int32_t* active, cudaStream_t st, int lane = 0) {
   const double* cg = (Cguess && P && C) ? Cguess : nullptr;
   int npop = 0;
   for (int c = 0; c < g_jacobi_ncls; ++c) npop += (b->cls_count[c] > 0);
@@ -240,10 +243,11 @@ static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, doub
   if (fork) {
     int rc = ensure_class_streams();
     if (rc) return rc;
-    cudaEventRecord(g_cls_fork, st);
+    cudaEventRecord(g_cls_fork[lane], st);
   }
 #else
   const bool fork = false;
+  (void)lane;
 #endif
   for (int c = g_jacobi_ncls - 1; c >= 0; --c) {
     const int cnt = b->cls_count[c], first = b->cls_begin[c];
@@ -251,8 +255,8 @@ static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, doub
     cudaStream_t cst = st;
 #ifndef SEQM_HOSTEMU
     if (fork) {
-      cst = g_cls_stream[c];
-      cudaStreamWaitEvent(cst, g_cls_fork, 0);
+      cst = g_cls_stream[lane][c];
+      cudaStreamWaitEvent(cst, g_cls_fork[lane], 0);
     }
 #endif
     switch (g_jacobi_np[c]) {
@@ -268,8 +272,8 @@ static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, doub
     if (rc) return rc;
 #ifndef SEQM_HOSTEMU
     if (fork) {
-      cudaEventRecord(g_cls_join[c], cst);
-      cudaStreamWaitEvent(st, g_cls_join[c], 0);
+      cudaEventRecord(g_cls_join[lane][c], cst);
+      cudaStreamWaitEvent(st, g_cls_join[lane][c], 0);
     }
 #endif
   }
@@ -353,14 +357,14 @@ long long seqm_launch_count(void) { return g_seqm_launches; }
 int seqm_jacobi_stats(unsigned long long* out, int reset) {
 #ifndef SEQM_HOSTEMU
   cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out, g_jacobi_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) return SEQM_ERR_CUDA;
+  if (cudaMemcpyFromSymbol(out, g_jacobi_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) return SEQM_ERR_CUDA;
   if (reset) {
-    unsigned long long z[4] = {0, 0, 0, 0};
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaMemcpyToSymbol(g_jacobi_stats, z, sizeof(z));
   }
 #else
-  for (int i = 0; i < 4; ++i) out[i] = g_jacobi_stats[i];
-  if (reset) for (int i = 0; i < 4; ++i) g_jacobi_stats[i] = 0;
+  for (int i = 0; i < 8; ++i) out[i] = g_jacobi_stats[i];
+  if (reset) for (int i = 0; i < 8; ++i) g_jacobi_stats[i] = 0;
 #endif
   return SEQM_OK;
 }
@@ -621,6 +625,183 @@ static int zero_nnot(const ScfWork& W, void* stream) {
   return SEQM_OK;
 }
 
+// ---- Pulay DIIS, pipelined (converger 2, shared-memory-resident molecules) ---------------------------------------
+// The batch is split into two half-batches with the same size mix.  Each half runs the iteration
+//   begin -> store -> solve -> extrapolate -> eigensolver -> mix -> Fock -> get_error
+// on its own high-priority stream, half an iteration out of phase with the other, so the HBM-bound kernels of one
+// half run under the FP64-bound eigensolver of the other.  Everything that decides iteration counts stays
+// batch-global exactly as in the reference: the DIIS ring state lives on the device (diis_begin_kernel), a reset
+// raised by either half in iteration k empties both histories before iteration k+1, and the loop ends when no
+// molecule of either half is left.  The host never waits for the iteration it has just enqueued: it reads the
+// not-converged counters of iteration k-1 while iteration k runs (one trailing iteration is therefore enqueued
+// with every molecule inactive; its kernels exit immediately).
+#ifndef SEQM_HOSTEMU
+static cudaStream_t g_half_stream[2];
+static cudaEvent_t g_ev_fork, g_ev_join[2], g_ev_solve[2][2], g_ev_enter[2], g_ev_done[2][2];
+static int* g_h_nnot = nullptr;  // pinned: [half][iteration parity]
+static int g_pipe_ready = 0;
+static int ensure_pipeline() {
+  if (g_pipe_ready) return SEQM_OK;
+  int least = 0, greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&least, &greatest);
+  if (getenv("SEQM_PIPE_NOPRIO")) greatest = least;
+  bool ok = cudaHostAlloc((void**)&g_h_nnot, 4 * sizeof(int), cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int h = 0; h < 2 && ok; ++h) {
+    ok = ok && cudaStreamCreateWithPriority(&g_half_stream[h], cudaStreamNonBlocking, greatest) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&g_ev_join[h], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&g_ev_enter[h], cudaEventDisableTiming) == cudaSuccess;
+    for (int q = 0; q < 2 && ok; ++q) {
+      ok = ok && cudaEventCreateWithFlags(&g_ev_solve[h][q], cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&g_ev_done[h][q], cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  if (!ok) {
+    seqm_set_error("could not create the SCF pipeline streams/events");
+    return SEQM_ERR_CUDA;
+  }
+  g_pipe_ready = 1;
+  return SEQM_OK;
+}
+#else
+static int g_h_nnot_emu[4];
+static int* g_h_nnot = g_h_nnot_emu;
+#endif
+
+static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, const ScfWork& W0, const double* H,
+                              const double* w, double* P, double* F, int32_t* notconverged, cudaStream_t st,
+                              int* n_iter) {
+  int rc = SEQM_OK;
+  const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
+  int nh = (o->pipeline == 1) ? 1 : ((o->pipeline == 2 || b->nmol >= 256) ? 2 : 1);
+  if (b->nmol < 2) nh = 1;
+#ifdef SEQM_HOSTEMU
+  cudaStream_t hs[2] = {st, st};
+#else
+  cudaStream_t hs[2] = {st, st};
+  rc = ensure_pipeline();
+  if (rc) return rc;
+  if (nh == 2) {
+    rc = ensure_class_streams();
+    if (rc) return rc;
+    hs[0] = g_half_stream[0];
+    hs[1] = g_half_stream[1];
+    cudaEventRecord(g_ev_fork, st);
+    cudaStreamWaitEvent(hs[0], g_ev_fork, 0);
+    cudaStreamWaitEvent(hs[1], g_ev_fork, 0);
+  }
+#endif
+  // half-batch views: same arrays, own processing order / size-class ranges / control block
+  seqm_batch_t bh[2] = {*b, *b};
+  ScfWork Wh[2] = {W0, W0};
+  if (nh == 2) {
+    const int nA = (b->nmol + 1) / 2;
+    bh[0].nmol = nA;
+    bh[0].mol_order = W0.order2;
+    bh[1].nmol = b->nmol - nA;
+    bh[1].mol_order = W0.order2 + nA;
+    Wh[1].ctrl = W0.ctrl + 1;
+    for (int c = 0; c < 12; ++c) {
+      const int b0 = b->cls_begin[c], e0 = b0 + b->cls_count[c];
+      const int pe = b0 + (b0 & 1), po = b0 + ((b0 & 1) ? 0 : 1);  // first even / odd position of the class
+      bh[0].cls_begin[c] = pe / 2;
+      bh[0].cls_count[c] = (pe < e0) ? (e0 - pe + 1) / 2 : 0;
+      bh[1].cls_begin[c] = (po - 1) / 2;
+      bh[1].cls_count[c] = (po < e0) ? (e0 - po + 1) / 2 : 0;
+    }
+  }
+#define CHKP(name)              \
+  rc = seqm_check_launch(name); \
+  if (rc) return rc
+  int k = 0, done_at = -1;
+  for (; k <= max_iter; ++k) {
+    for (int h = 0; h < nh; ++h) {
+      cudaStream_t s = hs[h];
+      const seqm_batch_t& B = bh[h];
+      const ScfWork& W = Wh[h];
+      const int nt = threads_for(b->nmax);
+      const size_t sm1 = sizeof(double) * (size_t)b->nmax * b->nmax;
+      const int gm = grid1d(B.nmol, 128);
+#ifndef SEQM_HOSTEMU
+      if (nh == 2) {
+        static const int nostagger = getenv("SEQM_PIPE_NOSTAGGER") ? atoi(getenv("SEQM_PIPE_NOSTAGGER")) : 0;
+        if (nostagger == 0 ? (k > 0 || h == 1) : (nostagger == 1 ? (k == 0 && h == 1) : false))
+          cudaStreamWaitEvent(s, g_ev_enter[1 - h], 0);  // half an iteration out of phase
+        if (k > 0) cudaStreamWaitEvent(s, g_ev_solve[1 - h][(k - 1) & 1], 0);  // the other half's reset flag of k-1
+      }
+#endif
+      SEQM_LAUNCH(diis_begin_kernel, gm, 128, 0, s, B, W, k, h);
+      CHKP("diis_begin_kernel");
+      PROF(PK_DIIS_STORE, s, SEQM_LAUNCH(diis_store_kernel, B.nmol, nt, 2 * sm1, s, B, W, (const double*)F, (const double*)P, -1, -1));
+      CHKP("diis_store_kernel");
+      PROF(PK_DIIS_SOLVE, s, SEQM_LAUNCH(diis_solve_kernel, diis_grid(B.nmol), 32 * SEQM_DIIS_WARPS, 0, s, B, W, -1, -1,
+                                         W0.rflag + 2 * h + (k & 1)));
+      CHKP("diis_solve_kernel");
+#ifndef SEQM_HOSTEMU
+      if (nh == 2) cudaEventRecord(g_ev_solve[h][k & 1], s);
+#endif
+      PROF(PK_DIIS_EXTRAP, s, SEQM_LAUNCH(diis_extrapolate_kernel, B.nmol, 256, 0, s, B, W, F, -1));
+      CHKP("diis_extrapolate_kernel");
+#ifndef SEQM_HOSTEMU
+      if (nh == 2) cudaEventRecord(g_ev_enter[h], s);
+#endif
+      if (o->use_sp2) {
+        const size_t smsp2 = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
+        PROF(PK_SP2, s, SEQM_LAUNCH(sp2_kernel, B.nmol, nt, smsp2, s, B, (const double*)F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, (const int32_t*)W.active));
+        CHKP("sp2_kernel");
+      } else {
+        PROF(PK_JACOBI, s, rc = launch_jacobi(&B, F, W.Pnew, (double*)nullptr, W.C,
+                                              (o->warm_start && k > 0) ? (const double*)W.C : (const double*)nullptr, W.active, s, h));
+        if (rc) return rc;
+      }
+      PROF(PK_MIX, s, SEQM_LAUNCH(mix_linear_kernel, B.nmol, 256, 0, s, B, W, P, -1.0));
+      CHKP("mix_linear_kernel");
+      rc = launch_fock(&B, P, H, w, F, (const int32_t*)W.active, s);
+      if (rc) return rc;
+      PROF(PK_ENERGY_ERR, s, SEQM_LAUNCH(energy_error_kernel, B.nmol, 128, 0, s, B, W, (const double*)P, H, (const double*)F, notconverged, o->eps, 1));
+      CHKP("energy_error_kernel");
+      SEQM_LAUNCH(commit_active_kernel, gm, 128, 0, s, B, W, (const int32_t*)notconverged);
+      CHKP("commit_active_kernel");
+#ifndef SEQM_HOSTEMU
+      cudaMemcpyAsync(g_h_nnot + 2 * h + (k & 1), &W.ctrl->nnot, sizeof(int), cudaMemcpyDeviceToHost, s);
+      cudaEventRecord(g_ev_done[h][k & 1], s);
+#else
+      g_h_nnot[2 * h + (k & 1)] = W.ctrl->nnot;
+#endif
+    }
+    // look one iteration behind: the GPU is busy with iteration k while the host learns about k-1
+    const int kk = k - 1;
+    if (kk >= 0) {
+      int nnot = 0;
+      for (int h = 0; h < nh; ++h) {
+#ifndef SEQM_HOSTEMU
+        cudaError_t e = cudaEventSynchronize(g_ev_done[h][kk & 1]);
+        if (e != cudaSuccess) {
+          seqm_set_error("SCF pipeline: %s", cudaGetErrorString(e));
+          return SEQM_ERR_CUDA;
+        }
+#endif
+        nnot += g_h_nnot[2 * h + (kk & 1)];
+      }
+      if (nnot == 0) {
+        done_at = kk + 1;
+        break;
+      }
+    }
+  }
+#undef CHKP
+#ifndef SEQM_HOSTEMU
+  if (nh == 2) {
+    for (int h = 0; h < 2; ++h) {
+      cudaEventRecord(g_ev_join[h], hs[h]);
+      cudaStreamWaitEvent(st, g_ev_join[h], 0);
+    }
+  }
+#endif
+  *n_iter = (done_at >= 0) ? done_at : max_iter + 1;
+  return SEQM_OK;
+}
+
 int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
              double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, double* C_last, void* stream) {
   int rc = check_batch(b);
@@ -667,12 +848,18 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   int counter = -1, cF = 0;
   int nnot = b->nmol;
   int printed = 0;
+  const bool pipelined = (o->converger == 2) && !large;
+  if (pipelined) {
+    rc = scf_diis_pipelined(b, o, W, H, w, P, F, notconverged, st, &printed);
+    if (rc) return rc;
+    have_C = o->use_sp2 ? 0 : 1;
+  }
   // iteration index conventions of the reference: converger 0 counts from 0, converger 1 from 1,
   // converger 2 reports the number of completed iterations.
   const int k_first = (o->converger == 1) ? 1 : 0;
   const int k_last = max_iter;
   int k = k_first;
-  for (; k <= k_last; ++k) {
+  for (; !pipelined && k <= k_last; ++k) {
     if (o->converger == 2) {
       if (nnot == 0) break;
       cF = (cF < SEQM_NFOCK) ? cF + 1 : SEQM_NFOCK;
@@ -708,7 +895,7 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
         }
       }
       if (cF >= 2) {
-        PROF(PK_DIIS_SOLVE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_solve_kernel, diis_grid(b->nmol), 32 * SEQM_DIIS_WARPS, 0, st, *b, W, counter, cF));
+        PROF(PK_DIIS_SOLVE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_solve_kernel, diis_grid(b->nmol), 32 * SEQM_DIIS_WARPS, 0, st, *b, W, counter, cF, &W.ctrl->reset));
         CHK("diis_solve_kernel");
         if (!large) {
           PROF(PK_DIIS_EXTRAP, SEQM_STREAM(stream), SEQM_LAUNCH(diis_extrapolate_kernel, b->nmol, 256, 0, st, *b, W, F, cF));
@@ -804,7 +991,7 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
     }
     printed = k;
   }
-  if (o->converger == 2) printed = (k > k_last) ? k_last + 1 : k;
+  if (o->converger == 2 && !pipelined) printed = (k > k_last) ? k_last + 1 : k;
   if (n_iter_out) *n_iter_out = printed;
   delete[] hm;
   delete[] h_active;

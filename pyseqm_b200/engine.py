@@ -295,6 +295,7 @@ def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_star
     o.sp2_eps = float(sp2[1]) if sp2[0] else 0.0
     o.max_iter = int(max_iter)
     o.warm_start = 1 if warm_start else 0
+    o.pipeline = int(os.environ.get("SEQM_B200_PIPELINE", "0"))  # 0 auto, 1 single stream, 2 two half-batches
     nbytes = plan.lib.dll.seqm_scf_workspace_bytes(plan.ref, C.byref(o))
     if nbytes < 0:
         raise SeqmError("seqm_scf_workspace_bytes failed")
