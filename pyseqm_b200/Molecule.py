@@ -35,16 +35,7 @@ def narrow_orbitals(P9, molsize, stride=9):
     return P9.reshape(b, molsize, stride, molsize, stride)[:, :, :4, :, :4].reshape(b, 4 * molsize, 4 * molsize).contiguous()
 
 
-def check_input(species):
-    """Rows must be non-increasing in Z (Molecule.py:188-206, same message)."""
-    ok = species[:, :-1] >= species[:, 1:]
-    row_ok = ok.all(dim=1)
-    if not bool(row_ok.all()):
-        bad = (~row_ok).nonzero(as_tuple=False).squeeze(1).tolist()
-        rows = ", ".join(map(str, bad))
-        row_word = "row" if len(bad) == 1 else "rows"
-        verb = "is" if len(bad) == 1 else "are"
-        raise ValueError(f"species must be non-increasing along each row, but {row_word} {rows} {verb} not sorted.")
+check_input = engine.check_input  # rows must be non-increasing in Z (Molecule.py:188-206); run by the batch plan
 
 
 def reject_unsupported(seqm_parameters):
@@ -81,8 +72,9 @@ class Molecule(torch.nn.Module):
                  do_large_tensors=True, _lib=None, *args, **kwargs):  # fmt: skip
         super().__init__()
         self.const = const
-        check_input(species)
         reject_unsupported(seqm_parameters)
+        if not species.is_cuda:
+            check_input(species)  # on the GPU the batch plan folds this test into its single host read-back
         if coordinates.dtype != torch.float64:
             raise NotImplementedError("the B200 path is fp64 only: pass float64 coordinates")
         self.species = species
@@ -94,8 +86,6 @@ class Molecule(torch.nn.Module):
         if not torch.is_tensor(mult):
             mult = mult * torch.ones(coordinates.shape[0], device=coordinates.device)
         self.mult = mult
-        if seqm_parameters.get("elements") is None:
-            seqm_parameters["elements"] = sorted(set([0] + torch.unique(species).tolist()))
         self.seqm_parameters = seqm_parameters
         self.method = seqm_parameters["method"]
         if callable(learned_parameters):
@@ -115,23 +105,19 @@ class Molecule(torch.nn.Module):
         lib = _lib if _lib is not None else get_lib()
         plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned_parameters, charges=charges, table=table)
         self._plan = plan
+        if seqm_parameters.get("elements") is None:
+            seqm_parameters["elements"] = plan.elements
         dev = coordinates.device
         self.nmol, self.molsize = plan.nmol, plan.molsize
         self.nHeavy, self.nHydro, self.nocc = plan.nheavy, plan.nhyd, plan.nocc
         self.nSuperHeavy = torch.zeros_like(plan.nheavy)
         self.Z = plan.Z
         self.atom_molid = plan.atom_mol
-        ms = plan.molsize
-        pos = plan.atom_local
-        self.maskd = plan.atom_mol * ms * ms + pos * (ms + 1)
         self.idxi, self.idxj = plan.pair_i, plan.pair_j
-        self.ni, self.nj = plan.Z[plan.pair_i], plan.Z[plan.pair_j]
-        self.pair_molid = plan.atom_mol[plan.pair_i]
-        self.mask = self.pair_molid * ms * ms + pos[plan.pair_i] * ms + pos[plan.pair_j]
-        self.mask_l = self.pair_molid * ms * ms + pos[plan.pair_j] * ms + pos[plan.pair_i]
-        self._refresh_geometry()
+        # maskd / mask / mask_l / ni / nj / pair_molid / xij / rij are derived on first access (see __getattr__):
+        # the kernels never read them, they exist for the reference's attribute contract
         cutoff = seqm_parameters.get("pair_outer_cutoff", 1.0e10)
-        if bool((self.rij / const.length_conversion_factor >= cutoff).any()):
+        if cutoff < 1.0e9 and bool((self.rij / const.length_conversion_factor >= cutoff).any()):
             raise NotImplementedError("pair_outer_cutoff that removes pairs is not supported by the B200 path yet")
         # per-atom parameter dict (Molecule.py:86-115)
         names = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha"]
@@ -144,7 +130,7 @@ class Molecule(torch.nn.Module):
         for k in ("zeta_d", "s_orb_exp_tail", "p_orb_exp_tail", "d_orb_exp_tail", "U_dd", "F0SD", "G2SD", "rho_core"):
             self.parameters[k] = zeros
         self.parameters["Kbeta"] = None
-        zmax = int(species.max())
+        zmax = plan.zmax
         if plan.pw is not None:
             self.alp, self.chi = plan.pw[0], plan.pw[1]
         else:
@@ -177,14 +163,36 @@ class Molecule(torch.nn.Module):
         self.cis_amplitudes = None
         self.n_scf_iter: Optional[int] = None  # the count the reference only prints (scf_loop.py:975-992)
 
+    _LAZY = ("maskd", "mask", "mask_l", "ni", "nj", "pair_molid", "xij", "rij")
+
+    def __getattr__(self, name):
+        if name in Molecule._LAZY and "_plan" in self.__dict__:
+            plan = self.__dict__["_plan"]
+            ms, pos = plan.molsize, plan.atom_local
+            d = self.__dict__
+            if name in ("xij", "rij"):  # unit vector i->j and distance in bohr (basics.py:737-746)
+                xyz = plan.real_xyz(self.coordinates)
+                dv = xyz[plan.pair_j] - xyz[plan.pair_i]
+                dist = torch.linalg.norm(dv, dim=1)
+                d["xij"] = dv / dist.unsqueeze(1)
+                d["rij"] = dist * self.const.length_conversion_factor
+            elif name == "maskd":
+                d["maskd"] = plan.atom_mol * ms * ms + pos * (ms + 1)
+            elif name in ("ni", "nj"):
+                d["ni"], d["nj"] = plan.Z[plan.pair_i], plan.Z[plan.pair_j]
+            else:
+                pm = plan.atom_mol[plan.pair_i]
+                d["pair_molid"] = pm
+                d["mask"] = pm * ms * ms + pos[plan.pair_i] * ms + pos[plan.pair_j]
+                d["mask_l"] = pm * ms * ms + pos[plan.pair_j] * ms + pos[plan.pair_i]
+            return d[name]
+        return super().__getattr__(name)
+
     def _refresh_geometry(self):
-        """xij (unit vector i->j) and rij in bohr (basics.py:737-746)."""
-        xyz = self._plan.real_xyz(self.coordinates)
-        d = xyz[self.idxj] - xyz[self.idxi]
-        dist = torch.linalg.norm(d, dim=1)
-        self.xij = d / dist.unsqueeze(1)
-        self.rij = dist * self.const.length_conversion_factor
-        return xyz
+        """Packed coordinates of the real atoms; the cached pair geometry (xij, rij) is invalidated."""
+        self.__dict__.pop("xij", None)
+        self.__dict__.pop("rij", None)
+        return self._plan.real_xyz(self.coordinates)
 
     def get_coordinates(self):
         return self.coordinates

@@ -11,7 +11,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libseqm_b200.so")
+LIB_PATH = os.environ.get("SEQM_B200_LIB") or os.path.join(_HERE, "lib", "libseqm_b200.so")  # env: kernel experiments
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
               "-Xcompiler", "-fPIC"]  # fmt: skip

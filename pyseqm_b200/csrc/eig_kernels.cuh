@@ -57,14 +57,27 @@ struct alignas(16) seqm_d2 { double x, y; };
 // SCF iterations -- where the warm-started A is already that close -- every sweep.  The eigenvectors handed to the
 // next warm start stay the uncorrected, exactly orthogonal product of rotations.
 // ---------------------------------------------------------------------------------------------------
+#ifndef SEQM_SR8_FROM
+#define SEQM_SR8_FROM 40
+#endif
 template <int NP>
 struct JacobiCfg {
   static constexpr int M = 2 * NP;
   static constexpr int LD = M + ((NP / 2) % 8);
-  static constexpr int SR = (NP >= 40) ? 8 : 4;  // threads per row of V (more for the big classes: 1 CTA/SM there,
+  static constexpr int SR = (NP >= SEQM_SR8_FROM && NP % 8 == 0) ? 8 : 4;  // threads per row of V (more for the big classes: 1 CTA/SM there,
                                                  // so the CTA itself must bring enough warps to hide latency)
   static constexpr int SEG = M / SR;             // V entries per thread
   static constexpr int THREADS = SR * M;
+#ifndef SEQM_JB16  // measured on B200 (4096 QM9-size molecules): 6/5/5/4/4 CTAs per SM beat the unconstrained allocation
+#define SEQM_JB16 6
+#define SEQM_JB20 5
+#define SEQM_JB24 5
+#define SEQM_JB28 4
+#define SEQM_JB32 4
+#endif
+  // resident CTAs per SM the register allocation is asked to allow (occupancy of a barrier/latency-bound kernel)
+  static constexpr int MINBLOCKS = NP == 16 ? SEQM_JB16 : NP == 20 ? SEQM_JB20 : NP == 24 ? SEQM_JB24
+                                   : NP == 28 ? SEQM_JB28 : NP == 32 ? SEQM_JB32 : 0;
   static constexpr size_t SMEM = sizeof(double) * ((size_t)M * LD + 2 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
 };
 
@@ -100,7 +113,7 @@ SEQM_HD void jacobi_tile_offsets(int k, int l, int* oe, int* oo) {
 }
 
 template <int NP>
-SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(JacobiCfg<NP>::THREADS) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINBLOCKS) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
                                      double* __restrict__ evals, double* __restrict__ Cout,
                                      const double* __restrict__ Cguess, const int32_t* __restrict__ active) {
   typedef JacobiCfg<NP> K;

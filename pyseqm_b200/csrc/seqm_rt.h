@@ -18,6 +18,7 @@
 #define SEQM_D __device__ __forceinline__
 #define SEQM_GLOBAL __global__
 #define SEQM_LAUNCH_BOUNDS(n) __launch_bounds__(n)
+#define SEQM_LAUNCH_BOUNDS2(n, b) __launch_bounds__(n, b)
 #define SEQM_CONSTANT __constant__
 #define SEQM_DYN_SMEM(type, name)                                   \
   extern __shared__ __align__(16) unsigned char seqm_dyn_smem_[];   \
@@ -42,6 +43,7 @@ void seqm_hostemu_ensure_smem(size_t bytes);
 #define SEQM_D inline
 #define SEQM_GLOBAL static
 #define SEQM_LAUNCH_BOUNDS(n)
+#define SEQM_LAUNCH_BOUNDS2(n, b)
 #define SEQM_CONSTANT static
 #define __restrict__
 #define __shared__ static

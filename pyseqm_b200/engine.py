@@ -46,6 +46,43 @@ def method_table(method):
     return _TABLE_CACHE[key]
 
 
+def check_input(species):
+    """Rows must be non-increasing in Z (Molecule.py:188-206, same message)."""
+    ok = species[:, :-1] >= species[:, 1:]
+    row_ok = ok.all(dim=1)
+    if not bool(row_ok.all()):
+        bad = (~row_ok).nonzero(as_tuple=False).squeeze(1).tolist()
+        rows = ", ".join(map(str, bad))
+        row_word = "row" if len(bad) == 1 else "rows"
+        verb = "is" if len(bad) == 1 else "are"
+        raise ValueError(f"species must be non-increasing along each row, but {row_word} {rows} {verb} not sorted.")
+
+
+def _device_tables(method, dev):
+    """Per-element tables resident on `dev` (cached): rows 0..27 of `atom_par` as (28, zmax+1), tore, class bounds."""
+    key = ("dev", method, str(dev))
+    if key not in _TABLE_CACHE:
+        tab, cols, pw = method_table(method)
+        el = element_tables()
+        nz = max(tab.shape[0], len(el["tore"]))
+        rows = torch.zeros((28, nz), dtype=torch.float64)
+        for r, name in enumerate(PAR_ROWS[:24]):
+            if name in cols:
+                rows[r, : tab.shape[0]] = tab[:, cols.index(name)]
+        rows[24, : len(el["tore"])] = torch.tensor(el["tore"], dtype=torch.float64)
+        rows[25, : len(el["qn"])] = torch.tensor(el["qn"], dtype=torch.float64)
+        if "rho_core" in cols:
+            rows[26, : tab.shape[0]] = tab[:, cols.index("rho_core")]
+        rows[27, : len(el["atomic_num"])] = torch.tensor(el["atomic_num"], dtype=torch.float64)
+        T = {
+            "rows": rows.to(dev).contiguous(),
+            "tore": rows[24].to(dev).contiguous(),
+            "jacobi_bounds": torch.tensor([2 * q for q in JACOBI_NP], device=dev),
+        }
+        _TABLE_CACHE[key] = (T, cols, pw)
+    return _TABLE_CACHE[key]
+
+
 class BatchPlan:
     """Index tensors of one molecule batch (topology only; coordinates are passed per call)."""
 
@@ -57,47 +94,67 @@ class BatchPlan:
         self.lib = lib
         dev = species.device
         self.device = dev
-        el = element_tables()
         nmol, molsize = species.shape
         self.nmol, self.molsize, self.method = nmol, molsize, method
+        T, cols, pw = _device_tables(table or method, dev)
+        # ---- per-molecule counts, then ONE host read-back of every scalar the host needs -------------------
         real = species > 0
         self.real_mask = real
-        self.real_atoms = torch.nonzero(real.reshape(-1), as_tuple=False).squeeze(1)
-        Z = species.reshape(-1)[self.real_atoms]
-        self.Z = Z
         na = real.sum(dim=1)
-        nheavy = (species > 1).sum(dim=1)
         nhyd = (species == 1).sum(dim=1)
-        tore = torch.tensor(el["tore"], dtype=torch.float64, device=dev)
-        nel = tore[species].sum(dim=1).to(torch.int64)
+        nheavy = na - nhyd
+        nel = T["tore"][species].sum(dim=1).to(torch.int64)
         if torch.is_tensor(charges):
             nel = nel - charges.reshape(-1).to(torch.int64).to(dev)
         else:
             nel = nel - int(charges)
-        if bool(((nel % 2) == 1).any()):
-            raise ValueError("RHF setting requires closed shell systems (even number of electrons)")
         nocc = nel // 2
         norb = 4 * nheavy + nhyd
-        self.na, self.nheavy, self.nhyd, self.nocc, self.norb = na, nheavy, nhyd, nocc, norb
-        self.nat = int(Z.shape[0])
-        self.nmax = int(norb.max())
-        zero = torch.zeros(1, dtype=torch.int64, device=dev)
-        atom0 = torch.cat([zero, torch.cumsum(na, 0)])
         npair_m = na * (na - 1) // 2
-        pair0 = torch.cat([zero, torch.cumsum(npair_m, 0)])
         nn = norb * norb
         nn = nn + (nn % 2)
-        mat0 = torch.cat([zero, torch.cumsum(nn, 0)])
-        self.mat_total = int(mat0[-1])
-        self.npairs = int(pair0[-1])
-        atom_mol = torch.repeat_interleave(torch.arange(nmol, device=dev), na)
-        local = torch.arange(self.nat, device=dev) - atom0[atom_mol]
+        cum = torch.cumsum(torch.stack((na, npair_m, nn)), dim=1)  # (3, nmol)
+        nxx, nxh, nhh = nheavy * (nheavy - 1) // 2, nheavy * nhyd, nhyd * (nhyd - 1) // 2
+        cls = torch.bucketize(norb, T["jacobi_bounds"])  # == len(JACOBI_NP) for n > 2*NP_max (large path)
+        ncls = len(JACOBI_NP)
+        sorted_ok = (species[:, :-1] >= species[:, 1:]).all() if molsize > 1 else torch.ones((), dtype=torch.bool, device=dev)
+        scal = torch.cat([
+            cum[:, -1], norb.max().reshape(1), (nel % 2).max().reshape(1), species.max().reshape(1),
+            (20 * nxx + 11 * nxh + 2 * nhh).max().reshape(1), sorted_ok.to(torch.int64).reshape(1),
+            torch.stack((nhh.sum(), nxh.sum(), nxx.sum())), torch.bincount(cls, minlength=ncls + 1),
+            torch.bincount(species.reshape(-1), minlength=128)[:128],
+        ]).cpu().tolist()  # fmt: skip
+        self.nat, self.npairs, self.mat_total, self.nmax = scal[0], scal[1], scal[2], scal[3]
+        odd, zmax, fock_scratch, self.sorted_ok = scal[4], scal[5], scal[6], bool(scal[7])
+        self.zmax = zmax
+        pair_cls_cnt, cls_cnt = scal[8:11], scal[11 : 12 + ncls]
+        self.elements = [z for z in range(128) if scal[12 + ncls + z] > 0 or z == 0]
+        if not self.sorted_ok:
+            check_input(species)
+        if odd:
+            raise ValueError("RHF setting requires closed shell systems (even number of electrons)")
+        self.na, self.nheavy, self.nhyd, self.nocc, self.norb = na, nheavy, nhyd, nocc, norb
+        # ---- atom and pair lists (rows are sorted by descending Z: real atoms are the first na of a row) ----
+        zero = torch.zeros((3, 1), dtype=torch.int64, device=dev)
+        starts = torch.cat([zero, cum], dim=1)
+        atom0, pair0, mat0 = starts[0], starts[1], starts[2]
+        ar_mol = torch.arange(nmol, device=dev)
+        atom_mol = torch.repeat_interleave(ar_mol, na, output_size=self.nat)
+        ar_at = torch.arange(self.nat, device=dev)
+        local = ar_at - atom0[atom_mol]
+        self.real_atoms = atom_mol * molsize + local
+        Z = species.reshape(-1)[self.real_atoms]
+        self.Z = Z
         # dense triangular pair list ordered (molecule, i, j)
         cnt = na[atom_mol] - 1 - local
-        pair_i = torch.repeat_interleave(torch.arange(self.nat, device=dev), cnt)
+        pair_i = torch.repeat_interleave(ar_at, cnt, output_size=self.npairs)
         first_of_i = torch.cumsum(cnt, 0) - cnt
         pair_j = pair_i + 1 + (torch.arange(self.npairs, device=dev) - first_of_i[pair_i])
         order = torch.argsort(norb, descending=True, stable=True)
+        # pair classes: 0 H-H, 1 X-H, 2 X-X (Z_i >= Z_j for every pair)
+        heavy = Z > 1
+        pcls = heavy[pair_i].to(torch.int8) + heavy[pair_j].to(torch.int8)
+        self.pair_perm = torch.argsort(pcls, stable=True).to(torch.int32)
         i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
         self.t = dict(
             mol_atom0=i32(atom0), mol_pair0=i32(pair0), mol_mat0=mat0.contiguous(), mol_nheavy=i32(nheavy),
@@ -106,31 +163,26 @@ class BatchPlan:
         )  # fmt: skip
         self.atom_mol, self.atom_local = atom_mol, local
         self.pair_i, self.pair_j = pair_i, pair_j
-        # per-atom parameter table
-        tab, cols, pw = method_table(table or method)
-        tabd = tab.to(dev)
+        # ---- per-atom parameter table: one gather from the cached per-element device table ------------------
         par = torch.zeros((NPAR, self.nat), dtype=torch.float64, device=dev)
-        for r, name in enumerate(PAR_ROWS[:24]):
-            if parameters is not None and name in parameters and parameters[name] is not None:
-                par[r] = parameters[name].to(torch.float64)
-            elif name in cols:
-                par[r] = tabd[Z, cols.index(name)]
-        par[24] = tore[Z]
-        par[25] = torch.tensor(el["qn"], dtype=torch.float64, device=dev)[Z]
-        if "rho_core" in cols:
-            par[26] = tabd[Z, cols.index("rho_core")]
-        par[27] = torch.tensor(el["atomic_num"], dtype=torch.float64, device=dev)[Z]
+        par[:28] = T["rows"][:, Z]
+        if parameters:
+            for r, name in enumerate(PAR_ROWS[:24]):
+                if parameters.get(name) is not None:
+                    par[r] = parameters[name].to(torch.float64)
         self.pw = None
         if pw is not None:
-            zmax = int(species.max())
             dim = max(zmax + 1, 2)
-            a = torch.zeros((dim, dim), dtype=torch.float64)
-            c = torch.zeros_like(a)
-            k = min(dim, pw[0].shape[0])
-            a[:k, :k] = pw[0][:k, :k]
-            c[:k, :k] = pw[1][:k, :k]
-            self.pw = (a.to(dev).contiguous(), c.to(dev).contiguous(), dim)
-        self.par = par.contiguous()
+            key = ("pwdev", table or method, str(dev), dim)
+            if key not in _TABLE_CACHE:
+                a = torch.zeros((dim, dim), dtype=torch.float64)
+                c = torch.zeros_like(a)
+                k = min(dim, pw[0].shape[0])
+                a[:k, :k] = pw[0][:k, :k]
+                c[:k, :k] = pw[1][:k, :k]
+                _TABLE_CACHE[key] = (a.to(dev).contiguous(), c.to(dev).contiguous(), dim)
+            self.pw = _TABLE_CACHE[key]
+        self.par = par
         s = SeqmBatchStruct()
         s.nmol, s.nat, s.npairs, s.method = nmol, self.nat, self.npairs, METHOD_ID[method]
         s.nmax, s.molsize, s.mat_total = self.nmax, molsize, self.mat_total
@@ -139,30 +191,21 @@ class BatchPlan:
         s.atom_par = self.par.data_ptr()
         if self.pw is not None:
             s.pw_alpha, s.pw_chi, s.pw_dim = self.pw[0].data_ptr(), self.pw[1].data_ptr(), self.pw[2]
-        # pair classes: 0 H-H, 1 X-H, 2 X-X (rows are sorted by descending Z, so Z_i >= Z_j for every pair)
-        pcls = (Z[pair_i] > 1).to(torch.int64) + (Z[pair_j] > 1).to(torch.int64)
-        self.pair_perm = torch.argsort(pcls, stable=True).to(torch.int32).contiguous()
-        cnt = torch.bincount(pcls, minlength=3).cpu().tolist()
-        s.pair_cls_off[0], s.pair_cls_off[1] = 0, cnt[0]
-        s.pair_cls_off[2], s.pair_cls_off[3] = cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]
+        s.pair_cls_off[0], s.pair_cls_off[1] = 0, pair_cls_cnt[0]
+        s.pair_cls_off[2], s.pair_cls_off[3] = pair_cls_cnt[0] + pair_cls_cnt[1], sum(pair_cls_cnt)
         s.pair_perm = self.pair_perm.data_ptr()
-        nxx, nxh, nhh = nheavy * (nheavy - 1) // 2, nheavy * nhyd, nhyd * (nhyd - 1) // 2
-        s.fock_scratch = int((20 * nxx + 11 * nxh + 2 * nhh).max())
+        s.fock_scratch = fock_scratch
         # eigensolver size classes over the descending-n processing order (host arrays inside the struct):
         # class c = smallest NP with 2*NP >= n; molecules beyond the last class (large path) belong to none
-        bounds = torch.tensor([2 * q for q in JACOBI_NP], device=dev)
-        cls = torch.bucketize(norb, bounds)  # == len(JACOBI_NP) for n > 2*NP_max
-        cnt = torch.bincount(cls, minlength=len(JACOBI_NP) + 1).cpu().tolist()
-        begin = cnt[len(JACOBI_NP)]  # mol_order is descending in n: the too-large molecules come first
-        for c in range(len(JACOBI_NP) - 1, -1, -1):
+        begin = cls_cnt[ncls]  # mol_order is descending in n: the too-large molecules come first
+        for c in range(ncls - 1, -1, -1):
             s.cls_begin[c] = begin
-            s.cls_count[c] = cnt[c]
-            begin += cnt[c]
+            s.cls_count[c] = cls_cnt[c]
+            begin += cls_cnt[c]
         self.struct = s
         self.ref = C.byref(s)
         self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path
-        z = torch.zeros(1, dtype=torch.float64, device=dev)
-        lib.check(lib.dll.seqm_atom_multipoles(self.ref, stream_of(z)), "seqm_atom_multipoles")
+        lib.check(lib.dll.seqm_atom_multipoles(self.ref, stream_of(par)), "seqm_atom_multipoles")
 
     # ---- helpers -----------------------------------------------------------------------------------
     def new_mat(self):
