@@ -173,7 +173,7 @@ class XL_BOMD(Molecular_Dynamics_Basic):
             )
             ctx["Pt"][self.m - 1 - cindx] = P
             ctx["P"] = P
-        r = self.esdriver.conservative_force_xl.forward_packed(molecule, P)
+        r = self.esdriver.conservative_force_xl.forward_packed(molecule, P, want_e=False)  # MD needs D, E, forces only
         ctx["D"] = r["D"]
         molecule.force, molecule.Hf, molecule.Etot = r["force"], r["Hf"], r["Etot"]
         molecule.Eelec, molecule.Enuc, molecule.Eiso = r["Eelec"], r["Enuc"], r["Eiso"]

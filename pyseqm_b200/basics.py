@@ -175,7 +175,7 @@ class ForceXL(torch.nn.Module):
         self.sp2 = seqm_parameters.get("sp2", [False])
         self._C = None  # eigenvectors of the previous step: warm start of the next density solve
 
-    def forward_packed(self, molecule, Pp):
+    def forward_packed(self, molecule, Pp, want_e=True):
         plan = molecule._plan
         const = molecule.const
         t0 = time.time()
@@ -188,7 +188,7 @@ class ForceXL(torch.nn.Module):
             D, _ = engine.op_sp2_density(plan, F, self.sp2[1])
             e_mo_n = None
         else:
-            e_mo_n, D, self._C = engine.op_eig_density(plan, F, want_P=True, want_C=True, Cguess=self._C)
+            e_mo_n, D, self._C = engine.op_eig_density(plan, F, want_P=True, want_C=True, Cguess=self._C, want_e=want_e)
         t0 = _timing(molecule, "D*", t0)
         Eelec = engine.op_elec_energy_xl(plan, D, Pp, F, H)
         EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)

@@ -78,6 +78,8 @@ def _device_tables(method, dev):
             "rows": rows.to(dev).contiguous(),
             "tore": rows[24].to(dev).contiguous(),
             "jacobi_bounds": torch.tensor([2 * q for q in JACOBI_NP], device=dev),
+            "cls_ids": torch.arange(len(JACOBI_NP) + 1, device=dev).unsqueeze(0),
+            "ones": torch.ones(1, dtype=torch.int64, device=dev),
         }
         _TABLE_CACHE[key] = (T, cols, pw)
     return _TABLE_CACHE[key]
@@ -117,12 +119,13 @@ class BatchPlan:
         nxx, nxh, nhh = nheavy * (nheavy - 1) // 2, nheavy * nhyd, nhyd * (nhyd - 1) // 2
         cls = torch.bucketize(norb, T["jacobi_bounds"])  # == len(JACOBI_NP) for n > 2*NP_max (large path)
         ncls = len(JACOBI_NP)
+        flat_species = species.reshape(-1)
         sorted_ok = (species[:, :-1] >= species[:, 1:]).all() if molsize > 1 else torch.ones((), dtype=torch.bool, device=dev)
         scal = torch.cat([
             cum[:, -1], norb.max().reshape(1), (nel % 2).max().reshape(1), species.max().reshape(1),
             (20 * nxx + 11 * nxh + 2 * nhh).max().reshape(1), sorted_ok.to(torch.int64).reshape(1),
-            torch.stack((nhh.sum(), nxh.sum(), nxx.sum())), torch.bincount(cls, minlength=ncls + 1),
-            torch.bincount(species.reshape(-1), minlength=128)[:128],
+            torch.stack((nhh, nxh, nxx)).sum(dim=1), (cls.unsqueeze(1) == T["cls_ids"]).sum(dim=0),
+            torch.zeros(128, dtype=torch.int64, device=dev).scatter_add_(0, flat_species.clamp(max=127), T["ones"].expand_as(flat_species)),
         ]).cpu().tolist()  # fmt: skip
         self.nat, self.npairs, self.mat_total, self.nmax = scal[0], scal[1], scal[2], scal[3]
         odd, zmax, fock_scratch, self.sorted_ok = scal[4], scal[5], scal[6], bool(scal[7])
@@ -237,10 +240,12 @@ def op_fock(plan, P, H, w, active=None, out=None):
     return F
 
 
-def op_eig_density(plan, F, want_P=True, want_C=False, Cguess=None, active=None):
+def op_eig_density(plan, F, want_P=True, want_C=False, Cguess=None, active=None, want_e=True):
+    """want_e=False asks for the density only: the eigensolver may then finish with its first-order
+    occupied-virtual correction instead of a last sweep (eig_kernels.cuh); eigenvalues are not returned."""
     P = plan.new_mat() if (want_P or Cguess is not None) else None
     Cm = plan.new_mat() if (want_C or Cguess is not None) else None  # the warm start needs both scratch slots
-    e = torch.zeros((plan.nmol, plan.nmax), dtype=torch.float64, device=plan.device)
+    e = torch.zeros((plan.nmol, plan.nmax), dtype=torch.float64, device=plan.device) if want_e else None
     plan.lib.check(
         plan.lib.dll.seqm_eig_density(plan.ref, ptr(F), ptr(P), ptr(e), ptr(Cm), ptr(Cguess), ptr(active), stream_of(F)),
         "seqm_eig_density",
