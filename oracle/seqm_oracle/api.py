@@ -42,7 +42,7 @@ def read_xyz(files):
     return species, coords
 
 
-def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True):
+def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True, charges=0, learned_parameters=None):
     """Returns a dict with the result contract of SURVEY 8(a15)."""
     T = Tables.get()
     method = seqm_parameters["method"]
@@ -61,8 +61,10 @@ def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True):
     eps = float(seqm_parameters["scf_eps"])
     conv = seqm_parameters.get("scf_converger", [2])
     sp2 = seqm_parameters.get("sp2", [False])
-    P = parse(species, coordinates, outer_cutoff=seqm_parameters.get("pair_outer_cutoff", 1.0e10))
+    P = parse(species, coordinates, charges=charges, outer_cutoff=seqm_parameters.get("pair_outer_cutoff", 1.0e10))
     par = method_parameters(table, P.Z)
+    for name in seqm_parameters.get("learned", []):  # basics.py:442-448: only the names listed in `learned` are taken
+        par[name] = np.asarray(learned_parameters[name], dtype=np.float64)
     mp = atom_multipoles(P.Z, par)
     hc = build_hcore(P, par, mp)
     H, w = hc["H"], hc["w"]

@@ -61,8 +61,6 @@ def reject_unsupported(seqm_parameters):
     conv = sp.get("scf_converger", [2])
     if conv[0] not in (0, 1, 2):
         bad.append(f"scf_converger={conv}")
-    if sp.get("learned"):
-        bad.append("learned parameter gradients")
     if bad:
         raise NotImplementedError("not implemented by the B200 SCF path: " + ", ".join(bad))
 
@@ -103,7 +101,15 @@ class Molecule(torch.nn.Module):
                 )
             kernel_method, table = "PM6_SP", "PM6"
         lib = _lib if _lib is not None else get_lib()
-        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned_parameters, charges=charges, table=table)
+        # basics.py:442-448: only the names listed in seqm_parameters["learned"] are taken from learned_parameters,
+        # everything else comes from the method's table.  Values only: no gradients flow back to them.
+        learned = {}
+        for name in seqm_parameters.get("learned", []):
+            t = learned_parameters[name]
+            if t.requires_grad:
+                raise NotImplementedError("gradients with respect to learned parameters need autograd through the SCF; not on the B200 path")
+            learned[name] = t.detach()
+        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned, charges=charges, table=table)
         self._plan = plan
         if seqm_parameters.get("elements") is None:
             seqm_parameters["elements"] = plan.elements

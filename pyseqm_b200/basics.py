@@ -35,9 +35,12 @@ class Energy(torch.nn.Module):
         self.notconverged = None
 
     def forward(self, molecule, learned_parameters=dict(), all_terms=False, P0=None, do_force=False, *args, **kwargs):
-        if learned_parameters:
-            raise NotImplementedError("pass learned parameters (dict of (nat,) tensors) to Molecule(...), not to forward()")
         plan = molecule._plan
+        if learned_parameters:
+            # basics.py:783-789 re-packs the parameters on every call: refresh the rows named in `learned`
+            if callable(learned_parameters):
+                raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
+            plan.set_parameters({k: learned_parameters[k] for k in self.seqm_parameters.get("learned", [])})
         const = molecule.const
         if plan.large and not self.sp2[0]:
             raise NotImplementedError(

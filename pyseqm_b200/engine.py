@@ -210,6 +210,16 @@ class BatchPlan:
         self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path
         lib.check(lib.dll.seqm_atom_multipoles(self.ref, stream_of(par)), "seqm_atom_multipoles")
 
+    def set_parameters(self, learned):
+        """Overwrite per-atom parameter rows (values only) and rebuild the multipole rows that depend on them."""
+        if not learned:
+            return
+        for name, t in learned.items():
+            if t.requires_grad:
+                raise NotImplementedError("gradients with respect to learned parameters are not on the B200 path")
+            self.par[PAR_ROWS.index(name)] = t.detach().to(torch.float64)
+        self.lib.check(self.lib.dll.seqm_atom_multipoles(self.ref, stream_of(self.par)), "seqm_atom_multipoles")
+
     # ---- helpers -----------------------------------------------------------------------------------
     def new_mat(self):
         return torch.zeros(self.mat_total, dtype=torch.float64, device=self.device)

@@ -28,14 +28,15 @@ def cuda_lib():
     return get_lib()
 
 
-def run_molecule(lib, device, species, coordinates, sp, P0=None):
+def run_molecule(lib, device, species, coordinates, sp, P0=None, charges=0, learned=None):
     torch.set_default_dtype(torch.float64)
     const = seqm.Constants().to(device)
+    kw = {} if learned is None else {"learned_parameters": learned}
     mol = seqm.Molecule(const, dict(sp), torch.as_tensor(coordinates, device=device),
-                        torch.as_tensor(species, device=device), _lib=lib)  # fmt: skip
+                        torch.as_tensor(species, device=device), charges=charges, _lib=lib, **kw)  # fmt: skip
     mol.verbose = False
     es = seqm.Electronic_Structure(dict(sp))
-    es(mol, P0=P0)
+    es(mol, P0=P0, **kw)
     return mol, es
 
 
@@ -43,9 +44,17 @@ def run_molecule(lib, device, species, coordinates, sp, P0=None):
 CHAOTIC_DIIS = {"thirdrow_MNDO_c2"}
 
 
+def golden_inputs(g, device):
+    """charges / learned per-atom parameters stored with the option-matrix fixtures"""
+    charges = torch.as_tensor(g["charges"], device=device) if "charges" in g else 0
+    learned = {k[len("learned_"):]: torch.as_tensor(g[k], device=device) for k in g if k.startswith("learned_")}
+    return charges, (learned or None)
+
+
 def check_golden_case(lib, device, name, sp2_tolerant=False):
     g = load_golden(name)
-    mol, es = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"])
+    charges, learned = golden_inputs(g, device)
+    mol, es = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"], charges=charges, learned=learned)
     if name not in CHAOTIC_DIIS:
         assert mol.n_scf_iter == g["n_scf_iter"], (mol.n_scf_iter, g["n_scf_iter"])
     assert not bool(es.notconverged.any())
