@@ -84,6 +84,37 @@ const char* seqm_last_error(void);
  * larger molecules run the global-memory Fock / GEMM-SP2 / GEMM-DIIS path and need sp2=[True, eps] */
 int seqm_max_orbitals(void);
 
+/* ---- batch plan construction on the device ---------------------------------------------------------------------
+ * Replaces Parser.forward (seqm/basics.py:219-403: real-atom compaction, pair list i<j, molecule ids, nHeavy /
+ * nHydro / nocc, closed-shell check) and Pack_Parameters.forward (basics.py:442-448: per-atom parameter gather).
+ * Two calls, because the atom / pair array sizes are results of the first:
+ *   1. seqm_plan_count : per-molecule arrays + every scalar the host needs (blocks until they are on the host)
+ *   2. seqm_plan_fill  : atom lists, per-atom parameter rows, pair list, class-sorted pair ids
+ * species: (nmol, molsize) int64 on the device, rows sorted by descending Z, zero padded (Molecule.py:188-206);
+ * charges: NULL or (nmol) int64; elem_rows: (nrows, nz) per-element table, row SEQM_P_TORE = valence electrons. */
+typedef struct {
+  int32_t nat, npairs, nmax, zmax;
+  int64_t mat_total;
+  int32_t odd_electrons;      /* some molecule has an odd electron count (basics.py:298-299 raises) */
+  int32_t unsorted;           /* some species row is not non-increasing (Molecule.py:198-206 raises) */
+  int32_t pairs_overflow;     /* more than 2^31-1 pairs */
+  int32_t fock_scratch;
+  int32_t pair_cls_cnt[3];    /* H-H, X-H, X-X */
+  int32_t jacobi_cls_cnt[13]; /* molecules per eigensolver size class; [12] = beyond the last class (large path) */
+  int32_t elements[128];      /* 1 where element Z occurs */
+} seqm_plan_counts_t;
+int seqm_plan_count(const int64_t* species, int32_t nmol, int32_t molsize, const int64_t* charges,
+                    const double* elem_rows, int32_t nz, int32_t* mol_atom0, int32_t* mol_pair0, int64_t* mol_mat0,
+                    int32_t* mol_nheavy, int32_t* mol_nhyd, int32_t* mol_nocc, int32_t* mol_order,
+                    int32_t* mol_cls_pair0 /* 3*nmol */, seqm_plan_counts_t* counts_dev, seqm_plan_counts_t* counts_host,
+                    void* stream);
+/* atom_par: (SEQM_NPAR, nat), rows [0, nrows) are written; real_atoms: (nat) int64 flat index mol*molsize + pos */
+int seqm_plan_fill(const int64_t* species, int32_t nmol, int32_t molsize, const seqm_plan_counts_t* counts_host,
+                   const int32_t* mol_atom0, const int32_t* mol_pair0, const int32_t* mol_nheavy,
+                   const int32_t* mol_cls_pair0, const double* elem_rows, int32_t nrows, int32_t nz, int32_t* atom_Z,
+                   int32_t* atom_mol, int64_t* real_atoms, double* atom_par, int32_t* pair_i, int32_t* pair_j,
+                   int32_t* pair_perm, void* stream);
+
 /* cal_par.py:11-28,112-169,198-257 + two_elec_two_center_int.py:116-247: dd, qq, rho0, rho1, rho2 per atom */
 int seqm_atom_multipoles(const seqm_batch_t* b, void* stream);
 

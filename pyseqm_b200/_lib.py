@@ -46,6 +46,13 @@ class SeqmScfOpts(C.Structure):
                 ("pipeline", C.c_int32)]  # fmt: skip
 
 
+class SeqmPlanCounts(C.Structure):  # mirrors seqm_plan_counts_t
+    _fields_ = [("nat", C.c_int32), ("npairs", C.c_int32), ("nmax", C.c_int32), ("zmax", C.c_int32),
+                ("mat_total", C.c_int64), ("odd_electrons", C.c_int32), ("unsorted", C.c_int32),
+                ("pairs_overflow", C.c_int32), ("fock_scratch", C.c_int32), ("pair_cls_cnt", C.c_int32 * 3),
+                ("jacobi_cls_cnt", C.c_int32 * 13), ("elements", C.c_int32 * 128)]  # fmt: skip
+
+
 class SeqmError(RuntimeError):
     pass
 
@@ -81,6 +88,10 @@ class SeqmLib:
             "seqm_abi_version": ([], C.c_int),
             "seqm_last_error": ([], C.c_char_p),
             "seqm_max_orbitals": ([], C.c_int),
+            "seqm_plan_count": ([P, C.c_int32, C.c_int32, P, P, C.c_int32, P, P, P, P, P, P, P, P, P,
+                                 C.POINTER(SeqmPlanCounts), P], C.c_int),
+            "seqm_plan_fill": ([P, C.c_int32, C.c_int32, C.POINTER(SeqmPlanCounts), P, P, P, P, P, C.c_int32, C.c_int32,
+                                P, P, P, P, P, P, P, P], C.c_int),
             "seqm_atom_multipoles": ([B, P], C.c_int),
             "seqm_pair_integrals": ([B, P, P, P, P], C.c_int),
             "seqm_hcore": ([B, P, P, P, P], C.c_int),

@@ -2,6 +2,7 @@
 // Single translation unit: all kernels live in the .cuh files included below.
 #include "pair_kernels.cuh"
 #include "scf_driver.cuh"
+#include "plan_kernels.cuh"
 
 #ifndef SEQM_HOSTEMU
 #define SEQM_STREAM(s) ((cudaStream_t)(s))
@@ -421,6 +422,56 @@ int seqm_profile_collect(double* ms, int32_t* counts) {
   g_ev_n = 0;
 #endif
   return SEQM_OK;
+}
+
+int seqm_plan_count(const int64_t* species, int32_t nmol, int32_t molsize, const int64_t* charges, const double* elem_rows,
+                    int32_t nz, int32_t* mol_atom0, int32_t* mol_pair0, int64_t* mol_mat0, int32_t* mol_nheavy,
+                    int32_t* mol_nhyd, int32_t* mol_nocc, int32_t* mol_order, int32_t* mol_cls_pair0,
+                    seqm_plan_counts_t* counts_dev, seqm_plan_counts_t* counts_host, void* stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (nmol <= 0 || molsize <= 0 || !species || !counts_dev || !counts_host) {
+    seqm_set_error("seqm_plan_count: empty batch or null pointer");
+    return SEQM_ERR_ARG;
+  }
+  PlanBounds pb;
+  for (int c = 0; c < SEQM_PLAN_NCLS; ++c) pb.np2[c] = 2 * g_jacobi_np[c];
+  const size_t dyn = sizeof(int) * 2 * (size_t)(4 * molsize + 2);
+  cudaStream_t st = SEQM_STREAM(stream);
+  SEQM_LAUNCH(plan_count_kernel, 1, SEQM_PLAN_THREADS, dyn, st, (const long long*)species, nmol, molsize, (const long long*)charges,
+              elem_rows + (size_t)SEQM_P_TORE * nz, nz, pb, mol_atom0, mol_pair0, (long long*)mol_mat0, mol_nheavy, mol_nhyd,
+              mol_nocc, mol_order, mol_cls_pair0, counts_dev);
+  rc = seqm_check_launch("plan_count_kernel");
+  if (rc) return rc;
+#ifndef SEQM_HOSTEMU
+  cudaError_t e = cudaMemcpyAsync(counts_host, counts_dev, sizeof(seqm_plan_counts_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    seqm_set_error("seqm_plan_count: %s", cudaGetErrorString(e));
+    return SEQM_ERR_CUDA;
+  }
+#else
+  *counts_host = *counts_dev;
+#endif
+  if (counts_host->pairs_overflow) {
+    seqm_set_error("seqm_plan_count: more than 2^31-1 atom pairs in one batch");
+    return SEQM_ERR_TOO_LARGE;
+  }
+  return SEQM_OK;
+}
+
+int seqm_plan_fill(const int64_t* species, int32_t nmol, int32_t molsize, const seqm_plan_counts_t* counts_host,
+                   const int32_t* mol_atom0, const int32_t* mol_pair0, const int32_t* mol_nheavy,
+                   const int32_t* mol_cls_pair0, const double* elem_rows, int32_t nrows, int32_t nz, int32_t* atom_Z,
+                   int32_t* atom_mol, int64_t* real_atoms, double* atom_par, int32_t* pair_i, int32_t* pair_j,
+                   int32_t* pair_perm, void* stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  const int off_xh = counts_host->pair_cls_cnt[0], off_xx = off_xh + counts_host->pair_cls_cnt[1];
+  SEQM_LAUNCH(plan_fill_kernel, nmol, 128, 0, SEQM_STREAM(stream), (const long long*)species, nmol, molsize, counts_host->nat,
+              mol_atom0, mol_pair0, mol_nheavy, mol_cls_pair0, elem_rows, nrows, nz, off_xh, off_xx, atom_Z, atom_mol,
+              (long long*)real_atoms, atom_par, pair_i, pair_j, pair_perm);
+  return seqm_check_launch("plan_fill_kernel");
 }
 
 int seqm_atom_multipoles(const seqm_batch_t* b, void* stream) {

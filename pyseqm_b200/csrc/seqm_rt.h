@@ -32,6 +32,7 @@ SEQM_D double seqm_rsqrt(double x) { return rsqrt(x); }
 SEQM_D void seqm_atomic_or(int* a, int v) { atomicOr(a, v); }
 SEQM_D int seqm_atomic_add(int* a, int v) { return atomicAdd(a, v); }
 SEQM_D void seqm_atomic_max_u32(unsigned* a, unsigned v) { atomicMax(a, v); }
+SEQM_D void seqm_atomic_max(int* a, int v) { atomicMax(a, v); }
 #else
 typedef void* cudaStream_t;
 typedef int cudaError_t;
@@ -68,6 +69,7 @@ inline double seqm_rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline void seqm_atomic_or(int* a, int v) { *a |= v; }
 inline int seqm_atomic_add(int* a, int v) { int o = *a; *a += v; return o; }
 inline void seqm_atomic_max_u32(unsigned* a, unsigned v) { if (v > *a) *a = v; }
+inline void seqm_atomic_max(int* a, int v) { if (v > *a) *a = v; }
 using std::exp; using std::fabs; using std::sqrt; using std::pow; using std::fmax; using std::fmin;
 template <class T> inline T min(T a, T b) { return a < b ? a : b; }
 template <class T> inline T max(T a, T b) { return a > b ? a : b; }

@@ -10,7 +10,8 @@ import os
 
 import torch
 
-from ._lib import JACOBI_NP, METHOD_ID, NPAR, PAR_ROWS, SeqmBatchStruct, SeqmError, SeqmScfOpts, ptr, stream_of
+from ._lib import (JACOBI_NP, METHOD_ID, NPAR, PAR_ROWS, SeqmBatchStruct, SeqmError, SeqmPlanCounts, SeqmScfOpts, ptr,
+                   stream_of)  # fmt: skip
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 _TABLE_CACHE = {}
@@ -99,76 +100,55 @@ class BatchPlan:
         nmol, molsize = species.shape
         self.nmol, self.molsize, self.method = nmol, molsize, method
         T, cols, pw = _device_tables(table or method, dev)
-        # ---- per-molecule counts, then ONE host read-back of every scalar the host needs -------------------
-        real = species > 0
-        self.real_mask = real
-        na = real.sum(dim=1)
-        nhyd = (species == 1).sum(dim=1)
-        nheavy = na - nhyd
-        nel = T["tore"][species].sum(dim=1).to(torch.int64)
+        sp64 = species.to(torch.int64).contiguous()
+        ch = None
         if torch.is_tensor(charges):
-            nel = nel - charges.reshape(-1).to(torch.int64).to(dev)
-        else:
-            nel = nel - int(charges)
-        nocc = nel // 2
-        norb = 4 * nheavy + nhyd
-        npair_m = na * (na - 1) // 2
-        nn = norb * norb
-        nn = nn + (nn % 2)
-        cum = torch.cumsum(torch.stack((na, npair_m, nn)), dim=1)  # (3, nmol)
-        nxx, nxh, nhh = nheavy * (nheavy - 1) // 2, nheavy * nhyd, nhyd * (nhyd - 1) // 2
-        cls = torch.bucketize(norb, T["jacobi_bounds"])  # == len(JACOBI_NP) for n > 2*NP_max (large path)
-        ncls = len(JACOBI_NP)
-        flat_species = species.reshape(-1)
-        sorted_ok = (species[:, :-1] >= species[:, 1:]).all() if molsize > 1 else torch.ones((), dtype=torch.bool, device=dev)
-        scal = torch.cat([
-            cum[:, -1], norb.max().reshape(1), (nel % 2).max().reshape(1), species.max().reshape(1),
-            (20 * nxx + 11 * nxh + 2 * nhh).max().reshape(1), sorted_ok.to(torch.int64).reshape(1),
-            torch.stack((nhh, nxh, nxx)).sum(dim=1), (cls.unsqueeze(1) == T["cls_ids"]).sum(dim=0),
-            torch.zeros(128, dtype=torch.int64, device=dev).scatter_add_(0, flat_species.clamp(max=127), T["ones"].expand_as(flat_species)),
-        ]).cpu().tolist()  # fmt: skip
-        self.nat, self.npairs, self.mat_total, self.nmax = scal[0], scal[1], scal[2], scal[3]
-        odd, zmax, fock_scratch, self.sorted_ok = scal[4], scal[5], scal[6], bool(scal[7])
-        self.zmax = zmax
-        pair_cls_cnt, cls_cnt = scal[8:11], scal[11 : 12 + ncls]
-        self.elements = [z for z in range(128) if scal[12 + ncls + z] > 0 or z == 0]
+            ch = charges.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        elif int(charges) != 0:
+            ch = torch.full((nmol,), int(charges), dtype=torch.int64, device=dev)
+        # ---- step 1 (seqm_plan_count): per-molecule arrays, scans, processing order, host scalars ------------
+        mi = torch.empty(9 * nmol + 2 + 256, dtype=torch.int32, device=dev)  # one allocation, sliced below
+        atom0, pair0 = mi[: nmol + 1], mi[nmol + 1 : 2 * nmol + 2]
+        o = 2 * nmol + 2
+        nheavy32, nhyd32, nocc32, order = (mi[o + k * nmol : o + (k + 1) * nmol] for k in range(4))
+        cls_pair0 = mi[o + 4 * nmol : o + 7 * nmol]
+        counts_dev = mi[o + 7 * nmol + (o + 7 * nmol) % 2 :]  # 8-byte aligned tail (>= sizeof(seqm_plan_counts_t))
+        mat0 = torch.empty(nmol + 1, dtype=torch.int64, device=dev)
+        cnt = SeqmPlanCounts()
+        st = stream_of(mi)
+        nz = T["rows"].shape[1]
+        lib.check(lib.dll.seqm_plan_count(ptr(sp64), nmol, molsize, ptr(ch), ptr(T["rows"]), nz, ptr(atom0), ptr(pair0),
+                                          ptr(mat0), ptr(nheavy32), ptr(nhyd32), ptr(nocc32), ptr(order), ptr(cls_pair0),
+                                          ptr(counts_dev), C.byref(cnt), st), "seqm_plan_count")  # fmt: skip
+        self.nat, self.npairs, self.mat_total, self.nmax = cnt.nat, cnt.npairs, cnt.mat_total, cnt.nmax
+        self.zmax, self.sorted_ok = cnt.zmax, not cnt.unsorted
+        self.elements = [0] + [z for z in range(1, 128) if cnt.elements[z]]
         if not self.sorted_ok:
             check_input(species)
-        if odd:
+        if cnt.odd_electrons:
             raise ValueError("RHF setting requires closed shell systems (even number of electrons)")
-        self.na, self.nheavy, self.nhyd, self.nocc, self.norb = na, nheavy, nhyd, nocc, norb
-        # ---- atom and pair lists (rows are sorted by descending Z: real atoms are the first na of a row) ----
-        zero = torch.zeros((3, 1), dtype=torch.int64, device=dev)
-        starts = torch.cat([zero, cum], dim=1)
-        atom0, pair0, mat0 = starts[0], starts[1], starts[2]
-        ar_mol = torch.arange(nmol, device=dev)
-        atom_mol = torch.repeat_interleave(ar_mol, na, output_size=self.nat)
-        ar_at = torch.arange(self.nat, device=dev)
-        local = ar_at - atom0[atom_mol]
-        self.real_atoms = atom_mol * molsize + local
-        Z = species.reshape(-1)[self.real_atoms]
-        self.Z = Z
-        # dense triangular pair list ordered (molecule, i, j)
-        cnt = na[atom_mol] - 1 - local
-        pair_i = torch.repeat_interleave(ar_at, cnt, output_size=self.npairs)
-        first_of_i = torch.cumsum(cnt, 0) - cnt
-        pair_j = pair_i + 1 + (torch.arange(self.npairs, device=dev) - first_of_i[pair_i])
-        order = torch.argsort(norb, descending=True, stable=True)
-        # pair classes: 0 H-H, 1 X-H, 2 X-X (Z_i >= Z_j for every pair)
-        heavy = Z > 1
-        pcls = heavy[pair_i].to(torch.int8) + heavy[pair_j].to(torch.int8)
-        self.pair_perm = torch.argsort(pcls, stable=True).to(torch.int32)
-        i32 = lambda t: t.to(torch.int32).contiguous()  # noqa: E731
-        self.t = dict(
-            mol_atom0=i32(atom0), mol_pair0=i32(pair0), mol_mat0=mat0.contiguous(), mol_nheavy=i32(nheavy),
-            mol_nhyd=i32(nhyd), mol_nocc=i32(nocc), mol_order=i32(order), atom_Z=i32(Z), atom_mol=i32(atom_mol),
-            pair_i=i32(pair_i), pair_j=i32(pair_j),
-        )  # fmt: skip
-        self.atom_mol, self.atom_local = atom_mol, local
-        self.pair_i, self.pair_j = pair_i, pair_j
-        # ---- per-atom parameter table: one gather from the cached per-element device table ------------------
+        # ---- step 2 (seqm_plan_fill): atoms, per-atom parameters, pair list, class-sorted pair ids -----------
+        ai = torch.empty(2 * self.nat + 3 * self.npairs, dtype=torch.int32, device=dev)
+        atom_Z32, atom_mol32 = ai[: self.nat], ai[self.nat : 2 * self.nat]
+        pair_i32, pair_j32, self.pair_perm = (ai[2 * self.nat + k * self.npairs : 2 * self.nat + (k + 1) * self.npairs] for k in range(3))
+        self.real_atoms = torch.empty(self.nat, dtype=torch.int64, device=dev)
         par = torch.zeros((NPAR, self.nat), dtype=torch.float64, device=dev)
-        par[:28] = T["rows"][:, Z]
+        lib.check(lib.dll.seqm_plan_fill(ptr(sp64), nmol, molsize, C.byref(cnt), ptr(atom0), ptr(pair0), ptr(nheavy32),
+                                         ptr(cls_pair0), ptr(T["rows"]), 28, nz, ptr(atom_Z32), ptr(atom_mol32),
+                                         ptr(self.real_atoms), ptr(par), ptr(pair_i32), ptr(pair_j32), ptr(self.pair_perm),
+                                         st), "seqm_plan_fill")  # fmt: skip
+        self._keep = (mi, ai, sp64, ch)
+        self.real_mask = None
+        self.t = dict(mol_atom0=atom0, mol_pair0=pair0, mol_mat0=mat0, mol_nheavy=nheavy32, mol_nhyd=nhyd32,
+                      mol_nocc=nocc32, mol_order=order, atom_Z=atom_Z32, atom_mol=atom_mol32, pair_i=pair_i32,
+                      pair_j=pair_j32)  # fmt: skip
+        # int64 views for torch-side index arithmetic are made on first use (see __getattr__)
+        pair_cls_cnt = list(cnt.pair_cls_cnt)
+        cls_cnt = list(cnt.jacobi_cls_cnt)
+        fock_scratch = cnt.fock_scratch
+        ncls = len(JACOBI_NP)
+        zmax = cnt.zmax
+        # ---- per-atom parameter overrides (values only) ---------------------------------------------------
         if parameters:
             for r, name in enumerate(PAR_ROWS[:24]):
                 if parameters.get(name) is not None:
@@ -209,6 +189,23 @@ class BatchPlan:
         self.ref = C.byref(s)
         self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path
         lib.check(lib.dll.seqm_atom_multipoles(self.ref, stream_of(par)), "seqm_atom_multipoles")
+
+    _LAZY64 = {"nheavy": "mol_nheavy", "nhyd": "mol_nhyd", "nocc": "mol_nocc", "Z": "atom_Z", "atom_mol": "atom_mol",
+               "pair_i": "pair_i", "pair_j": "pair_j"}  # fmt: skip
+
+    def __getattr__(self, name):  # int64 copies of the int32 kernel arrays, for torch indexing, on first use
+        d = self.__dict__
+        if name in BatchPlan._LAZY64 and "t" in d:
+            d[name] = d["t"][BatchPlan._LAZY64[name]].to(torch.int64)
+        elif name == "na" and "t" in d:
+            d["na"] = self.nheavy + self.nhyd
+        elif name == "norb" and "t" in d:
+            d["norb"] = 4 * self.nheavy + self.nhyd
+        elif name == "atom_local" and "t" in d:
+            d["atom_local"] = torch.arange(self.nat, device=self.device) - d["t"]["mol_atom0"].to(torch.int64)[self.atom_mol]
+        else:
+            raise AttributeError(name)
+        return d[name]
 
     def set_parameters(self, learned):
         """Overwrite per-atom parameter rows (values only) and rebuild the multipole rows that depend on them."""
