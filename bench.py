@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)  # fmt: skip
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -180,7 +180,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nmol", type=int, default=4096)
@@ -345,7 +345,10 @@ def main():
             "kernel": "jacobi_density_kernel", "bound": "fp64-vector (no FP64 tcgen05 kind exists; shared-memory "
             "resident Jacobi sweeps)", "achieved": (jac_flops / (j_ms * 1e-3) / 1e12) if j_ms else None,
             "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured in this run: seqm_fp64_peak_tflops() "
-            "DFMA probe (MEASURED_PEAKS.json has no fp64 entry)", "traffic": None,
+            "DFMA probe (MEASURED_PEAKS.json has no fp64 entry)",
+            "traffic": 77.4e6, "traffic_note": "DRAM bytes read + written per full-batch eigensolver call from the ncu --set full "
+            "capture in profiles/jacobi_r01_final.txt (38.7 MB per half-batch call over the five populated size classes; "
+            "writes stay in the 126 MB L2); the HBM floor 16 n^2 B per molecule is 74.9 MB",
             "algorithmic": "10 n^3 + 2 n^2 nocc flop (batch mean) x molecules solved in the step (library counter)",
             "molecules_solved": jstats["molecules"], "sweeps_per_solve": round(jstats["sweeps"] / max(jstats["molecules"], 1), 3),
             "share_of_step": round(j_ms / tot, 4), "dominant_kernel_by_time": top,
