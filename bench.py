@@ -145,12 +145,21 @@ def cpu_reference_rate(sample, cores, steps=1, warmup=0):
     species, coords, _ = workload(4096, 0)
     species, coords = species[:sample], coords[:sample]
     times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        out = so.single_point(species, coords, SP)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
+    import contextlib
+
+    try:  # torchrun exports OMP_NUM_THREADS=1: ask the BLAS/OpenMP pools for every host thread explicitly
+        from threadpoolctl import threadpool_limits
+
+        pool = threadpool_limits(limits=cores)
+    except Exception:
+        pool = contextlib.nullcontext()
+    with pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = so.single_point(species, coords, SP)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
     assert np.all(np.isfinite(out["Etot"])) and not out["notconverged"].any()
     dt = sum(times) / len(times)
     return sample / dt, dt

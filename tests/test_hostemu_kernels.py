@@ -75,3 +75,21 @@ def test_lazy_orbital_charge_table(lib):
     for m in range(3):
         assert np.abs(c[m, : norb[m]].sum(dim=1).numpy() - 1.0).max() < 1e-12
         assert float(c[m, norb[m] :].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("nmol", [1, 2, 3])
+def test_forced_half_batches_on_tiny_batches(lib, nmol, monkeypatch):
+    """seqm_scf_opts_t.pipeline = 2 on 1-3 molecules (empty / unequal halves) gives the single-stream result."""
+    from conftest import load_golden
+
+    g = load_golden("cfg1_AM1_c2")
+    sp_, xyz = g["species"][:nmol], g["coordinates"][:nmol]
+    res = {}
+    for mode in ("1", "2"):
+        monkeypatch.setenv("SEQM_B200_PIPELINE", mode)
+        mol, _ = run_molecule(lib, CPU, sp_, xyz, g["seqm_parameters"])
+        res[mode] = (mol.n_scf_iter, mol.Etot.numpy().copy(), mol.dm.numpy().copy())
+    assert res["1"][0] == res["2"][0]
+    assert np.array_equal(res["1"][1], res["2"][1]) and np.array_equal(res["1"][2], res["2"][2])
+    if nmol == 3:
+        assert res["1"][0] == g["n_scf_iter"]
