@@ -200,3 +200,58 @@ def check_level_b_signatures(lib, device, method):
         assert np.abs(-grad.cpu().numpy() - g["force"]).max() < TOL_F
     finally:
         _plans.use_library(None)
+
+
+def check_device_batch_plan(lib, device):
+    """seqm_plan_count / seqm_plan_fill (parser + parameter gather on the device) against a plain numpy restatement
+    of basics.py:219-403 on a ragged random batch: offsets, pair list order, class-sorted pair ids, processing order."""
+    from pyseqm_b200 import engine
+
+    rng = np.random.default_rng(5)
+    nmol, molsize = (37, 11) if device.type == "cpu" else (1500, 23)
+    species = np.zeros((nmol, molsize), dtype=np.int64)
+    for m in range(nmol):
+        na = int(rng.integers(1, molsize + 1))
+        z = rng.choice([1, 1, 1, 6, 7, 8], size=na)
+        if int(np.sum(np.array([0, 1, 0, 0, 0, 0, 4, 5, 6])[z])) % 2:  # keep the electron count even
+            z[0] = 7 if z[0] != 7 else 6
+            if int(np.sum(np.array([0, 1, 0, 0, 0, 0, 4, 5, 6])[z])) % 2:
+                z = np.append(z[:-1], 1) if z[-1] != 1 else z[:-1]
+        z = np.sort(z)[::-1]
+        if int(np.sum(np.array([0, 1, 0, 0, 0, 0, 4, 5, 6])[z])) % 2:
+            z = np.array([8, 1, 1])
+        species[m, : len(z)] = z
+    plan = engine.BatchPlan(lib, torch.as_tensor(species, device=device), "AM1")
+    na = (species > 0).sum(1)
+    nh = (species > 1).sum(1)
+    ny = na - nh
+    n = 4 * nh + ny
+    assert plan.nat == na.sum() and plan.npairs == (na * (na - 1) // 2).sum() and plan.nmax == n.max()
+    t = {k: v.cpu().numpy() for k, v in plan.t.items()}
+    assert np.array_equal(t["mol_atom0"], np.concatenate([[0], np.cumsum(na)]))
+    assert np.array_equal(t["mol_pair0"], np.concatenate([[0], np.cumsum(na * (na - 1) // 2)]))
+    nn = n * n + (n * n) % 2
+    assert np.array_equal(t["mol_mat0"], np.concatenate([[0], np.cumsum(nn)]))
+    assert np.array_equal(t["mol_nheavy"], nh) and np.array_equal(t["mol_nhyd"], ny)
+    tore = np.array([0, 1, 0, 0, 0, 0, 4, 5, 6])
+    assert np.array_equal(t["mol_nocc"], tore[species].sum(1) // 2)
+    assert np.array_equal(t["mol_order"], np.argsort(-n, kind="stable"))
+    Z = species[species > 0]  # row-major: molecule-major, sorted rows
+    assert np.array_equal(t["atom_Z"], Z) and np.array_equal(t["atom_mol"], np.repeat(np.arange(nmol), na))
+    pi, pj = [], []
+    a0 = np.concatenate([[0], np.cumsum(na)])
+    for m in range(nmol):
+        for i in range(na[m]):
+            for j in range(i + 1, na[m]):
+                pi.append(a0[m] + i)
+                pj.append(a0[m] + j)
+    pi, pj = np.array(pi), np.array(pj)
+    assert np.array_equal(t["pair_i"], pi) and np.array_equal(t["pair_j"], pj)
+    cls = (Z[pi] > 1).astype(int) + (Z[pj] > 1).astype(int)
+    assert np.array_equal(plan.pair_perm.cpu().numpy(), np.argsort(cls, kind="stable"))
+    assert [plan.struct.pair_cls_off[k] for k in range(4)] == [0] + list(np.cumsum(np.bincount(cls, minlength=3)))
+    assert np.array_equal(plan.real_atoms.cpu().numpy(), np.flatnonzero(species.reshape(-1) > 0))
+    assert plan.elements == [0] + sorted(set(Z.tolist()))
+    tab, cols, _ = engine.method_table("AM1")
+    assert np.array_equal(plan.parameter("U_ss").cpu().numpy(), tab[:, cols.index("U_ss")].numpy()[Z])
+    assert np.array_equal(plan.parameter("zeta_p").cpu().numpy(), tab[:, cols.index("zeta_p")].numpy()[Z])

@@ -184,3 +184,9 @@ def test_pipelined_scf_is_bitwise_identical_to_single_stream(lib, dev, monkeypat
     assert out["1"][0] == out["2"][0]
     for a, b in zip(out["1"][1:], out["2"][1:]):
         assert torch.equal(a, b)
+
+
+def test_device_batch_plan_against_numpy(lib, dev):
+    from helpers import check_device_batch_plan
+
+    check_device_batch_plan(lib, dev)

@@ -93,3 +93,9 @@ def test_forced_half_batches_on_tiny_batches(lib, nmol, monkeypatch):
     assert np.array_equal(res["1"][1], res["2"][1]) and np.array_equal(res["1"][2], res["2"][2])
     if nmol == 3:
         assert res["1"][0] == g["n_scf_iter"]
+
+
+def test_device_batch_plan_against_numpy(lib):
+    from helpers import check_device_batch_plan
+
+    check_device_batch_plan(lib, CPU)
