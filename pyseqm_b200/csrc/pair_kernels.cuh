@@ -106,8 +106,14 @@ SEQM_HD void pair_overlap(const seqm_batch_t& b, int i, int j, const PairGeom<T>
 
 // CLS: 0 H-H, 1 X-H, 2 X-X -- the kernel walks the class's pair list, so every warp is divergence-free and the
 // block sizes (1 | 10 orbital products, 1 | 4 | 22 local integrals) are compile-time constants.
+#ifndef SEQM_PI_MINB
+#define SEQM_PI_MINB 0
+#endif
+#ifndef SEQM_PG_MINB
+#define SEQM_PG_MINB 4  // 128 registers: measured 13 % faster than the unconstrained 168-188 (latency bound on its stack arrays)
+#endif
 template <int CLS>
-SEQM_GLOBAL void pair_integrals_kernel(seqm_batch_t b, const double* __restrict__ xyz, double* __restrict__ w,
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS == 2) ? SEQM_PI_MINB : 0) pair_integrals_kernel(seqm_batch_t b, const double* __restrict__ xyz, double* __restrict__ w,
                                        double* __restrict__ hab) {
   constexpr int nA = (CLS >= 1) ? 10 : 1, nB = (CLS == 2) ? 10 : 1, nint = (CLS == 2) ? 22 : ((CLS == 1) ? 4 : 1);
   const int q0 = b.pair_cls_off[CLS], q1 = b.pair_cls_off[CLS + 1];
@@ -207,7 +213,7 @@ SEQM_HD int cls_of(int kl) { return pack_class(kl); }
 // the XL-BOMD shadow energy  E = sum D o F(P) - 1/2 (F(P) - h) o P + E_nuc  (energy.py:76-88, xlbomd.py:430-447);
 // with D == P it is the ordinary SCF energy.  (No __restrict__ on D/P: they may alias.)
 template <int CLS>
-SEQM_GLOBAL void pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* D, const double* P,
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz, const double* D, const double* P,
                                       double* __restrict__ gpair) {
   constexpr bool hi = (CLS >= 1), hj = (CLS == 2);
   constexpr int ni = hi ? 4 : 1, nj = hj ? 4 : 1;
