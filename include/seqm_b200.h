@@ -191,7 +191,8 @@ typedef struct seqm_scf_opts {
   int32_t use_sp2;
   double sp2_eps;
   int32_t max_iter;  /* reference: 1000 */
-  int32_t warm_start;/* 1: eigensolver starts from the previous iteration's eigenvectors */
+  int32_t warm_start;/* 1: eigensolver starts from the previous iteration's eigenvectors; 2: additionally the FIRST
+                      * solve starts from the eigenvectors the caller left in C_last (restart from a nearby geometry) */
   int32_t pipeline;  /* Pulay DIIS only. 0: auto (two half-batches out of phase on two streams when nmol >= 256),
                       * 1: single stream, 2: always two half-batches. Results do not depend on it. */
 } seqm_scf_opts_t;

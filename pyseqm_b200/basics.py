@@ -59,8 +59,14 @@ class Energy(torch.nn.Module):
             P = engine.op_initial_density(plan)
         else:
             P = engine.op_pack(plan, narrow_orbitals(P0, plan.molsize, molecule.orbital_stride) if wide else P0)
+        # restart (P0 given, e.g. an MD step): the eigenvectors of the molecule's previous forward on this plan start
+        # the first density solve; a fresh single point (P0 None) always starts cold
+        C0 = molecule.__dict__.get("_C_last") if (P0 is not None and self.warm_start) else None
+        if C0 is not None and C0.numel() != plan.mat_total:
+            C0 = None
         F, Eelec, notconv, n_iter, Clast = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
-                                                         warm_start=self.warm_start, want_C=True)  # fmt: skip
+                                                         warm_start=self.warm_start, want_C=True, C0=C0)  # fmt: skip
+        molecule.__dict__["_C_last"] = Clast
         molecule.n_scf_iter = n_iter
         if molecule.verbose:
             tag = {0: "scf direct step  ", 1: "scf adaptive step    ", 2: "scf pulay diis   "}[self.scf_converger[0]]

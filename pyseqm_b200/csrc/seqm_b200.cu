@@ -721,7 +721,7 @@ static int* g_h_nnot = g_h_nnot_emu;
 
 static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, const ScfWork& W0, const double* H,
                               const double* w, double* P, double* F, int32_t* notconverged, cudaStream_t st,
-                              int* n_iter) {
+                              int* n_iter, bool have_guess) {
   int rc = SEQM_OK;
   const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
   int nh = (o->pipeline == 1) ? 1 : ((o->pipeline == 2 || b->nmol >= 256) ? 2 : 1);
@@ -802,7 +802,7 @@ static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, c
         CHKP("sp2_kernel");
       } else {
         PROF(PK_JACOBI, s, rc = launch_jacobi(&B, F, W.Pnew, (double*)nullptr, W.C,
-                                              (o->warm_start && k > 0) ? (const double*)W.C : (const double*)nullptr, W.active, s, h));
+                                              (o->warm_start && (k > 0 || have_guess)) ? (const double*)W.C : (const double*)nullptr, W.active, s, h));
         if (rc) return rc;
       }
       PROF(PK_MIX, s, SEQM_LAUNCH(mix_linear_kernel, B.nmol, 256, 0, s, B, W, P, -1.0));
@@ -899,9 +899,22 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   int counter = -1, cF = 0;
   int nnot = b->nmol;
   int printed = 0;
+  // warm_start == 2: C_last holds, on entry, eigenvectors to start the FIRST density solve from (a restart from a
+  // nearby geometry: MD steps, geometry optimisation); they must belong to the same batch layout
+  if (o->warm_start == 2 && C_last && !o->use_sp2 && !large) {
+#ifndef SEQM_HOSTEMU
+    if (cudaMemcpyAsync(W.C, C_last, sizeof(double) * (size_t)b->mat_total, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      seqm_set_error("seqm_scf: initial eigenvector copy failed");
+      return SEQM_ERR_CUDA;
+    }
+#else
+    memcpy(W.C, C_last, sizeof(double) * (size_t)b->mat_total);
+#endif
+    have_C = 1;
+  }
   const bool pipelined = (o->converger == 2) && !large;
   if (pipelined) {
-    rc = scf_diis_pipelined(b, o, W, H, w, P, F, notconverged, st, &printed);
+    rc = scf_diis_pipelined(b, o, W, H, w, P, F, notconverged, st, &printed, have_C != 0);
     if (rc) return rc;
     have_C = o->use_sp2 ? 0 : 1;
   }

@@ -340,8 +340,9 @@ def op_initial_density(plan):
     return P
 
 
-def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_start=True, want_C=False):
-    """Runs the SCF loop; P (packed) is updated in place.  Returns (F, Eelec, notconverged, n_iter)."""
+def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_start=True, want_C=False, C0=None):
+    """Runs the SCF loop; P (packed) is updated in place.  Returns (F, Eelec, notconverged, n_iter[, C]).
+    C0: packed eigenvectors of a nearby problem on the same plan; the first density solve starts from them."""
     o = SeqmScfOpts()
     o.eps = float(eps)
     o.converger = int(converger[0])
@@ -349,7 +350,7 @@ def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_star
     o.use_sp2 = 1 if sp2[0] else 0
     o.sp2_eps = float(sp2[1]) if sp2[0] else 0.0
     o.max_iter = int(max_iter)
-    o.warm_start = 1 if warm_start else 0
+    o.warm_start = (2 if (C0 is not None and want_C and not sp2[0]) else 1) if warm_start else 0
     o.pipeline = int(os.environ.get("SEQM_B200_PIPELINE", "0"))  # 0 auto, 1 single stream, 2 two half-batches
     nbytes = plan.lib.dll.seqm_scf_workspace_bytes(plan.ref, C.byref(o))
     if nbytes < 0:
@@ -360,6 +361,8 @@ def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_star
     nc = torch.ones(plan.nmol, dtype=torch.int32, device=plan.device)
     nit = C.c_int32(0)
     Clast = plan.new_mat() if (want_C and not sp2[0]) else None
+    if o.warm_start == 2:
+        Clast.copy_(C0)
     plan.lib.check(
         plan.lib.dll.seqm_scf(plan.ref, C.byref(o), ptr(H), ptr(w), ptr(P), ptr(F), ptr(E), ptr(nc), ptr(ws),
                               C.byref(nit), ptr(Clast), stream_of(P)),
