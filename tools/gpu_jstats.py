@@ -21,5 +21,5 @@ def timed(fn):
 for it in range(6):
     (e, P1, C1), ms = timed(lambda: engine.op_eig_density(plan, F, want_C=True, Cguess=(C1 if it else None)))
     st = lib.jacobi_stats()
-    print(f"iter {it}: {ms:.3f} ms  sweeps/mol {st['sweeps']/st['molecules']:.2f} rot-steps/mol {st['rotation_steps']/st['molecules']:.1f}  avg n {float(plan.norb.double().mean()):.1f}")
+    print(f"iter {it}: {ms:.3f} ms  sweeps/mol {st['sweeps']/st['molecules']:.2f} first-order finishes {st['first_order_finishes']/st['molecules']:.2f}  avg n {float(plan.norb.double().mean()):.1f}")
     F = engine.op_fock(plan, 0.5*P + 0.5*P1 if it == 0 else P1, H, w); P = P1
