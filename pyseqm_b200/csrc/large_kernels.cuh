@@ -95,6 +95,102 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) dgemm_kernel(int M, int N, int K, const
 #endif
 }
 
+// FP64 tensor-core variant: C = A B with mma.sync.m8n8k4.f64 (DMMA).  B200's DMMA rate equals its DFMA rate (37 vs
+// 34-36 TFLOP/s measured, tools/probes/dmma_peak.cu), but one DMMA retires 256 FMAs per issue slot instead of 32, so
+// the issue ports are free for the shared-memory fragment loads and the pipe can actually be kept full.
+// 128x128x16 CTA tile, 8 warps as 2 (m) x 4 (n), each warp 64x32 = 8x4 DMMA tiles with the accumulators in registers;
+// fragments are read straight from padded shared tiles (row strides 20 and 132 doubles: the 16 lanes of a wavefront
+// hit 16 distinct 8-byte banks); global -> register -> shared double buffering as in dgemm_kernel (74.8 KB dynamic).
+#define SEQM_DMMA_BK 16
+#define SEQM_DMMA_SMEM (2 * (128 * (SEQM_DMMA_BK + 4) + SEQM_DMMA_BK * 132) * sizeof(double))
+#ifndef SEQM_HOSTEMU
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) dgemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
+                                                            const double* __restrict__ B, int ldb, double* __restrict__ C, int ldc) {
+  constexpr int BM = 128, BN = 128, BK = SEQM_DMMA_BK, LDA = BK + 4, LDB = BN + 4;
+  SEQM_DYN_SMEM(double, dsm);
+  double* const sA0 = dsm;                 // [2][m][k]
+  double* const sB0 = dsm + 2 * BM * LDA;  // [2][k][n]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;
+  const int nbx = (N + BN - 1) / BN;
+  const int bm = (blockIdx.x / nbx) * BM, bn = (blockIdx.x % nbx) * BN;
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  constexpr int NQ = BK / 2;  // doubles per thread per matrix and stage
+  double ra[NQ], rb[NQ];
+  const int a_row = tid >> 1, a_col = (tid & 1) * NQ;  // NQ consecutive k of one A row
+  const int b_row0 = tid >> 5, b_col = (tid & 31) * 4;  // 4 consecutive columns of rows b_row0, b_row0 + 8, ...
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int r = bm + a_row, c = k0 + a_col + q;
+      ra[q] = (r < M && c < K) ? A[(long long)r * lda + c] : 0.0;
+      const int rr = k0 + b_row0 + 8 * (q >> 2), cc = bn + b_col + (q & 3);
+      rb[q] = (rr < K && cc < N) ? B[(long long)rr * ldb + cc] : 0.0;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      sA0[buf * BM * LDA + a_row * LDA + a_col + q] = ra[q];
+      sB0[buf * BK * LDB + (b_row0 + 8 * (q >> 2)) * LDB + b_col + (q & 3)] = rb[q];
+    }
+  };
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = (k0 + BK) < K;
+    if (more) load_tiles(k0 + BK);
+    const double* pa = sA0 + buf * BM * LDA + (wm + g) * LDA + t;
+    const double* pb = sB0 + buf * BK * LDB + t * LDB + wn + g;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = pa[i * 8 * LDA + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = pb[kk * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = bm + wm + i * 8 + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = bn + wn + j * 8 + 2 * t;
+      if (c + 1 < N) {
+        double2 v2;
+        v2.x = acc[i][j][0];
+        v2.y = acc[i][j][1];
+        if (((((long long)r * ldc + c) & 1) == 0)) *reinterpret_cast<double2*>(C + (long long)r * ldc + c) = v2;
+        else { C[(long long)r * ldc + c] = v2.x; C[(long long)r * ldc + c + 1] = v2.y; }
+      } else if (c < N) {
+        C[(long long)r * ldc + c] = acc[i][j][0];
+      }
+    }
+  }
+}
+#endif
+
 // ---- Fock build with everything in global memory -------------------------------------------------------
 // off-diagonal blocks: one work item per (pair, mu, lambda)
 SEQM_GLOBAL void fock_large_offdiag_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,

@@ -65,6 +65,7 @@ static int ensure_device() {
     e = cudaFuncSetAttribute(jacobi_fixed_kernel<NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JacobiCfg<NPV>::SMEM);
   SEQM_JACOBI_CLASSES(SEQM_ATTR)
 #undef SEQM_ATTR
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQM_DMMA_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
@@ -135,6 +136,13 @@ static int fetch_host_ints(const int32_t* dev, int32_t* host, int n, cudaStream_
 }
 static int launch_gemm(int n, const double* A, const double* B, double* C, cudaStream_t st) {
   const int nb = (n + SEQM_GEMM_BM - 1) / SEQM_GEMM_BM;
+#ifndef SEQM_HOSTEMU
+  static const int use_fma = getenv("SEQM_B200_GEMM_FMA") ? 1 : 0;  // experiments: the register-tiled DFMA kernel
+  if (!use_fma) {
+    PROF(PK_GEMM, st, SEQM_LAUNCH(dgemm_dmma_kernel, nb * nb, 256, SEQM_DMMA_SMEM, st, n, n, n, A, n, B, n, C, n));
+    return seqm_check_launch("dgemm_dmma_kernel");
+  }
+#endif
   PROF(PK_GEMM, st, SEQM_LAUNCH(dgemm_kernel, nb * nb, 256, 0, st, n, n, n, A, n, B, n, C, n));
   return seqm_check_launch("dgemm_kernel");
 }
