@@ -78,7 +78,9 @@ struct JacobiCfg {
   // resident CTAs per SM the register allocation is asked to allow (occupancy of a barrier/latency-bound kernel)
   static constexpr int MINBLOCKS = NP == 16 ? SEQM_JB16 : NP == 20 ? SEQM_JB20 : NP == 24 ? SEQM_JB24
                                    : NP == 28 ? SEQM_JB28 : NP == 32 ? SEQM_JB32 : 0;
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)M * LD + 2 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
+  static constexpr int LDT = M + ((M % 16 == 0) ? 4 : 12);  // staging stride of the tensor-core products: 4 mod 16
+  static constexpr int AREG = M * (LD > LDT ? LD : LDT);    // doubles reserved for A (also holds the staging tile)
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)AREG + 2 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
 };
 
 // element (r, c) of the plane-split matrix
@@ -112,6 +114,16 @@ SEQM_HD void jacobi_tile_offsets(int k, int l, int* oe, int* oo) {
   }
 }
 
+#ifndef SEQM_HOSTEMU
+// one FP64 tensor-core step: the 8x8 accumulator tile (c0, c1 = row lane/4, columns 2 (lane%4) + {0,1}) gains
+// A(8x4) B(4x8) with a = A[lane/4][lane%4], b = B[lane%4][lane/4]
+SEQM_D void seqm_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+#endif
+
 template <int NP>
 SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINBLOCKS) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
                                      double* __restrict__ evals, double* __restrict__ Cout,
@@ -124,7 +136,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   const int n = v.n;
   SEQM_DYN_SMEM(double, sm);
   double* A = sm;
-  seqm_d2* cs = reinterpret_cast<seqm_d2*>(A + M * LD);
+  seqm_d2* cs = reinterpret_cast<seqm_d2*>(A + K::AREG);
   double* scr = reinterpret_cast<double*>(cs + NP);
   double* dg = scr + 40;
   int* perm = reinterpret_cast<int*>(dg + M);
@@ -145,6 +157,74 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     const double* C0 = Cguess + v.mat0;
     double* G = Pout + v.mat0;
     double* G2 = Cout + v.mat0;
+#ifndef SEQM_HOSTEMU
+    // FP64 tensor cores (DMMA 8x8x4 tiles, one warp per output tile): C0 zero-padded to a multiple of 8 in shared
+    // memory with a row stride of 4 mod 16 (conflict-free fragment loads), F fragments straight from global / L1
+    {
+      constexpr int LDT = K::LDT;
+      const int np8 = (n + 7) & ~7, nt8 = np8 >> 3;
+      double* S = A;
+      for (int t = tid; t < np8 * LDT; t += nthr) {
+        const int r = t / LDT, c = t - r * LDT;
+        S[t] = (r < n && c < n) ? C0[r * n + c] : 0.0;
+      }
+      SEQM_SYNC();
+#pragma unroll
+      for (int e = 0; e < SEG; ++e) {
+        const int c = vseg * SEG + e;
+        vr[e] = (vrow < n && c < n) ? S[vrow * LDT + c] : ((vrow == c) ? 1.0 : 0.0);
+      }
+      const int warp = tid >> 5, nwarps = nthr >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+      // T = F C0 -> G
+      for (int tile = warp; tile < nt8 * nt8; tile += nwarps) {
+        const int m0 = (tile / nt8) * 8, n0 = (tile % nt8) * 8;
+        const int fr = m0 + g;
+        const double* frow = Fm + fr * n;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < np8; k0 += 16) {
+          double af[4], bf[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kc = k0 + 4 * u + t4;
+            af[u] = (fr < n && kc < n) ? frow[kc] : 0.0;
+            bf[u] = (kc < np8) ? S[kc * LDT + n0 + g] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) seqm_dmma(c0, c1, af[u], bf[u]);
+        }
+        const int r = m0 + g, c = n0 + 2 * t4;
+        if (r < n) {
+          if (c < n) G[r * n + c] = c0;
+          if (c + 1 < n) G[r * n + c + 1] = c1;
+        }
+      }
+      SEQM_SYNC();
+      // upper tiles of C0^t T -> G2 (tile (mi, nj >= mi); a diagonal tile is written in full)
+      const int ntri = nt8 * (nt8 + 1) / 2;
+      for (int tile = warp; tile < ntri; tile += nwarps) {
+        int mi = 0, rem = tile;
+        while (rem >= nt8 - mi) { rem -= nt8 - mi; ++mi; }
+        const int m0 = mi * 8, n0 = (mi + rem) * 8;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < np8; k0 += 16) {
+          double af[4], bf[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int kc = k0 + 4 * u + t4;
+            af[u] = (kc < np8) ? S[kc * LDT + m0 + g] : 0.0;  // C0^t[m][k] = C0[k][m]
+            bf[u] = (kc < n && n0 + g < n) ? G[kc * n + n0 + g] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) seqm_dmma(c0, c1, af[u], bf[u]);
+        }
+        const int r = m0 + g, c = n0 + 2 * t4;
+        if (r < n) {
+          if (c < n) G2[r * n + c] = c0;
+          if (c + 1 < n) G2[r * n + c + 1] = c1;
+        }
+      }
+    }
+#else
     double* S = A;  // C0 staged in shared memory, standard layout, row stride n
     for (int t = tid; t < n * n; t += nthr) S[t] = C0[t];
     SEQM_SYNC();
@@ -203,6 +283,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         if (i1 != i && bj > bi) G2[i1 * n + j] = a10;
       }
     }
+#endif
     SEQM_SYNC();
     for (int t = tid; t < M * M; t += nthr) {
       const int i = t / M, j = t - i * M;
@@ -428,9 +509,11 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   }
   double* V = A;
 #ifndef SEQM_HOSTEMU
+  constexpr int LV = K::LDT;  // row stride 4 mod 16: conflict-free tensor-core fragment loads
 #pragma unroll
-  for (int e = 0; e < SEG; ++e) V[vrow * M + vseg * SEG + e] = vr[e];
+  for (int e = 0; e < SEG; ++e) V[vrow * LV + vseg * SEG + e] = vr[e];
 #else
+  constexpr int LV = M;
   for (int t = 0; t < M * M; ++t) V[t] = Vh[t];
 #endif
   SEQM_SYNC();
@@ -438,15 +521,68 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     for (int r = tid; r < b.nmax; r += nthr) evals[(long long)mol * b.nmax + r] = (r < n) ? dg[perm[r]] : 0.0;
   if (Cout) {
     double* Cm = Cout + v.mat0;
-    for (int t = tid; t < n * n; t += nthr) Cm[t] = V[(t / n) * M + perm[t % n]];
+    for (int t = tid; t < n * n; t += nthr) Cm[t] = V[(t / n) * LV + perm[t % n]];
   }
+#ifndef SEQM_HOSTEMU
+  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3;
+  const int warp = tid >> 5, nwarps = nthr >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  if (pert) {
+    SEQM_SYNC();  // Cout took the uncorrected vectors
+    // C_occ += C_virt X on the tensor cores: tile (8 rows) x (8 occupied columns), k over the virtual columns
+    const int no = v.nocc, nto = (no + 7) >> 3;
+    for (int tile = warp; tile < nt8 * nto; tile += nwarps) {
+      const int i0 = (tile / nto) * 8, r0 = (tile % nto) * 8;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k0 = 0; k0 < nv; k0 += 4) {
+        const int q = k0 + t4;
+        const double a = (q < nv) ? V[(i0 + g) * LV + perm[no + q]] : 0.0;
+        const double bq = (q < nv && r0 + g < no) ? Xg[q * no + r0 + g] : 0.0;
+        seqm_dmma(c0, c1, a, bq);
+      }
+      const int row = i0 + g, r = r0 + 2 * t4;
+      if (row < n) {
+        if (r < no) V[row * LV + perm[r]] += c0;
+        if (r + 1 < no) V[row * LV + perm[r + 1]] += c1;
+      }
+    }
+    SEQM_SYNC();
+  }
+  if (Pout) {
+    // P = 2 C_occ C_occ^t on the tensor cores, upper tiles mirrored
+    double* Pm = Pout + v.mat0;
+    const int no = v.nocc;
+    const int ntri = nt8 * (nt8 + 1) / 2;
+    for (int tile = warp; tile < ntri; tile += nwarps) {
+      int mi = 0, rem = tile;
+      while (rem >= nt8 - mi) { rem -= nt8 - mi; ++mi; }
+      const int i0 = mi * 8, j0 = (mi + rem) * 8;
+      const double* va = V + (i0 + g) * LV;
+      const double* vb = V + (j0 + g) * LV;
+      double c0 = 0.0, c1 = 0.0;
+      for (int k0 = 0; k0 < no; k0 += 4) {
+        const int r = k0 + t4;
+        const int col = (r < no) ? perm[r] : 0;
+        const double a = (r < no) ? va[col] : 0.0;
+        const double bq = (r < no) ? vb[col] : 0.0;
+        seqm_dmma(c0, c1, a, bq);
+      }
+      c0 *= 2.0;
+      c1 *= 2.0;
+      const int row = i0 + g, c = j0 + 2 * t4;
+      if (row < n) {
+        if (c < n) { Pm[row * n + c] = c0; Pm[c * n + row] = c0; }
+        if (c + 1 < n) { Pm[row * n + c + 1] = c1; Pm[(c + 1) * n + row] = c1; }
+      }
+    }
+  }
+#else
   if (pert) {
     SEQM_SYNC();  // Cout took the uncorrected vectors
     for (int t = tid; t < n * v.nocc; t += nthr) {
       const int row = t / v.nocc, r = t - row * v.nocc;
       double sacc = 0.0;
-      for (int q = 0; q < nv; ++q) sacc += V[row * M + perm[v.nocc + q]] * Xg[q * v.nocc + r];
-      V[row * M + perm[r]] += sacc;
+      for (int q = 0; q < nv; ++q) sacc += V[row * LV + perm[v.nocc + q]] * Xg[q * v.nocc + r];
+      V[row * LV + perm[r]] += sacc;
     }
     SEQM_SYNC();
   }
@@ -462,7 +598,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
       double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
       for (int r = 0; r < nocc; ++r) {
         const int c = perm[r];
-        const double x0 = V[i * M + c], x1 = V[i1 * M + c], y0 = V[j * M + c], y1 = V[j1 * M + c];
+        const double x0 = V[i * LV + c], x1 = V[i1 * LV + c], y0 = V[j * LV + c], y1 = V[j1 * LV + c];
         a00 += x0 * y0;
         a01 += x0 * y1;
         a10 += x1 * y0;
@@ -479,6 +615,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
       }
     }
   }
+#endif
   if (tid == 0) {
     const long long clk3 = SEQM_CLOCK();
     stat_add(4, (unsigned long long)(clk1 - clk0));
