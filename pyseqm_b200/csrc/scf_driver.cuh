@@ -159,10 +159,58 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
   const MolView v = mol_view(b, mol);
   const int n = v.n, nn = n * n;
   SEQM_DYN_SMEM(double, sm);
-  double* sF = sm;
-  double* sP = sm + nn;
   const long long h0 = v.mat0 * SEQM_NFOCK;  // this molecule's history block: [slot][n*n]
   double* Fh = W.FOCK + h0 + (long long)counter * nn;
+  double* Rh = W.RES + h0 + (long long)counter * nn;
+  double dots[SEQM_NFOCK];
+  for (int j = 0; j < SEQM_NFOCK; ++j) dots[j] = 0.0;
+  double rmax = 0.0;
+#ifndef SEQM_HOSTEMU
+  // R = F P - P F on the FP64 tensor cores: F and P zero-padded to a multiple of 8 in shared memory (row stride
+  // 4 mod 16), one warp per upper 8x8 tile with two accumulators (F P and P F); R is antisymmetric
+  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, ld = np8 + ((np8 & 8) ? 12 : 4);
+  double* sF = sm;
+  double* sP = sm + np8 * ld;
+  for (int t = threadIdx.x; t < np8 * ld; t += blockDim.x) {
+    const int r = t / ld, c = t - r * ld;
+    const bool in = (r < n && c < n);
+    const double f = in ? F[v.mat0 + r * n + c] : 0.0;
+    sF[t] = f;
+    sP[t] = in ? P[v.mat0 + r * n + c] : 0.0;
+    if (in) Fh[r * n + c] = f;
+  }
+  SEQM_SYNC();
+  {
+    const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int ntri = nt8 * (nt8 + 1) / 2;
+    for (int tile = warp; tile < ntri; tile += nwarps) {
+      int mi = 0, rem = tile;
+      while (rem >= nt8 - mi) { rem -= nt8 - mi; ++mi; }
+      const int i0 = mi * 8, j0 = (mi + rem) * 8;
+      double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+      for (int k0 = 0; k0 < np8; k0 += 4) {
+        const int ka = (i0 + g) * ld + k0 + t4, kb = (k0 + t4) * ld + j0 + g;
+        seqm_dmma(x0, x1, sF[ka], sP[kb]);
+        seqm_dmma(y0, y1, sP[ka], sF[kb]);
+      }
+      const int a = i0 + g;
+      const double rv[2] = {x0 - y0, x1 - y1};
+      for (int e = 0; e < 2; ++e) {
+        const int c = j0 + 2 * t4 + e;
+        if (a >= n || c >= n || c <= a) continue;
+        const double sv = rv[e];
+        Rh[a * n + c] = sv;
+        Rh[c * n + a] = -sv;
+        rmax = fmax(rmax, fabs(sv));
+        for (int q = 0; q < cF; ++q)
+          dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + a * n + c]);
+      }
+    }
+  }
+#else
+  double* sF = sm;
+  double* sP = sm + nn;
+
   for (int t = threadIdx.x; t < nn; t += blockDim.x) {
     const double f = F[v.mat0 + t];
     sF[t] = f;
@@ -170,10 +218,6 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
     Fh[t] = f;
   }
   SEQM_SYNC();
-  double* Rh = W.RES + h0 + (long long)counter * nn;
-  double dots[SEQM_NFOCK];
-  for (int j = 0; j < SEQM_NFOCK; ++j) dots[j] = 0.0;
-  double rmax = 0.0;
   // R = F P - P F on the strict upper triangle (R is antisymmetric), 2x2 register blocks
   const int nb = (n + 1) >> 1;
   for (int t = threadIdx.x; t < nb * nb; t += blockDim.x) {
@@ -206,6 +250,7 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
         dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + a * n + c]);
     }
   }
+#endif
   for (int t = threadIdx.x; t < n; t += blockDim.x) Rh[t * n + t] = 0.0;
   rmax = block_max(rmax, red);
   double* E = W.EMAT + (long long)mol * SEQM_EM * SEQM_EM;

@@ -727,6 +727,12 @@ static int g_h_nnot_emu[4];
 static int* g_h_nnot = g_h_nnot_emu;
 #endif
 
+// F and P of one molecule, zero-padded to a multiple of 8 with a row stride of 4 mod 16 (tensor-core fragments)
+static size_t diis_store_smem(int nmax) {
+  const size_t np8 = ((size_t)nmax + 7) & ~(size_t)7;
+  return sizeof(double) * 2 * np8 * (np8 + 12);
+}
+
 static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, const ScfWork& W0, const double* H,
                               const double* w, double* P, double* F, int32_t* notconverged, cudaStream_t st,
                               int* n_iter, bool have_guess) {
@@ -791,7 +797,7 @@ static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, c
 #endif
       SEQM_LAUNCH(diis_begin_kernel, gm, 128, 0, s, B, W, k, h);
       CHKP("diis_begin_kernel");
-      PROF(PK_DIIS_STORE, s, SEQM_LAUNCH(diis_store_kernel, B.nmol, nt, 2 * sm1, s, B, W, (const double*)F, (const double*)P, -1, -1));
+      PROF(PK_DIIS_STORE, s, SEQM_LAUNCH(diis_store_kernel, B.nmol, nt, diis_store_smem(b->nmax), s, B, W, (const double*)F, (const double*)P, -1, -1));
       CHKP("diis_store_kernel");
       PROF(PK_DIIS_SOLVE, s, SEQM_LAUNCH(diis_solve_kernel, diis_grid(B.nmol), 32 * SEQM_DIIS_WARPS, 0, s, B, W, -1, -1,
                                          W0.rflag + 2 * h + (k & 1)));
@@ -937,7 +943,7 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       cF = (cF < SEQM_NFOCK) ? cF + 1 : SEQM_NFOCK;
       counter = (counter + 1) % SEQM_NFOCK;
       if (!large) {
-        PROF(PK_DIIS_STORE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, 2 * sm1, st, *b, W, F, P, counter, cF));
+        PROF(PK_DIIS_STORE, SEQM_STREAM(stream), SEQM_LAUNCH(diis_store_kernel, b->nmol, nt, diis_store_smem(b->nmax), st, *b, W, F, P, counter, cF));
         CHK("diis_store_kernel");
       } else {
         for (int m = 0; m < b->nmol; ++m) {
