@@ -643,12 +643,95 @@ SEQM_GLOBAL void sp2_kernel(seqm_batch_t b, const double* __restrict__ F, double
   const MolView v = mol_view(b, mol);
   const int n = v.n;
   SEQM_DYN_SMEM(double, sm);
-  double* X = sm;
-  double* X2 = X + n * n;
-  double* scr = X2 + n * n;  // 40 doubles
   const double* Fm = F + v.mat0;
   if (eps > 1.0e-3) eps = 1.0e-3;
   if (eps < 1.0e-7) eps = 1.0e-7;
+#ifndef SEQM_HOSTEMU
+  // X^2 on the FP64 tensor cores.  X lives zero-padded to a multiple of 8 in shared memory (row stride 4 mod 16);
+  // every warp owns up to 8 upper 8x8 tiles of X^2, keeps them in its DMMA accumulators until all warps are done
+  // reading X, then writes X^2 or 2X - X^2 back in place (mirrored): one matrix buffer, no X^2 buffer.
+  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, ld = np8 + ((np8 & 8) ? 12 : 4);
+  double* X = sm;
+  double* scr = X + np8 * ld;  // 40 doubles
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, nwarps = nthr >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  double lo = 1.0e300, hi = -1.0e300;
+  for (int i = tid; i < n; i += nthr) {
+    double r = 0.0;
+    for (int j = 0; j < n; ++j) r += fabs(Fm[i * n + j]);
+    const double aii = Fm[i * n + i];
+    r -= fabs(aii);
+    lo = fmin(lo, aii - r);
+    hi = fmax(hi, aii + r);
+  }
+  const double hN = block_max(hi, scr);
+  const double h1 = -block_max(-lo, scr);
+  for (int t = tid; t < np8 * ld; t += nthr) {
+    const int r = t / ld, c = t - r * ld;
+    X[t] = (r < n && c < n) ? (((r == c) ? hN : 0.0) - Fm[r * n + c]) / (hN - h1) : 0.0;
+  }
+  SEQM_SYNC();
+  const double nocc = (double)v.nocc;
+  double tr = 0.0;
+  for (int i = tid; i < n; i += nthr) tr += X[i * ld + i];
+  tr = block_sum(tr, scr);
+  double errm0 = fabs(tr - nocc), errm1 = errm0;
+  const int ntri = nt8 * (nt8 + 1) / 2;
+  int k = 0;
+  for (;;) {
+    double acc[8][2];
+    double t2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      acc[q][0] = acc[q][1] = 0.0;
+      const int tile = warp + q * nwarps;
+      if (tile < ntri) {
+        int mi = 0, rem = tile;
+        while (rem >= nt8 - mi) { rem -= nt8 - mi; ++mi; }
+        const int i0 = mi * 8, j0 = (mi + rem) * 8;
+        const double* xa = X + (i0 + g) * ld + t4;
+        const double* xb = X + t4 * ld + j0 + g;
+        for (int k0 = 0; k0 < np8; k0 += 4) seqm_dmma(acc[q][0], acc[q][1], xa[k0], xb[k0 * ld]);
+        if (i0 == j0) {
+          if (g == 2 * t4) t2 += acc[q][0];
+          if (g == 2 * t4 + 1) t2 += acc[q][1];
+        }
+      }
+    }
+    t2 = block_sum(t2, scr);  // its barriers also guarantee that every warp has finished reading X
+    const bool take_sq = fabs(t2 - nocc) < fabs(2.0 * tr - t2 - nocc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int tile = warp + q * nwarps;
+      if (tile < ntri) {
+        int mi = 0, rem = tile;
+        while (rem >= nt8 - mi) { rem -= nt8 - mi; ++mi; }
+        const int i0 = mi * 8, j0 = (mi + rem) * 8;
+        const int r = i0 + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = j0 + 2 * t4 + e;
+          const double xn = take_sq ? acc[q][e] : 2.0 * X[r * ld + c] - acc[q][e];
+          X[r * ld + c] = xn;
+          if (i0 != j0) X[c * ld + r] = xn;  // a diagonal tile owns both (r,c) and (c,r)
+        }
+      }
+    }
+    SEQM_SYNC();
+    // the reference re-sums the diagonal of the updated matrix; do the same
+    double tr2 = 0.0;
+    for (int i = tid; i < n; i += nthr) tr2 += X[i * ld + i];
+    tr = block_sum(tr2, scr);
+    errm1 = errm0;
+    errm0 = fabs(tr - nocc);
+    ++k;
+    if ((errm0 < eps && errm1 < eps) || k >= 10000) break;
+  }
+  for (int t = tid; t < n * n; t += nthr) Pout[v.mat0 + t] = 2.0 * X[(t / n) * ld + (t % n)];
+#else
+  double* X = sm;
+  double* X2 = X + n * n;
+  double* scr = X2 + n * n;  // 40 doubles
   // Gershgorin bounds
   double lo = 1.0e300, hi = -1.0e300;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -694,5 +777,6 @@ SEQM_GLOBAL void sp2_kernel(seqm_batch_t b, const double* __restrict__ F, double
     if ((errm0 < eps && errm1 < eps) || k >= 10000) break;
   }
   for (int t = threadIdx.x; t < n * n; t += blockDim.x) Pout[v.mat0 + t] = 2.0 * X[t];
+#endif
   if (niter && threadIdx.x == 0) niter[mol] = k;
 }

@@ -526,13 +526,14 @@ int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* 
   return rc;
 }
 
+static size_t sp2_smem(int nmax);
 int seqm_sp2_density(const seqm_batch_t* b, const double* F, double* P, double eps, int32_t* niter, const int32_t* active,
                      void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
   rc = check_small(b, "seqm_sp2_density");
   if (rc) return rc;
-  const size_t smem = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
+  const size_t smem = sp2_smem(b->nmax);
   PROF(PK_SP2, SEQM_STREAM(stream), SEQM_LAUNCH(sp2_kernel, b->nmol, threads_for(b->nmax), smem, SEQM_STREAM(stream), *b, F, P, eps, niter, active));
   return seqm_check_launch("sp2_kernel");
 }
@@ -727,6 +728,15 @@ static int g_h_nnot_emu[4];
 static int* g_h_nnot = g_h_nnot_emu;
 #endif
 
+// in-SM SP2: one zero-padded matrix (row stride 4 mod 16) + 40 scratch doubles; the host emulation keeps X and X^2
+static size_t sp2_smem(int nmax) {
+  const size_t np8 = ((size_t)nmax + 7) & ~(size_t)7;
+#ifndef SEQM_HOSTEMU
+  return sizeof(double) * (np8 * (np8 + 12) + 40);
+#else
+  return sizeof(double) * ((size_t)2 * nmax * nmax + np8 * 12 + 40);
+#endif
+}
 // F and P of one molecule, zero-padded to a multiple of 8 with a row stride of 4 mod 16 (tensor-core fragments)
 static size_t diis_store_smem(int nmax) {
   const size_t np8 = ((size_t)nmax + 7) & ~(size_t)7;
@@ -811,7 +821,7 @@ static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, c
       if (nh == 2) cudaEventRecord(g_ev_enter[h], s);
 #endif
       if (o->use_sp2) {
-        const size_t smsp2 = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
+        const size_t smsp2 = sp2_smem(b->nmax);
         PROF(PK_SP2, s, SEQM_LAUNCH(sp2_kernel, B.nmol, nt, smsp2, s, B, (const double*)F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, (const int32_t*)W.active));
         CHKP("sp2_kernel");
       } else {
@@ -881,7 +891,7 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   cudaStream_t st = SEQM_STREAM(stream);
   const int nt = threads_for(b->nmax);
   const size_t sm1 = sizeof(double) * (size_t)b->nmax * b->nmax;
-  const size_t smsp2 = sizeof(double) * ((size_t)2 * b->nmax * b->nmax + 40);
+  const size_t smsp2 = sp2_smem(b->nmax);
   const int gm = grid1d(b->nmol, 128);
   const int max_iter = o->max_iter > 0 ? o->max_iter : 1000;
 #define CHK(name)                     \

@@ -116,3 +116,28 @@ def test_gpu_xl_bomd_energy_conservation_replicas():
     E = (torch.stack(md.history["Etot"]) + torch.stack(md.history["Ek"])).cpu().numpy()
     assert np.abs(E - E[0]).max() < 5e-2  # the reference's own drift tolerance (tests/unit/test_md_suite.py:232)
     assert np.abs(E[:, 0] - E[:, 1]).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_gpu_xl_bomd_sp2_route_tracks_the_eigensolver_route():
+    """BASELINE configs[2] uses the SP2 density (eps 1e-5) in XL-BOMD; the reference cannot run that combination
+    (xlbomd.py:359), so the route is pinned against this package's eigensolver route, which is itself pinned against
+    the reference trajectories: same start, 30 steps, 16 coronene replicas."""
+    import pyseqm_b200 as seqm
+    from helpers import cuda_lib
+
+    torch.set_default_dtype(torch.float64)
+    dev = torch.device("cuda:0")
+    s, c = seqm.read_xyz([os.path.join(GOLDEN, "xyz", "coronene.xyz")] * 16)
+    out = {}
+    for tag, sp2 in (("eig", [False]), ("sp2", [True, 1.0e-5])):
+        sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2], "sp2": sp2}
+        mol = seqm.Molecule(seqm.Constants().to(dev), sp, torch.as_tensor(c, device=dev), torch.as_tensor(s, device=dev), _lib=cuda_lib())
+        torch.manual_seed(0)
+        md = seqm.XL_BOMD(xl_bomd_params={"k": 6}, seqm_parameters=sp, timestep=0.4, Temp=300.0)
+        md.run(mol, 30)
+        E = (torch.stack(md.history["Etot"]) + torch.stack(md.history["Ek"])).cpu().numpy()
+        out[tag] = (E, mol.coordinates.detach().cpu().numpy().copy())
+        assert np.abs(E - E[0]).max() < 5e-2
+    assert np.abs(out["eig"][0] - out["sp2"][0]).max() < 2e-3   # total energy along the trajectory, eV
+    assert np.abs(out["eig"][1] - out["sp2"][1]).max() < 1e-4   # final coordinates, Angstrom
