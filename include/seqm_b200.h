@@ -159,6 +159,11 @@ int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* 
 int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* pair_scratch, double* grad,
                   void* stream);
 
+/* XL-BOMD field propagation (MolecularDynamics.py:1418-1435): P_out = kappa [c D + (1-c) P_in] + sum_j coef[j] Pt[j],
+ * and Pt[slot] <- P_out, in one pass.  Pt: (m, total) history of field densities, coef: m device doubles, m <= 16.
+ * P_out may alias P_in. */
+int seqm_xl_propagate(int64_t total, double kappa, double c, const double* D, const double* P_in, double* Pt,
+                      const double* coef, int32_t m, int32_t slot, double* P_out, void* stream);
 /* XL-BOMD (seqm/dynamics/xlbomd.py:73-570, non-KSA branch): shadow electronic energy
  * sum D o F(P) - 1/2 (F(P) - Hcore) o P  (elec_energy_xl, energy.py:76-88) and its nuclear gradient at fixed
  * density D and field P (what ForceXL obtains by autograd through hcore + fock, xlbomd.py:536-551). */

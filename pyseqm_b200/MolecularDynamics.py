@@ -168,10 +168,8 @@ class XL_BOMD(Molecular_Dynamics_Basic):
             # P(n+1) = kappa [c D(n) + (1-c) P(n)] + sum_j coeff_j Pt[j]    (c = 0.95; eq. 22 of the paper)
             cindx = step % self.m
             c = 0.95
-            P = self.coeff_D * (c * ctx["D"] + (1.0 - c) * ctx["P"]) + torch.sum(
-                self.coeff[cindx : cindx + self.m].reshape(-1, 1) * ctx["Pt"], dim=0
-            )
-            ctx["Pt"][self.m - 1 - cindx] = P
+            P = engine.op_xl_propagate(plan, self.coeff_D, c, ctx["D"], ctx["P"], ctx["Pt"],
+                                       self.coeff[cindx : cindx + self.m].contiguous(), self.m - 1 - cindx)
             ctx["P"] = P
         r = self.esdriver.conservative_force_xl.forward_packed(molecule, P, want_e=False)  # MD needs D, E, forces only
         ctx["D"] = r["D"]

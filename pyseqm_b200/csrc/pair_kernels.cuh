@@ -472,3 +472,19 @@ SEQM_GLOBAL void elec_energy_xl_kernel(seqm_batch_t b, const double* __restrict_
   s = block_sum(s, red);
   if (threadIdx.x == 0) E[v.m] = s;
 }
+
+// XL-BOMD field propagation (MolecularDynamics.py:1418-1435 `_propagate_P`), one pass over the packed buffers:
+//   P(n+1) = kappa [c D + (1 - c) P(n)] + sum_j coef_j Pt_j ;  Pt[slot] <- P(n+1)
+#define SEQM_XL_MAXHIST 16
+SEQM_GLOBAL void xl_propagate_kernel(long long total, double kappa, double c, const double* __restrict__ D,
+                                     const double* __restrict__ Pin, double* __restrict__ Pt, const double* __restrict__ coef,
+                                     int m, int slot, double* __restrict__ Pout) {
+  double cf[SEQM_XL_MAXHIST];
+  for (int j = 0; j < SEQM_XL_MAXHIST; ++j) cf[j] = (j < m) ? coef[j] : 0.0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    double s = kappa * (c * D[t] + (1.0 - c) * Pin[t]);
+    for (int j = 0; j < m; ++j) s += cf[j] * Pt[(long long)j * total + t];
+    Pout[t] = s;
+    Pt[(long long)slot * total + t] = s;
+  }
+}

@@ -625,6 +625,18 @@ int seqm_gradient_xl(const seqm_batch_t* b, const double* xyz, const double* D, 
   PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad));
   return seqm_check_launch("atom_gradient_kernel");
 }
+int seqm_xl_propagate(int64_t total, double kappa, double c, const double* D, const double* P_in, double* Pt,
+                       const double* coef, int32_t m, int32_t slot, double* P_out, void* stream) {
+  int rc = ensure_device();
+  if (rc) return rc;
+  if (m < 1 || m > SEQM_XL_MAXHIST || slot < 0 || slot >= m || total <= 0) {
+    seqm_set_error("seqm_xl_propagate: bad history depth %d / slot %d", m, slot);
+    return SEQM_ERR_ARG;
+  }
+  PROF(PK_OTHER, SEQM_STREAM(stream), SEQM_LAUNCH(xl_propagate_kernel, grid1d(total, 256), 256, 0, SEQM_STREAM(stream), (long long)total,
+                                                  kappa, c, D, P_in, Pt, coef, m, slot, P_out));
+  return seqm_check_launch("xl_propagate_kernel");
+}
 int seqm_elec_energy_xl(const seqm_batch_t* b, const double* D, const double* P, const double* F, const double* H,
                         double* Eelec, void* stream) {
   int rc = check_batch(b);

@@ -313,6 +313,14 @@ def op_elec_energy_xl(plan, D, P, F, H):
     return E
 
 
+def op_xl_propagate(plan, kappa, c, D, P, Pt, coef, slot):
+    """P(n+1) = kappa [c D + (1-c) P] + sum_j coef_j Pt_j, stored into Pt[slot] as well; returns the new field density."""
+    out = torch.empty_like(P)
+    plan.lib.check(plan.lib.dll.seqm_xl_propagate(P.numel(), float(kappa), float(c), ptr(D), ptr(P), ptr(Pt), ptr(coef),
+                                                  Pt.shape[0], int(slot), ptr(out), stream_of(P)), "seqm_xl_propagate")  # fmt: skip
+    return out
+
+
 def op_orbitals_dense(plan, Cm):
     V = torch.empty((plan.nmol, plan.nmax, plan.nmax), dtype=torch.float64, device=plan.device)
     plan.lib.check(plan.lib.dll.seqm_orbitals_dense(plan.ref, ptr(Cm), ptr(V), stream_of(V)), "seqm_orbitals_dense")
