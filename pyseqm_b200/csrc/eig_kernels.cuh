@@ -78,7 +78,7 @@ struct JacobiCfg {
   // resident CTAs per SM the register allocation is asked to allow (occupancy of a barrier/latency-bound kernel)
   static constexpr int MINBLOCKS = NP == 16 ? SEQM_JB16 : NP == 20 ? SEQM_JB20 : NP == 24 ? SEQM_JB24
                                    : NP == 28 ? SEQM_JB28 : NP == 32 ? SEQM_JB32 : 0;
-  static constexpr int LDT = M + ((M % 16 == 0) ? 4 : 12);  // staging stride of the tensor-core products: 4 mod 16
+  static constexpr int LDT = M + 4;  // staging stride of the tensor-core products: 4 or 12 mod 16, conflict-free
   static constexpr int AREG = M * (LD > LDT ? LD : LDT);    // doubles reserved for A (also holds the staging tile)
   static constexpr size_t SMEM = sizeof(double) * ((size_t)AREG + 2 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
 };
@@ -650,7 +650,7 @@ SEQM_GLOBAL void sp2_kernel(seqm_batch_t b, const double* __restrict__ F, double
   // X^2 on the FP64 tensor cores.  X lives zero-padded to a multiple of 8 in shared memory (row stride 4 mod 16);
   // every warp owns up to 8 upper 8x8 tiles of X^2, keeps them in its DMMA accumulators until all warps are done
   // reading X, then writes X^2 or 2X - X^2 back in place (mirrored): one matrix buffer, no X^2 buffer.
-  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, ld = np8 + ((np8 & 8) ? 12 : 4);
+  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, ld = np8 + 4;  // 4 or 12 mod 16: conflict-free fragment loads
   double* X = sm;
   double* scr = X + np8 * ld;  // 40 doubles
   const int tid = threadIdx.x, nthr = blockDim.x;

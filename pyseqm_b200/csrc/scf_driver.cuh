@@ -168,7 +168,8 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
 #ifndef SEQM_HOSTEMU
   // R = F P - P F on the FP64 tensor cores: F and P zero-padded to a multiple of 8 in shared memory (row stride
   // 4 mod 16), one warp per upper 8x8 tile with two accumulators (F P and P F); R is antisymmetric
-  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, ld = np8 + ((np8 & 8) ? 12 : 4);
+  // row stride np8 + 4 is 4 or 12 mod 16 (conflict-free fragments); the largest size class (np8 = 120) only fits unpadded
+  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, ld = (np8 > 112) ? np8 : np8 + 4;
   double* sF = sm;
   double* sP = sm + np8 * ld;
   for (int t = threadIdx.x; t < np8 * ld; t += blockDim.x) {

@@ -744,15 +744,15 @@ static int* g_h_nnot = g_h_nnot_emu;
 static size_t sp2_smem(int nmax) {
   const size_t np8 = ((size_t)nmax + 7) & ~(size_t)7;
 #ifndef SEQM_HOSTEMU
-  return sizeof(double) * (np8 * (np8 + 12) + 40);
+  return sizeof(double) * (np8 * (np8 + 4) + 40);
 #else
-  return sizeof(double) * ((size_t)2 * nmax * nmax + np8 * 12 + 40);
+  return sizeof(double) * ((size_t)2 * nmax * nmax + np8 * 4 + 40);
 #endif
 }
 // F and P of one molecule, zero-padded to a multiple of 8 with a row stride of 4 mod 16 (tensor-core fragments)
 static size_t diis_store_smem(int nmax) {
   const size_t np8 = ((size_t)nmax + 7) & ~(size_t)7;
-  return sizeof(double) * 2 * np8 * (np8 + 12);
+  return sizeof(double) * 2 * np8 * ((np8 > 112) ? np8 : np8 + 4);
 }
 
 static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, const ScfWork& W0, const double* H,

@@ -255,3 +255,39 @@ def check_device_batch_plan(lib, device):
     tab, cols, _ = engine.method_table("AM1")
     assert np.array_equal(plan.parameter("U_ss").cpu().numpy(), tab[:, cols.index("U_ss")].numpy()[Z])
     assert np.array_equal(plan.parameter("zeta_p").cpu().numpy(), tab[:, cols.index("zeta_p")].numpy()[Z])
+
+
+def polyyne(k):
+    """H-(C#C)k-H on the z axis: n = 8k + 2 orbitals (k = 14 -> 114, inside the largest shared-memory size class)."""
+    z, zs = 0.0, []
+    for a in range(2 * k):
+        zs.append(z)
+        z += 1.21 if a % 2 == 0 else 1.37
+    zc = np.array(zs)
+    zh = np.array([zc[0] - 1.06, zc[-1] + 1.06])
+    species = np.array([[6] * (2 * k) + [1, 1]], dtype=np.int64)
+    coords = np.zeros((1, 2 * k + 2, 3))
+    coords[0, : 2 * k, 2] = zc
+    coords[0, 2 * k :, 2] = zh
+    coords[0, :, 0] = 0.01 * np.sin(np.arange(2 * k + 2))  # break the exact linearity a little
+    return species, coords
+
+
+def check_largest_in_sm_class(lib, device):
+    """n = 114 (np8 = 120: the one padded size that only fits shared memory unpadded) against the oracle, eigensolver
+    and SP2 routes."""
+    import seqm_oracle as so
+
+    species, coords = polyyne(14)
+    sp = {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2], "sp2": [False]}
+    ref = so.single_point(species, coords, sp)
+    mol, es = run_molecule(lib, device, species, coords, sp)
+    assert int(mol.norb[0]) == 114 and not bool(es.notconverged.any()) and not ref["notconverged"].any()
+    assert mol.n_scf_iter == ref["n_scf_iter"]
+    assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < TOL_E
+    assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < TOL_DM
+    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F
+    sp2 = dict(sp, sp2=[True, 1.0e-6])
+    mol2, es2 = run_molecule(lib, device, species, coords, sp2)
+    assert not bool(es2.notconverged.any())
+    assert np.abs(mol2.Etot.cpu().numpy() - ref["Etot"]).max() < 1e-3

@@ -190,3 +190,9 @@ def test_device_batch_plan_against_numpy(lib, dev):
     from helpers import check_device_batch_plan
 
     check_device_batch_plan(lib, dev)
+
+
+def test_largest_shared_memory_size_class(lib, dev):
+    from helpers import check_largest_in_sm_class
+
+    check_largest_in_sm_class(lib, dev)

@@ -99,3 +99,9 @@ def test_device_batch_plan_against_numpy(lib):
     from helpers import check_device_batch_plan
 
     check_device_batch_plan(lib, CPU)
+
+
+def test_largest_shared_memory_size_class(lib):
+    from helpers import check_largest_in_sm_class
+
+    check_largest_in_sm_class(lib, CPU)
