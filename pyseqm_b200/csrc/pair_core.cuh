@@ -211,15 +211,24 @@ SEQM_HD LEntry l_entry(int i) {
 // T[KL][kl]: coefficient of the local pair product KL in the molecular pair product kl.
 template <class T>
 SEQM_HD void pair_transform(const T rot[3][3], T Tm[10][10]) {
+#pragma unroll
   for (int i = 0; i < 10; ++i)
+#pragma unroll
     for (int j = 0; j < 10; ++j) Tm[i][j] = T(0.0);
   Tm[0][0] = T(1.0);
+#pragma unroll
   for (int a = 0; a < 3; ++a)
+#pragma unroll
     for (int k = 0; k < 3; ++k) Tm[pack2(a + 1, 0)][pack2(k + 1, 0)] = rot[a][k];
+#pragma unroll
   for (int a = 0; a < 3; ++a)
-    for (int b = 0; b <= a; ++b)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
       for (int k = 0; k < 3; ++k)
-        for (int l = 0; l <= k; ++l) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          if (b > a || l > k) continue;
           T t = rot[a][k] * rot[b][l];
           if (a != b) t = t + rot[b][k] * rot[a][l];
           Tm[pack2(a + 1, b + 1)][pack2(k + 1, l + 1)] = t;
@@ -239,20 +248,30 @@ SEQM_HD void rotate_to_molecular(const T* ri, int nint, const T Tm[10][10], T w[
     return;
   }
   T U[10][10];  // U[KL][mn] = sum_MN L[KL][MN] T[MN][mn]
+#pragma unroll
   for (int i = 0; i < 10; ++i)
-    for (int j = 0; j < nB; ++j) { U[i][j] = T(0.0); w[i][j] = T(0.0); }
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+      if (j < nB) { U[i][j] = T(0.0); w[i][j] = T(0.0); }
+#pragma unroll
   for (int e = 0; e < SEQM_NL; ++e) {
     const LEntry le = l_entry(e);
     if (le.k >= nint || le.mn >= nB) continue;
     const int c = pack_class(le.mn);
-    for (int mn = 0; mn < nB; ++mn)
-      if (pack_class(mn) == c) U[le.kl][mn] = U[le.kl][mn] + ri[le.k] * Tm[le.mn][mn];
+#pragma unroll
+    for (int mn = 0; mn < 10; ++mn)
+      if (mn < nB && pack_class(mn) == c) U[le.kl][mn] = U[le.kl][mn] + ri[le.k] * Tm[le.mn][mn];
   }
-  for (int kl = 0; kl < nA; ++kl) {
+#pragma unroll
+  for (int kl = 0; kl < 10; ++kl) {
+    if (kl >= nA) continue;
     const int c = pack_class(kl);
+#pragma unroll
     for (int KL = 0; KL < 10; ++KL) {
       if (pack_class(KL) != c) continue;
-      for (int mn = 0; mn < nB; ++mn) w[kl][mn] = w[kl][mn] + Tm[KL][kl] * U[KL][mn];
+#pragma unroll
+      for (int mn = 0; mn < 10; ++mn)
+        if (mn < nB) w[kl][mn] = w[kl][mn] + Tm[KL][kl] * U[KL][mn];
     }
   }
 }

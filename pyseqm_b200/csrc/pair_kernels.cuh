@@ -281,6 +281,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
     double Cm[10][10];
     {
       double pa[10], pb[10], da[10], db[10];  // weighted packed diagonal blocks of P and D
+      #pragma unroll
       for (int kl = 0; kl < 10; ++kl) {
         int mu = 0;
         while ((mu + 1) * (mu + 2) / 2 <= kl) ++mu;
@@ -292,14 +293,22 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
         db[kl] = (kl < nB) ? wt * Dm[(oj + mu) * n + oj + nu] : 0.0;
       }
       const double ti = par(b, SEQM_P_TORE, i), tj = par(b, SEQM_P_TORE, j);
+      #pragma unroll
       for (int kl = 0; kl < nA; ++kl)
+        #pragma unroll
         for (int mn = 0; mn < nB; ++mn)
           Cm[kl][mn] = (da[kl] - 0.5 * pa[kl]) * pb[mn] + pa[kl] * (db[mn] - 0.5 * pb[mn]);
+      #pragma unroll
       for (int kl = 0; kl < nA; ++kl) Cm[kl][0] -= tj * da[kl];
+      #pragma unroll
       for (int mn = 0; mn < nB; ++mn) Cm[0][mn] -= ti * db[mn];
+      #pragma unroll
       for (int mu = 0; mu < ni; ++mu)
+        #pragma unroll
         for (int nu = 0; nu < ni; ++nu)
+          #pragma unroll
           for (int la = 0; la < nj; ++la)
+            #pragma unroll
             for (int sg = 0; sg < nj; ++sg)
               Cm[pack2(mu, nu)][pack2(la, sg)] -=
                   (Dm[(oi + mu) * n + oj + la] - 0.5 * Pm[(oi + mu) * n + oj + la]) * Pm[(oi + nu) * n + oj + sg];
@@ -315,41 +324,59 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
       pair_transform(rot, Tm);
       // U2 = T C (rows: local pair index, cols: molecular mn) ; U1 = T C^t
       double U1[10][10], U2[10][10], GT[10][10];
+      #pragma unroll
       for (int a = 0; a < 10; ++a)
+        #pragma unroll
         for (int c = 0; c < 10; ++c) { U1[a][c] = 0.0; U2[a][c] = 0.0; GT[a][c] = 0.0; }
+      #pragma unroll
       for (int KL = 0; KL < nA; ++KL)
+        #pragma unroll
         for (int kl = 0; kl < nA; ++kl) {
           if (cls_of(KL) != cls_of(kl)) continue;
           const double t = Tm[KL][kl];
+          #pragma unroll
           for (int c = 0; c < nB; ++c) U2[KL][c] += t * Cm[kl][c];
         }
+      #pragma unroll
       for (int MN = 0; MN < nB; ++MN)
+        #pragma unroll
         for (int mn = 0; mn < nB; ++mn) {
           if (cls_of(MN) != cls_of(mn)) continue;
           const double t = Tm[MN][mn];
+          #pragma unroll
           for (int c = 0; c < nA; ++c) U1[MN][c] += t * Cm[c][mn];
         }
+      #pragma unroll
       for (int e = 0; e < SEQM_NL; ++e) {
         const LEntry le = l_entry(e);
         if (le.k >= nint || le.mn >= nB) continue;
         const int cK = cls_of(le.kl), cM = cls_of(le.mn);
         double cl = 0.0;  // (T C T^t)[KL][MN]
+        #pragma unroll
         for (int c = 0; c < nB; ++c)
           if (cls_of(c) == cM) cl += U2[le.kl][c] * Tm[le.mn][c];
         dEdr += cl * ri[le.k].d;
         const double lv = ri[le.k].v;
+        #pragma unroll
         for (int c = 0; c < nA; ++c)
           if (cls_of(c) == cK) GT[le.kl][c] += lv * U1[le.mn][c];
+        #pragma unroll
         for (int c = 0; c < nB; ++c)
           if (cls_of(c) == cM) GT[le.mn][c] += lv * U2[le.kl][c];
       }
       // dE/drot from dE/dT
       double Gr[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      #pragma unroll
       for (int a = 0; a < 3; ++a)
+        #pragma unroll
         for (int k = 0; k < 3; ++k) Gr[a][k] += GT[pack2(a + 1, 0)][pack2(k + 1, 0)];
+      #pragma unroll
       for (int a = 0; a < 3; ++a)
+        #pragma unroll
         for (int c = 0; c <= a; ++c)
+          #pragma unroll
           for (int k = 0; k < 3; ++k)
+            #pragma unroll
             for (int l = 0; l <= k; ++l) {
               const double gt = GT[pack2(a + 1, c + 1)][pack2(k + 1, l + 1)];
               Gr[a][k] += gt * rot[c][l];
@@ -363,7 +390,9 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
       Dual3 vd[3] = {Dual3(vdir[0], 1.0, 0.0, 0.0), Dual3(vdir[1], 0.0, 1.0, 0.0), Dual3(vdir[2], 0.0, 0.0, 1.0)};
       Dual3 rd[3][3];
       rotation_rows(vd, rd);
+      #pragma unroll
       for (int a = 0; a < 3; ++a)
+        #pragma unroll
         for (int k = 0; k < 3; ++k) {
           dEde[0] -= Gr[a][k] * rd[a][k].d0;
           dEde[1] -= Gr[a][k] * rd[a][k].d1;
