@@ -114,6 +114,10 @@ SEQM_HD void jacobi_tile_offsets(int k, int l, int* oe, int* oo) {
   }
 }
 
+// Optional fused DIIS mixing (scf_loop.py:1045-1056) at the end of the density solve: Pold <- P ;
+// P <- a P + (1 - a) Pnew with a = 0.5 until two Fock matrices are stored (*cF < 2), else 0.
+struct JacobiMix { double* P; double* Pold; const int* cF; };
+
 #ifndef SEQM_HOSTEMU
 // one FP64 tensor-core step: the 8x8 accumulator tile (c0, c1 = row lane/4, columns 2 (lane%4) + {0,1}) gains
 // A(8x4) B(4x8) with a = A[lane/4][lane%4], b = B[lane%4][lane/4]
@@ -127,7 +131,8 @@ SEQM_D void seqm_dmma(double& c0, double& c1, double a, double b) {
 template <int NP>
 SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINBLOCKS) jacobi_fixed_kernel(seqm_batch_t b, int first, const double* __restrict__ F, double* __restrict__ Pout,
                                      double* __restrict__ evals, double* __restrict__ Cout,
-                                     const double* __restrict__ Cguess, const int32_t* __restrict__ active) {
+                                     const double* __restrict__ Cguess, const int32_t* __restrict__ active,
+                                     JacobiMix mix) {
   typedef JacobiCfg<NP> K;
   constexpr int M = K::M, LD = K::LD, SEG = K::SEG, SR = K::SR;
   const int mol = b.mol_order[first + blockIdx.x];
@@ -616,6 +621,18 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     }
   }
 #endif
+  if (mix.P && Pout) {
+    SEQM_SYNC();  // the whole new density of this molecule is in Pout (global, L1/L2 resident)
+    const double a = (*mix.cF < 2) ? 0.5 : 0.0, oma = 1.0 - a;
+    const double* Pn = Pout + v.mat0;
+    double* Pc = mix.P + v.mat0;
+    double* Po = mix.Pold + v.mat0;
+    for (int t = tid; t < n * n; t += nthr) {
+      const double p = Pc[t];
+      Po[t] = p;
+      Pc[t] = (a == 0.0) ? Pn[t] : a * p + oma * Pn[t];
+    }
+  }
   if (tid == 0) {
     const long long clk3 = SEQM_CLOCK();
     stat_add(4, (unsigned long long)(clk1 - clk0));

@@ -106,8 +106,22 @@ SEQM_D void tri_decode(int t, int m, int& i, int& j) {  // t-th pair (i<j) of m 
 }
 SEQM_D int tri_index(int i, int j, int m) { return i * (2 * m - i - 1) / 2 + (j - i - 1); }
 
+// Optional tail of the Fock kernel inside the DIIS loop: elec_energy of the new density + get_error
+// (scf_loop.py:106-147) + the update of the active mask, for the molecule this CTA has just finished.
+struct FockErr {
+  int on, use_diis;
+  double eps;
+  const double* Pold;
+  const double* diis_err;
+  double *Eel_run, *Eel_new, *err, *dm_err, *dm_elem;
+  int32_t *notconv, *active_out;
+  int* nnot;
+};
+
 SEQM_GLOBAL void fock_pair_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,
-                                  const double* __restrict__ w, double* __restrict__ F, const int32_t* __restrict__ active) {
+                                  const double* __restrict__ w, double* __restrict__ F, const int32_t* __restrict__ active,
+                                  FockErr fe) {
+  __shared__ double red[33];
   const int m = b.mol_order[blockIdx.x];
   if (active && !active[m]) return;
   const MolView v = mol_view(b, m);
@@ -240,6 +254,39 @@ SEQM_GLOBAL void fock_pair_kernel(seqm_batch_t b, const double* __restrict__ P, 
     const double f = Hm[(oa + mu) * n + oa + nu] + g;
     Fm[(oa + mu) * n + oa + nu] = f;
     Fm[(oa + nu) * n + oa + mu] = f;
+  }
+  if (fe.on) {
+    SEQM_SYNC();  // every element of this molecule's F has been written by this CTA
+    const double* Po = fe.Pold + v.mat0;
+    double e = 0.0, d2 = 0.0, dmax = 0.0;
+    for (int t = tid; t < n * n; t += nthr) {
+      const double p = sP[t];
+      e += p * (Hm[t] + Fm[t]);
+      const double d = p - Po[t];
+      d2 += d * d;
+      dmax = fmax(dmax, fabs(d));
+    }
+    e = 0.5 * block_sum(e, red);
+    d2 = block_sum(d2, red);
+    dmax = block_max(dmax, red);
+    if (tid == 0) {
+      const double err = e - fe.Eel_run[m];
+      fe.err[m] = err;
+      bool bad = fabs(err) > fe.eps;
+      if (fe.use_diis) bad = bad || (fe.diis_err[m] > 50.0 * fe.eps);
+      if (!bad) {
+        fe.dm_err[m] = sqrt(d2) / (double)(4 * nh + 4 * ny);
+        fe.dm_elem[m] = dmax;
+      }
+      const bool nc = bad || (fe.dm_err[m] > 2.0 * fe.eps) || (fe.dm_elem[m] > 15.0 * fe.eps);
+      fe.Eel_new[m] = e;
+      fe.notconv[m] = nc ? 1 : 0;
+      fe.active_out[m] = nc ? 1 : 0;
+      if (nc) {
+        fe.Eel_run[m] = e;
+        seqm_atomic_add(fe.nnot, 1);
+      }
+    }
   }
 }
 static inline size_t fock_pair_smem_bytes(int nmax, int scratch, int threads) {

@@ -184,8 +184,12 @@ static int sp2_large_one(int n, int nocc, const double* Fm, double* Pm, double e
 }
 
 static int threads_for(int nmax);
+// fe: optional get_error tail; *fused tells the caller whether the kernel that ran could carry it
 static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, const double* w, double* F,
-                       const int32_t* active, cudaStream_t st) {
+                       const int32_t* active, cudaStream_t st, const FockErr* fe = nullptr, bool* fused = nullptr) {
+  if (fused) *fused = false;
+  FockErr none;
+  memset(&none, 0, sizeof(none));
   if (b->nmax > SEQM_MAX_ORB) {  // matrices in global memory, grid over all pairs / atoms
     if (b->npairs > 0)
       PROF(PK_FOCK, st, SEQM_LAUNCH(fock_large_offdiag_kernel, grid1d((long long)b->npairs * 16, 256), 256, 0, st, *b, P, H, w, F, active));
@@ -195,7 +199,8 @@ static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, 
   const int nt = threads_for(b->nmax);
   const size_t sm_pair = fock_pair_smem_bytes(b->nmax, b->fock_scratch, nt);
   if (b->fock_scratch > 0 && sm_pair <= (size_t)(g_smem_optin - 2048)) {  // pair-centric: w read once
-    PROF(PK_FOCK, st, SEQM_LAUNCH(fock_pair_kernel, b->nmol, nt, sm_pair, st, *b, P, H, w, F, active));
+    PROF(PK_FOCK, st, SEQM_LAUNCH(fock_pair_kernel, b->nmol, nt, sm_pair, st, *b, P, H, w, F, active, fe ? *fe : none));
+    if (fused) *fused = (fe != nullptr);
     return seqm_check_launch("fock_pair_kernel");
   }
   const size_t smem = sizeof(double) * (size_t)b->nmax * b->nmax;
@@ -243,7 +248,7 @@ static int ensure_class_streams() {
 }
 #endif
 static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const double* Cguess,
-                         const int32_t* active, cudaStream_t st, int lane = 0) {
+                         const int32_t* active, cudaStream_t st, int lane = 0, JacobiMix mix = JacobiMix{nullptr, nullptr, nullptr}) {
   const double* cg = (Cguess && P && C) ? Cguess : nullptr;
   int npop = 0;
   for (int c = 0; c < g_jacobi_ncls; ++c) npop += (b->cls_count[c] > 0);
@@ -272,7 +277,7 @@ static int launch_jacobi(const seqm_batch_t* b, const double* F, double* P, doub
 #define SEQM_CASE(NPV)                                                                                               \
   case NPV:                                                                                                          \
     SEQM_LAUNCH(jacobi_fixed_kernel<NPV>, cnt, JacobiCfg<NPV>::THREADS, JacobiCfg<NPV>::SMEM, cst, *b, first, F, P, evals, \
-                C, cg, active);                                                                                      \
+                C, cg, active, mix);                                                                                 \
     break;
       SEQM_JACOBI_CLASSES(SEQM_CASE)
 #undef SEQM_CASE
@@ -837,18 +842,40 @@ static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, c
         PROF(PK_SP2, s, SEQM_LAUNCH(sp2_kernel, B.nmol, nt, smsp2, s, B, (const double*)F, W.Pnew, o->sp2_eps, (int32_t*)nullptr, (const int32_t*)W.active));
         CHKP("sp2_kernel");
       } else {
+        // the DIIS mixing (Pold <- P, P <- mix(P, Pnew)) is the tail of the density kernel
         PROF(PK_JACOBI, s, rc = launch_jacobi(&B, F, W.Pnew, (double*)nullptr, W.C,
-                                              (o->warm_start && (k > 0 || have_guess)) ? (const double*)W.C : (const double*)nullptr, W.active, s, h));
+                                              (o->warm_start && (k > 0 || have_guess)) ? (const double*)W.C : (const double*)nullptr, W.active, s, h,
+                                              JacobiMix{P, W.Pold, &W.ctrl->cF}));
         if (rc) return rc;
       }
-      PROF(PK_MIX, s, SEQM_LAUNCH(mix_linear_kernel, B.nmol, 256, 0, s, B, W, P, -1.0));
-      CHKP("mix_linear_kernel");
-      rc = launch_fock(&B, P, H, w, F, (const int32_t*)W.active, s);
+      if (o->use_sp2) {
+        PROF(PK_MIX, s, SEQM_LAUNCH(mix_linear_kernel, B.nmol, 256, 0, s, B, W, P, -1.0));
+        CHKP("mix_linear_kernel");
+      }
+      // elec_energy + get_error + active-mask update ride on the Fock kernel when the pair-centric one runs
+      FockErr fe;
+      fe.on = 1;
+      fe.use_diis = 1;
+      fe.eps = o->eps;
+      fe.Pold = W.Pold;
+      fe.diis_err = W.diis_err;
+      fe.Eel_run = W.Eel_run;
+      fe.Eel_new = W.Eel_new;
+      fe.err = W.err;
+      fe.dm_err = W.dm_err;
+      fe.dm_elem = W.dm_elem;
+      fe.notconv = notconverged;
+      fe.active_out = W.active;
+      fe.nnot = &W.ctrl->nnot;
+      bool fused = false;
+      rc = launch_fock(&B, P, H, w, F, (const int32_t*)W.active, s, &fe, &fused);
       if (rc) return rc;
-      PROF(PK_ENERGY_ERR, s, SEQM_LAUNCH(energy_error_kernel, B.nmol, 128, 0, s, B, W, (const double*)P, H, (const double*)F, notconverged, o->eps, 1));
-      CHKP("energy_error_kernel");
-      SEQM_LAUNCH(commit_active_kernel, gm, 128, 0, s, B, W, (const int32_t*)notconverged);
-      CHKP("commit_active_kernel");
+      if (!fused) {
+        PROF(PK_ENERGY_ERR, s, SEQM_LAUNCH(energy_error_kernel, B.nmol, 128, 0, s, B, W, (const double*)P, H, (const double*)F, notconverged, o->eps, 1));
+        CHKP("energy_error_kernel");
+        SEQM_LAUNCH(commit_active_kernel, gm, 128, 0, s, B, W, (const int32_t*)notconverged);
+        CHKP("commit_active_kernel");
+      }
 #ifndef SEQM_HOSTEMU
       cudaMemcpyAsync(g_h_nnot + 2 * h + (k & 1), &W.ctrl->nnot, sizeof(int), cudaMemcpyDeviceToHost, s);
       cudaEventRecord(g_ev_done[h][k & 1], s);
