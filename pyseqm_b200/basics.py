@@ -127,17 +127,10 @@ class Energy(torch.nn.Module):
             P0.copy_(Pd)
             Pd = P0
         Etot = Eelec + Enuc
-        Z = plan.Z
-        Eiso_atom = (
-            plan.parameter("U_ss") * const.ussc[Z] + plan.parameter("U_pp") * const.uppc[Z]
-            + plan.parameter("g_ss") * const.gssc[Z] + plan.parameter("g_pp") * const.gppc[Z]
-            + plan.parameter("g_sp") * const.gspc[Z] + plan.parameter("g_p2") * const.gp2c[Z]
-            + plan.parameter("h_sp") * const.hspc[Z]
-        )  # fmt: skip  (energy.py:8-23)
-        Eiso = torch.zeros_like(Etot).index_add_(0, plan.atom_mol, Eiso_atom)
+        Eiso, eheat = _atom_sums(plan, const)  # cached on the plan: they depend on the parameters only
         Hf = Etot - Eiso
         if self.Hf_flag:
-            Hf = Hf + torch.zeros_like(Etot).index_add_(0, plan.atom_mol, const.eheat[Z])
+            Hf = Hf + eheat
         self._grad = grad
         if all_terms:
             return Hf, Etot, Eelec, Enuc, Eiso, EnucAB, e_gap, e_mo, Pd, None, notconv
@@ -235,6 +228,9 @@ class ForceXL(torch.nn.Module):
 
 def _atom_sums(plan, const):
     """Per-molecule sums of the isolated-atom electronic energies (energy.py:8-23) and heats of formation."""
+    cached = plan.__dict__.get("_atom_sums")
+    if cached is not None and cached[0] == plan.par_version:
+        return cached[1], cached[2]
     Z = plan.Z
     Eiso_atom = (
         plan.parameter("U_ss") * const.ussc[Z] + plan.parameter("U_pp") * const.uppc[Z]
@@ -243,7 +239,9 @@ def _atom_sums(plan, const):
         + plan.parameter("h_sp") * const.hspc[Z]
     )  # fmt: skip
     z = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
-    return z.clone().index_add_(0, plan.atom_mol, Eiso_atom), z.clone().index_add_(0, plan.atom_mol, const.eheat[Z])
+    out = (z.clone().index_add_(0, plan.atom_mol, Eiso_atom), z.clone().index_add_(0, plan.atom_mol, const.eheat[Z]))
+    plan.__dict__["_atom_sums"] = (plan.par_version, out[0], out[1])
+    return out
 
 
 class Force(torch.nn.Module):

@@ -166,6 +166,7 @@ class BatchPlan:
                 _TABLE_CACHE[key] = (a.to(dev).contiguous(), c.to(dev).contiguous(), dim)
             self.pw = _TABLE_CACHE[key]
         self.par = par
+        self.par_version = 0  # bumped by set_parameters(): invalidates per-plan caches of parameter-derived sums
         s = SeqmBatchStruct()
         s.nmol, s.nat, s.npairs, s.method = nmol, self.nat, self.npairs, METHOD_ID[method]
         s.nmax, s.molsize, s.mat_total = self.nmax, molsize, self.mat_total
@@ -215,6 +216,7 @@ class BatchPlan:
             if t.requires_grad:
                 raise NotImplementedError("gradients with respect to learned parameters are not on the B200 path")
             self.par[PAR_ROWS.index(name)] = t.detach().to(torch.float64)
+        self.par_version += 1
         self.lib.check(self.lib.dll.seqm_atom_multipoles(self.ref, stream_of(self.par)), "seqm_atom_multipoles")
 
     # ---- helpers -----------------------------------------------------------------------------------
