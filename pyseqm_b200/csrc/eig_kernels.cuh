@@ -80,7 +80,7 @@ struct JacobiCfg {
                                    : NP == 28 ? SEQM_JB28 : NP == 32 ? SEQM_JB32 : 0;
   static constexpr int LDT = M + 4;  // staging stride of the tensor-core products: 4 or 12 mod 16, conflict-free
   static constexpr int AREG = M * (LD > LDT ? LD : LDT);    // doubles reserved for A (also holds the staging tile)
-  static constexpr size_t SMEM = sizeof(double) * ((size_t)AREG + 2 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)AREG + 4 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
 };
 
 // element (r, c) of the plane-split matrix
@@ -114,6 +114,55 @@ SEQM_HD void jacobi_tile_offsets(int k, int l, int* oe, int* oo) {
   }
 }
 
+// part-A tile a (0 <= a < 2 NP): diagonal (a,a), super-diagonal (a-NP, a-NP+1), corner (0, NP-1)
+template <int NP>
+SEQM_HD void jacobi_part_a_tile(int a, int& k, int& l) {
+  if (a < NP) { k = a; l = a; }
+  else if (a < 2 * NP - 1) { k = a - NP; l = k + 1; }
+  else { k = 0; l = NP - 1; }
+}
+// remaining tile r: rows k = 0.. with l = k+2..NP-1, the corner (0, NP-1) left out
+template <int NP>
+SEQM_HD void jacobi_rest_tile(int r, int& k, int& l) {
+  k = 0;
+  int cnt = NP - 3;  // row 0: l = 2..NP-2
+  while (r >= cnt) {
+    r -= cnt;
+    ++k;
+    cnt = NP - k - 2;
+  }
+  l = k + 2 + r;
+}
+// rotation (a, b) = (sin, cos) [rotate + swap] of the pair at slots (p, p+1), or (0, 1) [swap only] below tol;
+// (1, 0) for the wrap pair of odd steps
+template <int NP>
+SEQM_D seqm_d2 jacobi_pair_rotation(const double* A, int k, int ph, double tol, double tol_big, int* flag) {
+  constexpr int LD = JacobiCfg<NP>::LD;
+  seqm_d2 ab;
+  ab.x = 0.0;
+  ab.y = 1.0;
+  if (ph && k == NP - 1) {
+    ab.x = 1.0;
+    ab.y = 0.0;
+    return ab;
+  }
+  const int p = 2 * k + ph, q = p + 1;
+  const double apq = A[SEQM_AIDX(p, q)];
+  if (fabs(apq) > tol) {
+    // |theta| <= pi/4 from two reciprocal square roots (no division on the critical path):
+    // cos 2t = |d|/h, sin 2t = sgn(d) 2 a_pq / h, c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c)
+    const double d = A[SEQM_AIDX(q, q)] - A[SEQM_AIDX(p, p)], b2 = 2.0 * apq;
+    const double rh = seqm_rsqrt(d * d + b2 * b2);
+    const double c2 = 0.5 + 0.5 * fabs(d) * rh;
+    const double ic = seqm_rsqrt(c2);
+    ab.y = c2 * ic;                                 // cos
+    ab.x = (d >= 0.0 ? 0.5 : -0.5) * b2 * rh * ic;  // sin
+    flag[0] = 1;  // benign races: every writer stores 1
+    if (fabs(apq) > tol_big) flag[1] = 1;
+  }
+  return ab;
+}
+
 // Optional fused DIIS mixing (scf_loop.py:1045-1056) at the end of the density solve: Pold <- P ;
 // P <- a P + (1 - a) Pnew with a = 0.5 until two Fock matrices are stored (*cF < 2), else 0.
 struct JacobiMix { double* P; double* Pold; const int* cF; };
@@ -142,7 +191,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   SEQM_DYN_SMEM(double, sm);
   double* A = sm;
   seqm_d2* cs = reinterpret_cast<seqm_d2*>(A + K::AREG);
-  double* scr = reinterpret_cast<double*>(cs + NP);
+  double* scr = reinterpret_cast<double*>(cs + 2 * NP);  // cs is double buffered: [2][NP]
   double* dg = scr + 40;
   int* perm = reinterpret_cast<int*>(dg + M);
   int* occm = perm + M;
@@ -323,24 +372,28 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   for (int d = n + tid; d < M; d += nthr) A[SEQM_AIDX(d, d)] = (d + 2.0) * dmax + 1.0 + d;  // dummies above the spectrum
   SEQM_SYNC();
 
-  // step-invariant tile ownership: tile t -> (k <= l) and the four shared-memory offsets of the tile in even
-  // and in odd steps, all hoisted into registers (no integer division or address selects in the hot loop)
+  // Tile ownership.  The NP diagonal tiles (k,k), the NP-1 super-diagonal tiles (k,k+1) and the corner tile
+  // (0,NP-1) hold every element the NEXT step's rotations are computed from; they belong to threads 0..2NP-1 (the
+  // first warps), are updated first, and those warps then work out the next step's rotations while all the other
+  // threads update the remaining tiles and V: one block barrier per step, the rsqrt chain off the critical path.
+  // The four shared-memory offsets of every owned tile in even and in odd steps are hoisted into registers.
   constexpr int NT = NP * (NP + 1) / 2;
-  constexpr int TPT = (NT + K::THREADS - 1) / K::THREADS;
+  constexpr int NA = 2 * NP;                          // part-A tiles
+  constexpr int GA = ((NA + 31) / 32) * 32;           // threads of the warps that own them
+  constexpr int NR = NT - NA;                         // remaining tiles: l >= k + 2 without the corner
+  constexpr int NO = (K::THREADS > NA) ? K::THREADS - NA : 1;
+  constexpr int TPO = (NR + NO - 1) / NO;             // remaining tiles per non-part-A thread
+  constexpr int TPX = (TPO > 1) ? TPO : 1;
 #ifndef SEQM_HOSTEMU
-  int tk[TPT], tl[TPT], oe[TPT][4], oo[TPT][4];
+  int tk[TPX], tl[TPX], oe[TPX][4], oo[TPX][4];
 #pragma unroll
-  for (int qt = 0; qt < TPT; ++qt) {
-    const int t = tid + qt * nthr;
+  for (int qt = 0; qt < TPX; ++qt) {
     int k = -1, l = 0;
-    if (t < NT) {
-      int rem = t;  // row k of the upper triangle holds NP - k tiles
-      k = 0;
-      while (rem >= NP - k) {
-        rem -= NP - k;
-        ++k;
-      }
-      l = k + rem;
+    if (tid < NA) {
+      if (qt == 0) jacobi_part_a_tile<NP>(tid, k, l);
+    } else {
+      const int r = (tid - NA) + qt * NO;
+      if (r < NR) jacobi_rest_tile<NP>(r, k, l);
     }
     tk[qt] = k;
     tl[qt] = l;
@@ -381,56 +434,51 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     }
     ++nsweep;
     int* flag = s_flag[sweep & 1];
+    // rotations of step 0 (the later ones are computed inside the previous step)
+    for (int k = tid; k < NP; k += nthr) cs[k] = jacobi_pair_rotation<NP>(A, k, 0, tol, tol_big, flag);
+    SEQM_SYNC();
     for (int step = 0; step < M; ++step) {
       const int ph = step & 1;
-      // ---- transforms of the NP pairs
-      for (int k = tid; k < NP; k += nthr) {
-        seqm_d2 ab;
-        ab.x = 0.0;
-        ab.y = 1.0;  // swap only
-        if (ph && k == NP - 1) {
-          ab.x = 1.0;
-          ab.y = 0.0;  // wrap pair (m-1, 0)
-        } else {
-          const int p = 2 * k + ph, q = p + 1;
-          const double apq = A[SEQM_AIDX(p, q)];
-          if (fabs(apq) > tol) {
-            // rotation with |theta| <= pi/4 from two reciprocal square roots (no division on the critical
-            // path): cos 2t = |d|/h, sin 2t = sgn(d) 2 a_pq / h, c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c)
-            const double d = A[SEQM_AIDX(q, q)] - A[SEQM_AIDX(p, p)], b2 = 2.0 * apq;
-            const double rh = seqm_rsqrt(d * d + b2 * b2);
-            const double c2 = 0.5 + 0.5 * fabs(d) * rh;
-            const double ic = seqm_rsqrt(c2);
-            ab.y = c2 * ic;                                 // cos
-            ab.x = (d >= 0.0 ? 0.5 : -0.5) * b2 * rh * ic;  // sin
-            flag[0] = 1;  // benign races: every writer stores 1
-            if (fabs(apq) > tol_big) flag[1] = 1;
-          }
-        }
-        cs[k] = ab;
-      }
-      SEQM_SYNC();
-      if (step == 0 && tid == 0) { s_flag[(sweep + 1) & 1][0] = 0; s_flag[(sweep + 1) & 1][1] = 0; }
+      const seqm_d2* csc = cs + (step & 1) * NP;       // this step's rotations
+      seqm_d2* csn = cs + ((step + 1) & 1) * NP;       // next step's
+      if (step == 1 && tid == 0) { s_flag[(sweep + 1) & 1][0] = 0; s_flag[(sweep + 1) & 1][1] = 0; }
       // ---- A <- M_k^t A M_l on the upper-triangular tiles k <= l only (A is symmetric; elements (r,c) with
       //      r <= c are authoritative, the wrap pair (m-1,0) of odd steps uses the mirrored location (0,r))
 #ifndef SEQM_HOSTEMU
 #pragma unroll
-      for (int qt = 0; qt < TPT; ++qt) {
+      for (int qt = 0; qt < TPX; ++qt) {
         const int k = tk[qt], l = tl[qt];
-        if (k < 0) continue;
-        const int a00 = ph ? oo[qt][0] : oe[qt][0], a01 = ph ? oo[qt][1] : oe[qt][1];
-        const int a10 = ph ? oo[qt][2] : oe[qt][2], a11 = ph ? oo[qt][3] : oe[qt][3];
+        if (k >= 0) {
+          const int a00 = ph ? oo[qt][0] : oe[qt][0], a01 = ph ? oo[qt][1] : oe[qt][1];
+          const int a10 = ph ? oo[qt][2] : oe[qt][2], a11 = ph ? oo[qt][3] : oe[qt][3];
+          const seqm_d2 ck = csc[k], cl = csc[l];
+          const bool diag = (k == l);
+          const double x0 = A[a00], y0 = A[a01], y1 = A[a11];
+          const double x1 = diag ? y0 : A[a10];
+          const double bx0 = cl.x * x0 + cl.y * y0, by0 = cl.y * x0 - cl.x * y0;
+          const double bx1 = cl.x * x1 + cl.y * y1, by1 = cl.y * x1 - cl.x * y1;
+          A[a00] = ck.x * bx0 + ck.y * bx1;
+          A[a01] = ck.x * by0 + ck.y * by1;
+          A[a11] = ck.y * by0 - ck.x * by1;
+          if (!diag) A[a10] = ck.y * bx0 - ck.x * bx1;
+        }
+        if (qt == 0 && tid < GA) {
+          // the part-A tiles are done: their warps (only) meet on named barrier 1 and compute the next rotations
+          if (GA == K::THREADS) __syncthreads();
+          else asm volatile("bar.sync 1, %0;" ::"r"(GA) : "memory");
+          if (step + 1 < M && tid < NP) csn[tid] = jacobi_pair_rotation<NP>(A, tid, ph ^ 1, tol, tol_big, flag);
+        }
+      }
 #else
-      for (int t = 0; t < NT; ++t) {  // the single emulation thread plays every tile owner
-        int k = 0, rem = t;
-        while (rem >= NP - k) { rem -= NP - k; ++k; }
-        const int l = k + rem;
+      for (int t = 0; t < NT; ++t) {  // the single emulation thread plays every tile owner, part A first
+        int k, l;
+        if (t < NA) jacobi_part_a_tile<NP>(t, k, l);
+        else jacobi_rest_tile<NP>(t - NA, k, l);
         int oe1[4], oo1[4];
         jacobi_tile_offsets<NP>(k, l, oe1, oo1);
         const int a00 = ph ? oo1[0] : oe1[0], a01 = ph ? oo1[1] : oe1[1];
         const int a10 = ph ? oo1[2] : oe1[2], a11 = ph ? oo1[3] : oe1[3];
-#endif
-        const seqm_d2 ck = cs[k], cl = cs[l];
+        const seqm_d2 ck = csc[k], cl = csc[l];
         const bool diag = (k == l);
         const double x0 = A[a00], y0 = A[a01], y1 = A[a11];
         const double x1 = diag ? y0 : A[a10];
@@ -440,13 +488,16 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         A[a01] = ck.x * by0 + ck.y * by1;
         A[a11] = ck.y * by0 - ck.x * by1;
         if (!diag) A[a10] = ck.y * bx0 - ck.x * bx1;
+        if (t == NA - 1 && step + 1 < M)
+          for (int kk = 0; kk < NP; ++kk) csn[kk] = jacobi_pair_rotation<NP>(A, kk, ph ^ 1, tol, tol_big, flag);
       }
+#endif
       // ---- V <- V M
 #ifndef SEQM_HOSTEMU
       if (!ph) {
 #pragma unroll
         for (int j = 0; j < SEG / 2; ++j) {
-          const seqm_d2 c = cs[vseg * (SEG / 2) + j];
+          const seqm_d2 c = csc[vseg * (SEG / 2) + j];
           const double x = vr[2 * j], y = vr[2 * j + 1];
           vr[2 * j] = c.x * x + c.y * y;
           vr[2 * j + 1] = c.y * x - c.x * y;
@@ -458,13 +509,13 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~(SR - 1)) | ((lane + SR - 1) & (SR - 1)));
 #pragma unroll
         for (int j = 0; j < SEG / 2 - 1; ++j) {
-          const seqm_d2 c = cs[vseg * (SEG / 2) + j];
+          const seqm_d2 c = csc[vseg * (SEG / 2) + j];
           const double x = vr[2 * j + 1], y = vr[2 * j + 2];
           vr[2 * j + 1] = c.x * x + c.y * y;
           vr[2 * j + 2] = c.y * x - c.x * y;
         }
-        const seqm_d2 cn = cs[vseg * (SEG / 2) + SEG / 2 - 1];    // pair (my last, next quarter's first)
-        const seqm_d2 cp = cs[(vseg * (SEG / 2) + NP - 1) % NP];  // pair (previous quarter's last, my first)
+        const seqm_d2 cn = csc[vseg * (SEG / 2) + SEG / 2 - 1];    // pair (my last, next quarter's first)
+        const seqm_d2 cp = csc[(vseg * (SEG / 2) + NP - 1) % NP];  // pair (previous quarter's last, my first)
         vr[SEG - 1] = cn.x * last_old + cn.y * y_next;
         vr[0] = cp.y * x_prev - cp.x * first_old;
       }
@@ -473,8 +524,8 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         for (int l = 0; l < NP; ++l) {
           const int p = 2 * l + ph, q = (p + 1) % M;
           const double x = Vh[i * M + p], y = Vh[i * M + q];
-          Vh[i * M + p] = cs[l].x * x + cs[l].y * y;
-          Vh[i * M + q] = cs[l].y * x - cs[l].x * y;
+          Vh[i * M + p] = csc[l].x * x + csc[l].y * y;
+          Vh[i * M + q] = csc[l].y * x - csc[l].x * y;
         }
 #endif
       SEQM_SYNC();
