@@ -63,7 +63,10 @@ struct alignas(16) seqm_d2 { double x, y; };
 template <int NP>
 struct JacobiCfg {
   static constexpr int M = 2 * NP;
-  static constexpr int LD = M + ((NP / 2) % 8);
+#ifndef SEQM_LDPAD0
+#define SEQM_LDPAD0 6  // the classes whose natural pad is 0 (NP = 16, 32, 48, 64): measured best of 0/2/4/6
+#endif
+  static constexpr int LD = M + (((NP / 2) % 8) ? ((NP / 2) % 8) : SEQM_LDPAD0);
   static constexpr int SR = (NP >= SEQM_SR8_FROM && NP % 8 == 0) ? 8 : 4;  // threads per row of V (more for the big classes: 1 CTA/SM there,
                                                  // so the CTA itself must bring enough warps to hide latency)
   static constexpr int SEG = M / SR;             // V entries per thread
