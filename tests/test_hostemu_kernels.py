@@ -105,3 +105,24 @@ def test_largest_shared_memory_size_class(lib):
     from helpers import check_largest_in_sm_class
 
     check_largest_in_sm_class(lib, CPU)
+
+
+@pytest.mark.parametrize("pipe", ["1", "2"])
+def test_scf_iteration_cap_reports_not_converged(lib, pipe, monkeypatch):
+    """seqm_scf with max_iter = 3 (the reference's MAX_ITER is 1000, scf_loop.py:29): the loop runs iterations
+    0..max_iter, leaves the not-converged flags set and reports max_iter + 1, on both host-loop variants."""
+    from conftest import load_golden
+    from pyseqm_b200 import engine
+
+    monkeypatch.setenv("SEQM_B200_PIPELINE", pipe)
+    g = load_golden("cfg1_AM1_c2")
+    plan = engine.BatchPlan(lib, torch.as_tensor(g["species"]), "AM1")
+    xyz = plan.real_xyz(torch.as_tensor(g["coordinates"]))
+    w, hab = engine.op_pair_integrals(plan, xyz)
+    H = engine.op_hcore(plan, w, hab)
+    P = engine.op_initial_density(plan)
+    F, E, nc, n_iter = engine.op_scf(plan, H, w, P, 1e-7, [2], max_iter=3)
+    assert n_iter == 4 and bool(nc.all()) and torch.isfinite(E).all()
+    P2 = engine.op_initial_density(plan)
+    F2, E2, nc2, n_iter2 = engine.op_scf(plan, H, w, P2, 1e-7, [2])
+    assert n_iter2 == g["n_scf_iter"] and not bool(nc2.any())
