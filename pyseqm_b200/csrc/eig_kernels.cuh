@@ -546,6 +546,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     if (nsweep == 0) stat_add(3, 1);
   }
   // eigenvalues -> dg and their ranking, then reuse the A storage for V in standard layout (row stride M)
+  SEQM_SYNC();  // the convergence check above may still be reading dg / perm in other warps
   for (int i = tid; i < M; i += nthr) dg[i] = A[SEQM_AIDX(i, i)];
   SEQM_SYNC();
   for (int i = tid; i < M; i += nthr) {
