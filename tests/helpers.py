@@ -291,3 +291,22 @@ def check_largest_in_sm_class(lib, device):
     mol2, es2 = run_molecule(lib, device, species, coords, sp2)
     assert not bool(es2.notconverged.any())
     assert np.abs(mol2.Etot.cpu().numpy() - ref["Etot"]).max() < 1e-3
+
+
+def check_isolated_atoms(lib, device):
+    """Molecules without any pair (a lone O atom), alone and next to water: zero-length pair ranges, the
+    atom-centric Fock fallback when nobody in the batch needs the pair parking area."""
+    import seqm_oracle as so
+
+    species = np.array([[8, 0, 0], [8, 1, 1]])
+    coords = np.zeros((2, 3, 3))
+    coords[1, 1] = [0.96, 0.0, 0.0]
+    coords[1, 2] = [-0.24, 0.93, 0.0]
+    sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2]}
+    for sl in (slice(0, 2), slice(0, 1)):
+        ref = so.single_point(species[sl], coords[sl], sp)
+        mol, es = run_molecule(lib, device, species[sl], coords[sl], sp)
+        assert mol.n_scf_iter == ref["n_scf_iter"] and not bool(es.notconverged.any())
+        assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < TOL_E
+        assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < TOL_DM
+        assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F

@@ -196,3 +196,9 @@ def test_largest_shared_memory_size_class(lib, dev):
     from helpers import check_largest_in_sm_class
 
     check_largest_in_sm_class(lib, dev)
+
+
+def test_isolated_atoms(lib, dev):
+    from helpers import check_isolated_atoms
+
+    check_isolated_atoms(lib, dev)

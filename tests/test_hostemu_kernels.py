@@ -126,3 +126,9 @@ def test_scf_iteration_cap_reports_not_converged(lib, pipe, monkeypatch):
     P2 = engine.op_initial_density(plan)
     F2, E2, nc2, n_iter2 = engine.op_scf(plan, H, w, P2, 1e-7, [2])
     assert n_iter2 == g["n_scf_iter"] and not bool(nc2.any())
+
+
+def test_isolated_atoms(lib):
+    from helpers import check_isolated_atoms
+
+    check_isolated_atoms(lib, CPU)
