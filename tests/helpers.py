@@ -308,5 +308,9 @@ def check_isolated_atoms(lib, device):
         mol, es = run_molecule(lib, device, species[sl], coords[sl], sp)
         assert mol.n_scf_iter == ref["n_scf_iter"] and not bool(es.notconverged.any())
         assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < TOL_E
-        assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < TOL_DM
         assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F
+        # the lone O atom has a degenerate, partly filled p shell: its density is not unique (which two of the three
+        # p orbitals are occupied), only tr P is; the water molecule next to it is compared in full
+        assert abs(float(mol.dm[0].diagonal().sum()) - 6.0) < 1e-10
+        if mol.dm.shape[0] > 1:
+            assert np.abs(mol.dm[1].cpu().numpy() - ref["dm"][1]).max() < TOL_DM
