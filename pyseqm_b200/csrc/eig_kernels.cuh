@@ -430,7 +430,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
       }
       ov = block_max(ov, scr);
       const double gap = dg[perm[v.nocc]] - dg[perm[v.nocc - 1]];
-      if (ov <= tol_pert && ov <= 1.0e-6 * gap) {
+      if (gap > 0.0 && ov <= tol_pert && ov <= 1.0e-6 * gap) {  // gap > 0: no 0/0 for a degenerate open shell
         pert = true;
         break;
       }
