@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SEQM_ABI_VERSION 1
+#define SEQM_ABI_VERSION 2
 
 /* rows of the per-atom parameter table atom_par[row * nat + atom] */
 enum seqm_par_row {
@@ -76,6 +76,10 @@ typedef struct seqm_batch {
   /* doubles of shared-memory Coulomb scratch the pair-centric Fock kernel needs for the largest molecule:
    * max over molecules of 20 nXX + 11 nXH + 2 nHH (pairs by class); 0 = use the two-pass kernel */
   int32_t fock_scratch;
+  /* seqm_parameters["pair_outer_cutoff"] in Angstrom (Parser, basics.py:209, 326: pairs with |R_i - R_j| >= cutoff
+   * are dropped from the pair list).  Here the dense triangular pair list is kept and such a pair contributes
+   * exactly nothing: w, its overlap block, its core-core energy and its gradient are zero.  <= 0: no cutoff. */
+  double pair_outer_cutoff;
 } seqm_batch_t;
 
 int seqm_abi_version(void);

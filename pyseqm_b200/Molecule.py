@@ -109,7 +109,8 @@ class Molecule(torch.nn.Module):
             if t.requires_grad:
                 raise NotImplementedError("gradients with respect to learned parameters need autograd through the SCF; not on the B200 path")
             learned[name] = t.detach()
-        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned, charges=charges, table=table)
+        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned, charges=charges, table=table,
+                                outer_cutoff=seqm_parameters.get("pair_outer_cutoff", 1.0e10))
         self._plan = plan
         if seqm_parameters.get("elements") is None:
             seqm_parameters["elements"] = plan.elements
@@ -122,9 +123,9 @@ class Molecule(torch.nn.Module):
         self.idxi, self.idxj = plan.pair_i, plan.pair_j
         # maskd / mask / mask_l / ni / nj / pair_molid / xij / rij are derived on first access (see __getattr__):
         # the kernels never read them, they exist for the reference's attribute contract
-        cutoff = seqm_parameters.get("pair_outer_cutoff", 1.0e10)
-        if cutoff < 1.0e9 and bool((self.rij / const.length_conversion_factor >= cutoff).any()):
-            raise NotImplementedError("pair_outer_cutoff that removes pairs is not supported by the B200 path yet")
+        # pair_outer_cutoff (basics.py:209, 326): the pair list stays the dense triangular one; a pair at or beyond the
+        # cutoff contributes exactly nothing (the kernels return zero for its w, overlap block, core-core energy and
+        # gradient), which is what dropping it from the reference's list does.  idxi/idxj/rij/xij/w keep such pairs.
         # per-atom parameter dict (Molecule.py:86-115)
         names = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha"]
         ng = {"MNDO": 0, "AM1": 4, "PM3": 2, "PM6_SP": 4, "PM6": 4}[self.method]

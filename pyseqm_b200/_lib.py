@@ -35,6 +35,7 @@ class SeqmBatchStruct(C.Structure):
         ("atom_par", C.c_void_p), ("cls_begin", C.c_int32 * 12), ("cls_count", C.c_int32 * 12),
         ("pw_alpha", C.c_void_p), ("pw_chi", C.c_void_p), ("pw_dim", C.c_int32),
         ("pair_cls_off", C.c_int32 * 4), ("pair_perm", C.c_void_p), ("fock_scratch", C.c_int32),
+        ("pair_outer_cutoff", C.c_double),
     ]  # fmt: skip
 
 JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64)
@@ -126,7 +127,7 @@ class SeqmLib:
             fn.argtypes = args
             fn.restype = res
         self.symbols = list(sig)
-        if self.dll.seqm_abi_version() != 1:
+        if self.dll.seqm_abi_version() != 2:
             raise SeqmError("libseqm_b200 ABI version mismatch")
 
     def jacobi_stats(self, reset=True):

@@ -79,6 +79,12 @@ SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<Dual3>& g) {
   g.r = d * (1.0 / SEQM_A0);
 }
 
+// Parser's outer cutoff (basics.py:326: a pair is kept when |R_i - R_j|^2 < cutoff^2).  The dense pair list keeps the
+// pair; every kernel that evaluates pair physics from the geometry returns zero for it instead.
+SEQM_HD bool pair_cut(const seqm_batch_t& b, double r_bohr) {
+  return b.pair_outer_cutoff > 0.0 && r_bohr * SEQM_A0 >= b.pair_outer_cutoff;
+}
+
 // w of one pair in the molecular frame (only the entries that exist for the pair class are non-zero)
 // Only the entries that exist for the pair class are written: [0][0] (H-H), [0..9][0] (X-H), all (X-X).
 template <class T>
@@ -122,9 +128,14 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS == 2) ? SEQM_PI_MINB : 0) pair_in
     const int i = b.pair_i[p], j = b.pair_j[p];
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
+    double* wp = w + (long long)p * 100;
+    if (pair_cut(b, g.r)) {
+      for (int k = 0; k < 100; ++k) wp[k] = 0.0;
+      for (int k = 0; k < 16; ++k) hab[(long long)p * 16 + k] = 0.0;
+      continue;
+    }
     double wl[10][10];
     pair_w(b, i, j, g, wl, nint);
-    double* wp = w + (long long)p * 100;
     for (int k = 0; k < 10; ++k)
       for (int l = 0; l < 10; ++l) wp[k * 10 + l] = (k < nA && l < nB) ? wl[k][l] : 0.0;
     double S[4][4];
@@ -183,6 +194,10 @@ SEQM_GLOBAL void nuclear_energy_kernel(seqm_batch_t b, const double* __restrict_
     const int i = b.pair_i[p], j = b.pair_j[p];
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
+    if (pair_cut(b, g.r)) {
+      EnucAB[p] = 0.0;
+      continue;
+    }
     double alp, chi;
     pair_pw(b, i, j, alp, chi);
     EnucAB[p] = core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), g.r,
@@ -227,6 +242,10 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
     const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
+    if (pair_cut(b, g.r)) {
+      gpair[3 * (long long)p] = gpair[3 * (long long)p + 1] = gpair[3 * (long long)p + 2] = 0.0;
+      continue;
+    }
     const double dist = g.r * SEQM_A0;
     const Dual1 r1(g.r, 1.0);
     double dEdr = 0.0, dEde[3] = {0.0, 0.0, 0.0};
@@ -424,6 +443,10 @@ SEQM_GLOBAL void pair_gradient_forward_kernel(seqm_batch_t b, const double* __re
     const int ni = orb_cnt(v, i - v.a0), nj = orb_cnt(v, j - v.a0);
     PairGeom<Dual3> g;
     pair_geom(xyz, i, j, g);
+    if (pair_cut(b, g.r.v)) {
+      gpair[3 * (long long)p] = gpair[3 * (long long)p + 1] = gpair[3 * (long long)p + 2] = 0.0;
+      continue;
+    }
     Dual3 E(0.0);
     {  // resonance term
       Dual3 S[4][4];

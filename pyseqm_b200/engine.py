@@ -89,7 +89,7 @@ def _device_tables(method, dev):
 class BatchPlan:
     """Index tensors of one molecule batch (topology only; coordinates are passed per call)."""
 
-    def __init__(self, lib, species, method, parameters=None, charges=0, table=None):
+    def __init__(self, lib, species, method, parameters=None, charges=0, table=None, outer_cutoff=None):
         if method not in METHOD_ID:
             raise NotImplementedError(
                 f"method {method!r} is not implemented by the B200 path (supported: {sorted(METHOD_ID)})"
@@ -179,6 +179,8 @@ class BatchPlan:
         s.pair_cls_off[2], s.pair_cls_off[3] = pair_cls_cnt[0] + pair_cls_cnt[1], sum(pair_cls_cnt)
         s.pair_perm = self.pair_perm.data_ptr()
         s.fock_scratch = fock_scratch
+        # Parser's pair_outer_cutoff in Angstrom (basics.py:209, 326); the reference default 1e10 keeps every pair
+        s.pair_outer_cutoff = float(outer_cutoff) if outer_cutoff is not None and outer_cutoff < 1.0e9 else 0.0
         # eigensolver size classes over the descending-n processing order (host arrays inside the struct):
         # class c = smallest NP with 2*NP >= n; molecules beyond the last class (large path) belong to none
         begin = cls_cnt[ncls]  # mol_order is descending in n: the too-large molecules come first

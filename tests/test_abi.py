@@ -30,7 +30,7 @@ def test_cuda_library_exports_all_declared_symbols():
     for name in declared_symbols():
         assert hasattr(dll, name), name
     dll.seqm_abi_version.restype = ctypes.c_int
-    assert dll.seqm_abi_version() == 1
+    assert dll.seqm_abi_version() == 2
     # the host-emulation build exposes the same ABI
     emu = ctypes.CDLL(ge.build_hostemu())
     for name in declared_symbols():

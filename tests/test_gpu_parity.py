@@ -25,7 +25,7 @@ def dev():
 
 def test_cuda_library_is_the_one_loaded(lib):
     assert lib.path.endswith("pyseqm_b200/lib/libseqm_b200.so")
-    assert lib.dll.seqm_abi_version() == 1
+    assert lib.dll.seqm_abi_version() == 2
 
 
 @pytest.mark.parametrize("method", ["AM1", "PM3", "MNDO", "PM6_SP"])
@@ -44,7 +44,7 @@ def test_reference_operator_signatures(lib, dev, method):
     "name",
     ["cfg1_AM1_c2", "cfg1_AM1_c1", "cfg1_AM1_c0", "cfg1_PM3_c2", "cfg1_PM3_c1", "cfg1_PM3_c0", "cfg1_MNDO_c2",
      "cfg1_MNDO_c1", "cfg1_MNDO_c0", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48", "cfg1_PM6_SP_c2", "cfg1_PM6_SP_c1",
-     "cfg2_PM6_SP_24", "opt_charged_AM1", "opt_learned_PM3", "opt_flags_MNDO", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2",
+     "cfg2_PM6_SP_24", "opt_charged_AM1", "opt_learned_PM3", "opt_flags_MNDO", "opt_cutoff_AM1", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2",
      "cfg3_coronene_AM1"],
 )  # fmt: skip
 def test_single_point_golden(lib, dev, name):

@@ -31,7 +31,7 @@ def test_reference_operator_signatures(lib, method):
     "name",
     ["cfg1_AM1_c2", "cfg1_AM1_c1", "cfg1_AM1_c0", "cfg1_PM3_c2", "cfg1_PM3_c1", "cfg1_MNDO_c2", "cfg1_MNDO_c0",
      "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48", "cfg1_PM6_SP_c2", "cfg1_PM6_SP_c1",
-     "cfg2_PM6_SP_24", "opt_charged_AM1", "opt_learned_PM3", "opt_flags_MNDO", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2", "cfg3_coronene_AM1"],
+     "cfg2_PM6_SP_24", "opt_charged_AM1", "opt_learned_PM3", "opt_flags_MNDO", "opt_cutoff_AM1", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2", "cfg3_coronene_AM1"],
 )  # fmt: skip
 def test_single_point_golden(lib, name):
     check_golden_case(lib, CPU, name)

@@ -13,7 +13,7 @@ from conftest import GOLDEN, TOL_DM, TOL_E, TOL_F, load_golden
 XYZ = os.path.join(GOLDEN, "xyz")
 
 CASES = [f"cfg1_{m}_{c}" for m in ("AM1", "PM3", "MNDO", "PM6_SP") for c in ("c2", "c1", "c0")] + [
-    "cfg2_PM6_SP_24", "pm6_sp_elements_c2", "opt_charged_AM1", "opt_learned_PM3", "opt_flags_MNDO", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2",
+    "cfg2_PM6_SP_24", "pm6_sp_elements_c2", "opt_charged_AM1", "opt_learned_PM3", "opt_flags_MNDO", "opt_cutoff_AM1", "thirdrow_PM3_c2", "thirdrow_AM1_c2", "thirdrow_MNDO_c2", "thirdrow_PM6_SP_c2",
     "cfg1_AM1_sp2", "ref_batch_single_point_am1", "ref_ground_force_methanal", "cfg2_PM3_48", "cfg3_coronene_AM1",
 ]  # fmt: skip
 

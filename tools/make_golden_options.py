@@ -67,3 +67,8 @@ save("opt_learned_PM3", run(species, coords, sp, learned=learned), species, coor
 # 3. Hf_flag / eig off, constant mixing
 sp = {"method": "MNDO", "scf_eps": 1e-6, "scf_converger": [0, 0.3], "sp2": [False], "Hf_flag": False, "eig": False}
 save("opt_flags_MNDO", run(species, coords, sp), species, coords, sp)
+
+# 4. pair_outer_cutoff that removes pairs (Parser, basics.py:209, 326): 3.5 Angstrom drops every para C...C, most
+#    C...H and H...H pairs of benzene / toluene; methane keeps all of its pairs
+sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2], "sp2": [False], "pair_outer_cutoff": 3.5}
+save("opt_cutoff_AM1", run(species, coords, sp), species, coords, sp)
