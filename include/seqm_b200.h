@@ -183,6 +183,15 @@ int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double
 /* packed eigenvector matrices -> dense (nmol, nmax, nmax), identity on the padding: the `v` of diag.py:110-241 */
 int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void* stream);
 
+/* MO crossing matcher -- Energy._crossing_match_molecular_orbitals / _grouped, seqm/basics.py:596-719 (called on every
+ * forward after the first one on the same Molecule, basics.py:846-857): the new orbitals are permuted inside the
+ * occupied and inside the virtual block so that orbital k continues old orbital k (largest |overlap|, greedy repair
+ * when that is not a permutation), their signs are aligned with the old ones, and the eigenvalues follow.
+ * V_new, V_old, V_out: (nmol, nmax, nmax) dense, column = MO (the `molecular_orbitals` layout; V_out must not alias
+ * V_new); e_in, e_out: (nmol, nmax); S_scratch: mat_total doubles; perm, used: (nmol, nmax) int32; prio: (nmol, nmax). */
+int seqm_mo_match(const seqm_batch_t* b, const double* V_new, const double* V_old, const double* e_in, double* S_scratch,
+                  int32_t* perm, int32_t* used, double* prio, double* V_out, double* e_out, void* stream);
+
 /* pack()/unpack() -- pack.py:64-96 between dense (nmol, 4*molsize, 4*molsize) and packed matrices */
 int seqm_pack(const seqm_batch_t* b, const double* dense, double* packed, void* stream);
 int seqm_unpack(const seqm_batch_t* b, const double* packed, double* dense, void* stream);

@@ -114,6 +114,7 @@ class SeqmLib:
             "seqm_elec_energy_xl": ([B, P, P, P, P, P, P], C.c_int),
             "seqm_xl_propagate": ([C.c_int64, C.c_double, C.c_double, P, P, P, P, C.c_int32, C.c_int32, P, P], C.c_int),
             "seqm_orbitals_dense": ([B, P, P, P], C.c_int),
+            "seqm_mo_match": ([B, P, P, P, P, P, P, P, P, P, P], C.c_int),
             "seqm_launch_count": ([], C.c_longlong),
             "seqm_fp64_peak_tflops": ([], C.c_double),
             "seqm_jacobi_stats": ([C.POINTER(C.c_ulonglong), C.c_int], C.c_int),

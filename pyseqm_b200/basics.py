@@ -20,6 +20,17 @@ def _timing(molecule, key, t0):
     return t0
 
 
+def _match_orbitals(plan, V, prev_mos, e_mo):
+    """Crossing matcher of basics.py:846-857: from the second forward on the same Molecule on, orbital k continues
+    the previous orbital k (permutation inside the occupied / virtual blocks + sign); e_mo follows in place, e_gap
+    does not (the reference computes it before the matching, basics.py:840-842)."""
+    if not torch.is_tensor(prev_mos) or prev_mos.shape != V.shape or prev_mos.device != V.device:
+        return V
+    V, e = engine.op_mo_match(plan, V, prev_mos.detach(), e_mo[:, : plan.nmax])
+    e_mo[:, : plan.nmax] = e
+    return V
+
+
 class Energy(torch.nn.Module):
     def __init__(self, seqm_parameters):
         super().__init__()
@@ -83,6 +94,7 @@ class Energy(torch.nn.Module):
         else:
             molecule.w = w
         molecule._gam = w[:, 0, 0]
+        prev_mos = molecule.molecular_orbitals  # basics.py:846: the orbitals of the previous forward on this molecule
         if self.eig and plan.large:
             # final eigenpairs of a large molecule: one cuSOLVER call outside the SCF hot loop
             Fd = engine.op_unpack(plan, F)
@@ -97,7 +109,7 @@ class Energy(torch.nn.Module):
                 V[m, : idx.numel(), : idx.numel()] = vec
             lumo = plan.nocc.unsqueeze(1)
             e_gap = (e_mo.gather(1, lumo) - e_mo.gather(1, lumo - 1)).reshape(-1)
-            molecule.molecular_orbitals = V
+            molecule.molecular_orbitals = _match_orbitals(plan, V, prev_mos, e_mo)
         elif self.eig:
             # eigenpairs of the converged Fock matrix, warm-started from the last SCF eigenbasis
             e_mo_n, _, Cm = engine.op_eig_density(plan, F, want_P=False, want_C=True,
@@ -107,7 +119,7 @@ class Energy(torch.nn.Module):
             e_mo[:, : plan.nmax] = e_mo_n
             lumo = plan.nocc.unsqueeze(1)
             e_gap = (e_mo.gather(1, lumo) - e_mo.gather(1, lumo - 1)).reshape(-1)
-            molecule.molecular_orbitals = engine.op_orbitals_dense(plan, Cm)
+            molecule.molecular_orbitals = _match_orbitals(plan, engine.op_orbitals_dense(plan, Cm), prev_mos, e_mo)
         else:
             e_mo, e_gap = None, None
         EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)

@@ -332,6 +332,121 @@ SEQM_GLOBAL void orbitals_dense_kernel(seqm_batch_t b, const double* __restrict_
     Vm[t] = (i < n && j < n) ? C[v.mat0 + i * n + j] : ((i == j) ? 1.0 : 0.0);
   }
 }
+// ---- MO crossing matcher (Energy._crossing_match_molecular_orbitals[_grouped], basics.py:596-719) ---------------
+// Orbitals are dense (nmol, N, N), N = nmax, column k = MO k (the layout of `molecular_orbitals`).
+// Step 1: signed overlaps S[k][l] = sum_r Vold[r][k] Vnew[r][l], old k and new l both occupied or both virtual, in a
+// packed-size scratch buffer (nocc^2 + nvirt^2 <= n^2 doubles per molecule): occupied block first.
+SEQM_GLOBAL void mo_overlap_kernel(seqm_batch_t b, int parts, const double* __restrict__ Vold,
+                                   const double* __restrict__ Vnew, double* __restrict__ S) {
+  const MolView v = mol_view(b, blockIdx.x / parts);
+  const int part = blockIdx.x % parts;
+  const int n = v.n, N = b.nmax, no = v.nocc, nv = n - no;
+  const double* Co = Vold + (long long)v.m * N * N;
+  const double* Cn = Vnew + (long long)v.m * N * N;
+  const int total = no * no + nv * nv;
+  for (int t = part * blockDim.x + threadIdx.x; t < total; t += parts * blockDim.x) {
+    int k, l;
+    if (t < no * no) {
+      k = t / no;
+      l = t - k * no;
+    } else {
+      const int u = t - no * no;
+      k = u / nv;
+      l = no + u - k * nv;
+      k += no;
+    }
+    double s = 0.0;
+    for (int r = 0; r < n; ++r) s += Co[(long long)r * N + k] * Cn[(long long)r * N + l];
+    S[v.mat0 + t] = s;
+  }
+}
+// Step 2, one CTA per molecule and block (occupied, virtual): every old orbital takes the new orbital of largest
+// |overlap| (basics.py:651-653); when that is not a permutation the rows are served greedily in the order of
+// their margin top1 - top2, each taking its best still unused column (greedy_unique_perm, basics.py:606-626).
+// Then V_out[:, k] = sign(S[k][p_k]) V_new[:, p_k] (sign 0 -> +1, basics.py:631-635) and e_out[k] = e[p_k].
+SEQM_GLOBAL void mo_match_kernel(seqm_batch_t b, const double* __restrict__ Vnew, const double* __restrict__ S,
+                                 const double* __restrict__ e_in, int32_t* __restrict__ perm, int32_t* __restrict__ used,
+                                 double* __restrict__ prio, double* __restrict__ Vout, double* __restrict__ e_out) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n, N = b.nmax;
+  int32_t* p = perm + (long long)v.m * N;
+  int32_t* u = used + (long long)v.m * N;
+  double* pr = prio + (long long)v.m * N;
+  for (int blk = 0; blk < 2; ++blk) {
+    const int o = blk ? v.nocc : 0, r = blk ? n - v.nocc : v.nocc;
+    if (r == 0) continue;
+    const double* Sb = S + v.mat0 + (blk ? v.nocc * v.nocc : 0);
+    for (int t = threadIdx.x; t < r; t += blockDim.x) u[o + t] = 0;
+    SEQM_SYNC();
+    for (int t = threadIdx.x; t < r; t += blockDim.x) {
+      double b1 = -1.0, b2 = -1.0;
+      int i1 = 0;
+      for (int c = 0; c < r; ++c) {
+        const double a = fabs(Sb[(long long)t * r + c]);
+        if (a > b1) {
+          b2 = b1;
+          b1 = a;
+          i1 = c;
+        } else if (a > b2) {
+          b2 = a;
+        }
+      }
+      p[o + t] = i1;
+      pr[o + t] = (r > 1) ? b1 - b2 : b1;
+      seqm_atomic_add(&u[o + i1], 1);
+    }
+    SEQM_SYNC();
+    int bad = 0;
+    for (int t = threadIdx.x; t < r; t += blockDim.x) bad |= (u[o + t] != 1);
+    bad = seqm_sync_or(bad);
+    if (bad) {
+      if (threadIdx.x == 0) {
+        for (int c = 0; c < r; ++c) u[o + c] = 0;
+        for (int it = 0; it < r; ++it) {
+          int row = 0;
+          double best = -1.0;
+          for (int t = 0; t < r; ++t)
+            if (pr[o + t] > best) {
+              best = pr[o + t];
+              row = t;
+            }
+          pr[o + row] = -2.0;  // served (margins are >= 0)
+          int col = 0;
+          double bv = -1.0;
+          for (int c = 0; c < r; ++c) {
+            const double a = fabs(Sb[(long long)row * r + c]);
+            if (!u[o + c] && a > bv) {
+              bv = a;
+              col = c;
+            }
+          }
+          p[o + row] = col;
+          u[o + col] = 1;
+        }
+      }
+      SEQM_SYNC();
+    }
+  }
+  SEQM_SYNC();
+  const double* Cn = Vnew + (long long)v.m * N * N;
+  double* Cout = Vout + (long long)v.m * N * N;
+  const int no = v.nocc;
+  for (int t = threadIdx.x; t < N * N; t += blockDim.x) {
+    const int i = t / N, k = t - i * N;
+    double x;
+    if (i < n && k < n) {
+      const int blk = k >= no, o = blk ? no : 0, r = blk ? n - no : no;
+      const int c = p[k];  // p is indexed by absolute MO, its value is block-local
+      const double sg = S[v.mat0 + (blk ? no * no : 0) + (long long)(k - o) * r + c];
+      x = (sg < 0.0 ? -1.0 : 1.0) * Cn[(long long)i * N + o + c];
+    } else {
+      x = Cn[t];
+    }
+    Cout[t] = x;
+  }
+  for (int k = threadIdx.x; k < N; k += blockDim.x)
+    e_out[(long long)v.m * N + k] = (k < n) ? e_in[(long long)v.m * N + (k >= no ? no : 0) + p[k]] : e_in[(long long)v.m * N + k];
+}
 SEQM_GLOBAL void initial_density_kernel(seqm_batch_t b, double* __restrict__ P) {
   const MolView v = mol_view(b, blockIdx.x);
   const int n = v.n;
@@ -618,6 +733,25 @@ int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void*
   if (rc) return rc;
   SEQM_LAUNCH(orbitals_dense_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, C, V);
   return seqm_check_launch("orbitals_dense_kernel");
+}
+int seqm_mo_match(const seqm_batch_t* b, const double* V_new, const double* V_old, const double* e_in, double* S_scratch,
+                  int32_t* perm, int32_t* used, double* prio, double* V_out, double* e_out, void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (!V_new || !V_old || !e_in || !S_scratch || !perm || !used || !prio || !V_out || !e_out || V_out == V_new) {
+    seqm_set_error("seqm_mo_match: null buffer or V_out aliases V_new");
+    return SEQM_ERR_ARG;
+  }
+  long long per = (long long)b->nmax * b->nmax;
+  int parts = (int)((per + 8191) / 8192);  // ~32 overlap elements per thread
+  if (parts < 1) parts = 1;
+  if (parts > 1024) parts = 1024;
+  SEQM_LAUNCH(mo_overlap_kernel, b->nmol * parts, 256, 0, SEQM_STREAM(stream), *b, parts, V_old, V_new, S_scratch);
+  rc = seqm_check_launch("mo_overlap_kernel");
+  if (rc) return rc;
+  SEQM_LAUNCH(mo_match_kernel, b->nmol, 256, 0, SEQM_STREAM(stream), *b, V_new, (const double*)S_scratch, e_in, perm, used,
+              prio, V_out, e_out);
+  return seqm_check_launch("mo_match_kernel");
 }
 int seqm_gradient_xl(const seqm_batch_t* b, const double* xyz, const double* D, const double* P, double* pair_scratch,
                      double* grad, void* stream) {

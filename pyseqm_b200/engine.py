@@ -331,6 +331,18 @@ def op_orbitals_dense(plan, Cm):
     return V
 
 
+def op_mo_match(plan, V_new, V_old, e):
+    """Energy._crossing_match_molecular_orbitals[_grouped] (basics.py:596-719): V (nmol, nmax, nmax), e (nmol, nmax)."""
+    V_new, V_old, e = V_new.contiguous(), V_old.contiguous(), e.contiguous()
+    S = plan.new_mat()
+    ints = torch.empty((2, plan.nmol, plan.nmax), dtype=torch.int32, device=plan.device)
+    prio = torch.empty((plan.nmol, plan.nmax), dtype=torch.float64, device=plan.device)
+    V_out, e_out = torch.empty_like(V_new), torch.empty_like(e)
+    plan.lib.check(plan.lib.dll.seqm_mo_match(plan.ref, ptr(V_new), ptr(V_old), ptr(e), ptr(S), ptr(ints[0]), ptr(ints[1]),
+                                              ptr(prio), ptr(V_out), ptr(e_out), stream_of(V_new)), "seqm_mo_match")  # fmt: skip
+    return V_out, e_out
+
+
 def op_pack(plan, dense):
     out = plan.new_mat()
     d = dense.detach().contiguous()

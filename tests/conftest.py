@@ -17,8 +17,10 @@ def pytest_configure(config):
 
 def load_golden(name):
     d = dict(np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False))
-    d["seqm_parameters"] = json.loads(str(d["seqm_parameters"]))
-    d["n_scf_iter"] = int(d["n_scf_iter"])
+    if "seqm_parameters" in d:
+        d["seqm_parameters"] = json.loads(str(d["seqm_parameters"]))
+    if "n_scf_iter" in d:
+        d["n_scf_iter"] = int(d["n_scf_iter"])
     return d
 
 

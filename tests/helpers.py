@@ -314,3 +314,41 @@ def check_isolated_atoms(lib, device):
         assert abs(float(mol.dm[0].diagonal().sum()) - 6.0) < 1e-10
         if mol.dm.shape[0] > 1:
             assert np.abs(mol.dm[1].cpu().numpy() - ref["dm"][1]).max() < TOL_DM
+
+
+def check_mo_match(lib, device, name):
+    """seqm_mo_match against Energy._crossing_match_molecular_orbitals[_grouped] (basics.py:596-719) on crafted
+    orbital sets: the outputs are permuted / sign-flipped copies of the inputs, so the comparison is exact."""
+    g = load_golden(name)
+    plan = engine.BatchPlan(lib, torch.as_tensor(g["species"], device=device), "AM1")
+    assert plan.nocc.cpu().tolist() == g["nocc"].tolist()
+    V, e = engine.op_mo_match(plan, torch.as_tensor(g["V_new"], device=device), torch.as_tensor(g["V_old"], device=device),
+                              torch.as_tensor(g["e"], device=device))  # fmt: skip
+    assert np.array_equal(e.cpu().numpy(), g["e_out"])
+    assert np.array_equal(V.cpu().numpy(), g["V_out"])
+
+
+def check_two_forwards_match_orbitals(lib, device):
+    """Second forward on the same Molecule: orbitals and e_mo continue the first forward's (basics.py:846-857);
+    e_gap is taken before the matching."""
+    g = load_golden("md_momatch_two_forwards")
+    sp = {"method": "PM3", "scf_eps": 1e-8, "scf_converger": [2], "sp2": [False]}
+    mol, es = run_molecule(lib, device, g["species"], g["coordinates"].copy(), sp)
+    nmax = mol.molecular_orbitals.shape[1]
+    V1 = mol.molecular_orbitals.cpu().numpy().copy()
+    assert np.abs(mol.e_mo.cpu().numpy() - g["e1"]).max() < 1e-7
+    with torch.no_grad():
+        mol.coordinates += torch.as_tensor(g["displacement"], device=device)
+    es(mol)
+    assert np.abs(mol.Etot.cpu().numpy() - g["Etot2"]).max() < TOL_E
+    assert np.abs(mol.e_mo.cpu().numpy() - g["e2"]).max() < 1e-7
+    assert np.abs(mol.e_gap.cpu().numpy() - g["e_gap2"]).max() < 1e-7
+    # eigenvectors: the sign is fixed by continuity with the first forward, whose own signs are arbitrary -> compare
+    # the sign-invariant products V2[:, k] * <V1[:, k], V2[:, k]> ... through |overlap| with the reference's V2
+    V2, R2 = mol.molecular_orbitals.cpu().numpy(), g["V2"]
+    ov = np.abs(np.einsum("mrk,mrk->mk", V2, R2))
+    assert np.abs(ov - 1.0).max() < 1e-6
+    # and the relative sign between the two forwards is the reference's: <V1_k, V2_k> has the same sign in both
+    ours = np.einsum("mrk,mrk->mk", V1, V2)
+    ref = np.einsum("mrk,mrk->mk", g["V1"], R2)
+    assert (ours > 0).all() and (ref > 0).all() and nmax == R2.shape[1]

@@ -51,6 +51,19 @@ def test_single_point_golden(lib, dev, name):
     check_golden_case(lib, dev, name)
 
 
+@pytest.mark.parametrize("name", ["op_momatch_mixed", "op_momatch_uniform"])
+def test_mo_crossing_matcher(lib, dev, name):
+    from helpers import check_mo_match
+
+    check_mo_match(lib, dev, name)
+
+
+def test_second_forward_continues_the_orbitals(lib, dev):
+    from helpers import check_two_forwards_match_orbitals
+
+    check_two_forwards_match_orbitals(lib, dev)
+
+
 def test_pm6_on_elements_without_d_shell(lib, dev):
     from helpers import check_pm6_sp_elements
 

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import check_golden_case, check_operator_level, check_pm6_sp_elements, hostemu_lib, run_molecule
+from helpers import (check_golden_case, check_mo_match, check_operator_level, check_pm6_sp_elements,
+                     check_two_forwards_match_orbitals, hostemu_lib, run_molecule)
 
 CPU = torch.device("cpu")
 
@@ -35,6 +36,15 @@ def test_reference_operator_signatures(lib, method):
 )  # fmt: skip
 def test_single_point_golden(lib, name):
     check_golden_case(lib, CPU, name)
+
+
+@pytest.mark.parametrize("name", ["op_momatch_mixed", "op_momatch_uniform"])
+def test_mo_crossing_matcher(lib, name):
+    check_mo_match(lib, CPU, name)
+
+
+def test_second_forward_continues_the_orbitals(lib):
+    check_two_forwards_match_orbitals(lib, CPU)
 
 
 def test_pm6_on_elements_without_d_shell(lib):
