@@ -75,6 +75,12 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """Only rows sampled after this call are reported (the timed region).  The sampler itself is started before
+        the warm-up steps: nvidia-smi's start-up (NVML attaching to every GPU of the box) stalls the driver for
+        ~0.1-0.2 s on multi-GPU boxes, which must not land inside a timed step."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -84,7 +90,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[getattr(self, "first", 0):]:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -253,12 +259,14 @@ def main():
             return gather_results(dict(Etot=mol.Etot, Hf=mol.Hf, force=mol.force), gidx, nmol * world)
         return None
 
-    for _ in range(max(3, args.warmup)):
-        step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    if rank == 0:
+        sampler.mark()
     launches0 = lib.dll.seqm_launch_count()
     ms = []
     for _ in range(args.steps):
@@ -271,6 +279,7 @@ def main():
         barrier()
         ms.append(e0.elapsed_time(e1))
     launches = lib.dll.seqm_launch_count() - launches0
+    print("resident step times (ms):", [round(x, 2) for x in ms], file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     t_local = torch.tensor([sum(ms) / len(ms)], device=dev)
     if world > 1:
