@@ -352,3 +352,33 @@ def check_two_forwards_match_orbitals(lib, device):
     ours = np.einsum("mrk,mrk->mk", V1, V2)
     ref = np.einsum("mrk,mrk->mk", g["V1"], R2)
     assert (ours > 0).all() and (ref > 0).all() and nmax == R2.shape[1]
+
+
+def check_mo_match_vs_oracle(lib, device, nmol=24, seed=17):
+    """seqm_mo_match against the oracle's restatement on a seeded ragged batch (QM9-like molecules, random orthogonal
+    old orbitals, new = old mixed inside the occupied / virtual blocks with strengths from 'barely' to 'scrambled')."""
+    import seqm_oracle as so
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    species, _ = qm9_like_batch(nmol, seed=seed)
+    plan = engine.BatchPlan(lib, torch.as_tensor(species, device=device), "PM3")
+    nocc, norb = plan.nocc.cpu().numpy(), (4 * plan.nheavy + plan.nhyd).cpu().numpy()
+    nmax = plan.nmax
+    rng = np.random.default_rng(seed)
+    V_old = np.tile(np.eye(nmax), (nmol, 1, 1))
+    V_new = V_old.copy()
+    e = np.zeros((nmol, nmax))
+    for m in range(nmol):
+        n, no = int(norb[m]), int(nocc[m])
+        q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        new = q * rng.choice([-1.0, 1.0], n)
+        for lo, hi in ((0, no), (no, n)):
+            g, _ = np.linalg.qr(np.eye(hi - lo) + 10.0 ** rng.uniform(-2, 0.3) * rng.standard_normal((hi - lo, hi - lo)))
+            new[:, lo:hi] = new[:, lo:hi][:, rng.permutation(hi - lo)] @ g
+        V_old[m, :n, :n], V_new[m, :n, :n] = q, new
+        e[m, :n] = np.sort(rng.uniform(-40.0, 5.0, n))
+    V_ref, e_ref = so.match_orbitals(V_new, V_old, nocc, norb, e)
+    V, eo = engine.op_mo_match(plan, torch.as_tensor(V_new, device=device), torch.as_tensor(V_old, device=device),
+                               torch.as_tensor(e, device=device))  # fmt: skip
+    assert np.array_equal(eo.cpu().numpy(), e_ref)
+    assert np.array_equal(V.cpu().numpy(), V_ref)

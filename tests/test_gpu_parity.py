@@ -58,6 +58,12 @@ def test_mo_crossing_matcher(lib, dev, name):
     check_mo_match(lib, dev, name)
 
 
+def test_mo_crossing_matcher_against_oracle(lib, dev):
+    from helpers import check_mo_match_vs_oracle
+
+    check_mo_match_vs_oracle(lib, dev, nmol=96)
+
+
 def test_second_forward_continues_the_orbitals(lib, dev):
     from helpers import check_two_forwards_match_orbitals
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (check_golden_case, check_mo_match, check_operator_level, check_pm6_sp_elements,
+from helpers import (check_golden_case, check_mo_match, check_mo_match_vs_oracle, check_operator_level, check_pm6_sp_elements,
                      check_two_forwards_match_orbitals, hostemu_lib, run_molecule)
 
 CPU = torch.device("cpu")
@@ -41,6 +41,10 @@ def test_single_point_golden(lib, name):
 @pytest.mark.parametrize("name", ["op_momatch_mixed", "op_momatch_uniform"])
 def test_mo_crossing_matcher(lib, name):
     check_mo_match(lib, CPU, name)
+
+
+def test_mo_crossing_matcher_against_oracle(lib):
+    check_mo_match_vs_oracle(lib, CPU)
 
 
 def test_second_forward_continues_the_orbitals(lib):

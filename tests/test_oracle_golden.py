@@ -137,6 +137,16 @@ def test_input_validation_matches_reference_errors():
         so.parse(s, c)
 
 
+@pytest.mark.parametrize("name", ["op_momatch_mixed", "op_momatch_uniform"])
+def test_mo_crossing_matcher_matches_reference(name):
+    """oracle restatement of basics.py:596-719 against the reference's own outputs on crafted orbital sets (row argmax
+    and greedy-repair routes, block-internal permutations, sign flips): permuted copies, so exact."""
+    g = load_golden(name)
+    V, e = so.match_orbitals(g["V_new"], g["V_old"], g["nocc"], g["norb"], g["e"])
+    assert np.array_equal(e, g["e_out"])
+    assert np.array_equal(V, g["V_out"])
+
+
 def test_rotation_invariance():
     """tests/unit/test_invariants.py:28-55: Etot invariant, forces co-rotate (z rotation by 0.7 rad)."""
     s, c = so.read_xyz([os.path.join(XYZ, "methane.xyz")])
