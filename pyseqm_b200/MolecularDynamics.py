@@ -145,8 +145,15 @@ class XL_BOMD(Molecular_Dynamics_Basic):
     def initialize(self, molecule, remove_com=None, learned_parameters=dict(), steps=None, *args, **kwargs):
         molecule.Electronic_entropy = torch.zeros(molecule.species.shape[0], dtype=torch.float64,
                                                   device=molecule.coordinates.device)  # fmt: skip
+        if self.step_offset > 0 and self._ctx is not None and self._ctx.get("plan") is molecule._plan:
+            # resume (MolecularDynamics.py:1530-1541): restored XL state (P, Pt, D) survives; only the MD bookkeeping
+            # of the base class is redone
+            self.set_dof(molecule)
+            self.initialize_velocity(molecule)
+            return
         super().initialize(molecule, remove_com=remove_com, learned_parameters=learned_parameters, steps=steps)
         plan = molecule._plan
+        molecule.__dict__.pop("_C_xl", None)  # a new trajectory starts its density solves cold
         with torch.no_grad():
             dm = molecule.dm
             if molecule.orbital_stride != 4:  # method="PM6": back to the 4-slot layout the packed kernels use
@@ -154,7 +161,7 @@ class XL_BOMD(Molecular_Dynamics_Basic):
 
                 dm = narrow_orbitals(dm, plan.molsize, molecule.orbital_stride)
             Dp = engine.op_pack(plan, dm)  # converged SCF density at t = 0
-            self._ctx = {"P": Dp.clone(), "Pt": Dp.unsqueeze(0).repeat(self.m, 1), "D": Dp}
+            self._ctx = {"P": Dp.clone(), "Pt": Dp.unsqueeze(0).repeat(self.m, 1), "D": Dp, "plan": plan}
         self.coeff = self.coeff.to(molecule.coordinates.device)
 
     def one_step(self, molecule, step, learned_parameters=dict(), *args, **kwargs):
@@ -171,7 +178,10 @@ class XL_BOMD(Molecular_Dynamics_Basic):
             P = engine.op_xl_propagate(plan, self.coeff_D, c, ctx["D"], ctx["P"], ctx["Pt"],
                                        self.coeff[cindx : cindx + self.m].contiguous(), self.m - 1 - cindx)
             ctx["P"] = P
-        r = self.esdriver.conservative_force_xl.forward_packed(molecule, P, want_e=False)  # MD needs D, E, forces only
+        # MD needs D, E, forces only.  molecule.dm / molecule.q are refreshed at the end of run() (or on demand by
+        # refresh_density()); inside the loop the density lives in the packed layout (molecule._dm_packed)
+        r = self.esdriver.conservative_force_xl.forward_packed(molecule, P, want_e=False,
+                                                               learned_parameters=learned_parameters)
         ctx["D"] = r["D"]
         molecule.force, molecule.Hf, molecule.Etot = r["force"], r["Hf"], r["Etot"]
         molecule.Eelec, molecule.Enuc, molecule.Eiso = r["Eelec"], r["Enuc"], r["Eiso"]
@@ -187,12 +197,20 @@ class XL_BOMD(Molecular_Dynamics_Basic):
     def _do_integrator_step(self, i, molecule, learned_parameters, **kwargs):
         return self.one_step(molecule, i, learned_parameters=learned_parameters, **kwargs)
 
+    def refresh_density(self, molecule):
+        """Dense `molecule.dm` (and Mulliken `molecule.q`) of the latest step.  The step loop keeps the density packed;
+        observers that read `molecule.dm` mid-run call this first (run() does at its end)."""
+        if self._ctx is None:
+            return
+        molecule.dm = engine.op_unpack(molecule._plan, self._ctx["D"])
+        if molecule.orbital_stride != 4:
+            from .Molecule import widen_orbitals
+
+            molecule.dm = widen_orbitals(molecule.dm, molecule._plan.molsize, molecule.orbital_stride)
+        molecule.q = molecule.const.tore[molecule.species] - Electronic_Structure.atomic_charges(
+            molecule.dm, n_orbital=molecule.orbital_stride)
+
     def run(self, molecule, steps, *args, **kwargs):
         out = super().run(molecule, steps, *args, **kwargs)
-        if self._ctx is not None:
-            molecule.dm = engine.op_unpack(molecule._plan, self._ctx["D"])  # dense density of the last step
-            if molecule.orbital_stride != 4:
-                from .Molecule import widen_orbitals
-
-                molecule.dm = widen_orbitals(molecule.dm, molecule._plan.molsize, molecule.orbital_stride)
+        self.refresh_density(molecule)
         return out

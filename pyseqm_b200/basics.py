@@ -187,11 +187,16 @@ class ForceXL(torch.nn.Module):
         self.seqm_parameters = seqm_parameters
         self.Hf_flag = seqm_parameters.get("Hf_flag", True)
         self.sp2 = seqm_parameters.get("sp2", [False])
-        self._C = None  # eigenvectors of the previous step: warm start of the next density solve
+        # the warm-start eigenvectors of the previous step live on the MOLECULE, tagged with its plan (`_C_xl`): a
+        # driver reused for another batch must never feed the eigensolver a guess that belongs to a different plan
 
-    def forward_packed(self, molecule, Pp, want_e=True):
+    def forward_packed(self, molecule, Pp, want_e=True, learned_parameters=None):
         plan = molecule._plan
         const = molecule.const
+        if learned_parameters:  # xlbomd.py:90-116 re-packs the parameters on every step
+            if callable(learned_parameters):
+                raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
+            plan.set_parameters({k: learned_parameters[k] for k in self.seqm_parameters.get("learned", [])})
         t0 = time.time()
         xyz = molecule._refresh_geometry()
         w, hab = engine.op_pair_integrals(plan, xyz)
@@ -202,7 +207,11 @@ class ForceXL(torch.nn.Module):
             D, _ = engine.op_sp2_density(plan, F, self.sp2[1])
             e_mo_n = None
         else:
-            e_mo_n, D, self._C = engine.op_eig_density(plan, F, want_P=True, want_C=True, Cguess=self._C, want_e=want_e)
+            tag, C0 = molecule.__dict__.get("_C_xl", (None, None))
+            if tag is not plan or C0 is None or C0.numel() != plan.mat_total:
+                C0 = None
+            e_mo_n, D, C1 = engine.op_eig_density(plan, F, want_P=True, want_C=True, Cguess=C0, want_e=want_e)
+            molecule.__dict__["_C_xl"] = (plan, C1)
         t0 = _timing(molecule, "D*", t0)
         Eelec = engine.op_elec_energy_xl(plan, D, Pp, F, H)
         EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)
@@ -223,7 +232,7 @@ class ForceXL(torch.nn.Module):
         if molecule.orbital_stride != 4:
             raise NotImplementedError("XL-BOMD with method='PM6' is not on the B200 path; use 'PM6_SP' for sp-only elements")
         plan = molecule._plan
-        r = self.forward_packed(molecule, engine.op_pack(plan, P))
+        r = self.forward_packed(molecule, engine.op_pack(plan, P), learned_parameters=learned_parameters)
         Dd = engine.op_unpack(plan, r["D"])
         _ground_dipole(molecule, Dd)
         N = 4 * plan.molsize

@@ -1,5 +1,8 @@
 // seqm_b200.cu -- C-ABI entry points of libseqm_b200.so (see include/seqm_b200.h) and the SCF host loop.
 // Single translation unit: all kernels live in the .cuh files included below.
+#include <mutex>
+#include <vector>
+
 #include "pair_kernels.cuh"
 #include "scf_driver.cuh"
 #include "plan_kernels.cuh"
@@ -47,11 +50,29 @@ static void prof_end(cudaStream_t) {}
 static int g_num_sms = 148;
 static int g_smem_optin = 227 * 1024;
 static int g_dev_ready = 0;
+static int g_device = -1;  // the ONE device this process-wide library state (function attributes, streams, events) is for
+// Process-wide state (opt-in shared-memory attributes, eigensolver class streams, pipeline streams/events, the pinned
+// convergence mailbox) belongs to one device and one caller at a time: one process per GPU.  A call
+// with another current device fails loudly; concurrent calls from several host threads are serialised by g_api_mutex.
+static std::mutex g_api_mutex;
+#define SEQM_SERIAL std::lock_guard<std::mutex> seqm_serial_guard(g_api_mutex)
 static int ensure_device() {
-  if (g_dev_ready) return SEQM_OK;
 #ifndef SEQM_HOSTEMU
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
+  if (g_dev_ready) {
+    if (e == cudaSuccess && dev != g_device) {
+      seqm_set_error("libseqm_b200 holds per-device state for cuda:%d but the current device is cuda:%d: run one process "
+                     "per GPU (torch.cuda.set_device(LOCAL_RANK) before the first call)", g_device, dev);
+      return SEQM_ERR_UNSUPPORTED;
+    }
+    return SEQM_OK;
+  }
+  g_device = dev;
+#else
+  if (g_dev_ready) return SEQM_OK;
+#endif
+#ifndef SEQM_HOSTEMU
   if (e != cudaSuccess) {
     seqm_set_error("cudaGetDevice: %s (libseqm_b200 needs a CUDA device; there is no CPU fallback)", cudaGetErrorString(e));
     return SEQM_ERR_CUDA;
@@ -103,8 +124,10 @@ static int grid1d(long long n, int block);
 // ---- large-molecule helpers (host side) ------------------------------------------------------------------
 struct HostMol { long long mat0; int n, nocc; };
 static int fetch_host_mols(const seqm_batch_t* b, HostMol* hm, cudaStream_t st) {
-  long long* m0 = new long long[b->nmol + 1];
-  int *nh = new int[b->nmol], *ny = new int[b->nmol], *no = new int[b->nmol];
+  std::vector<long long> m0v(b->nmol + 1);
+  std::vector<int> nhv(b->nmol), nyv(b->nmol), nov(b->nmol);
+  long long* m0 = m0v.data();
+  int *nh = nhv.data(), *ny = nyv.data(), *no = nov.data();
 #ifndef SEQM_HOSTEMU
   cudaError_t e = cudaMemcpyAsync(m0, b->mol_mat0, sizeof(long long) * (b->nmol + 1), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(nh, b->mol_nheavy, sizeof(int) * b->nmol, cudaMemcpyDeviceToHost, st);
@@ -120,7 +143,6 @@ static int fetch_host_mols(const seqm_batch_t* b, HostMol* hm, cudaStream_t st) 
   memcpy(no, b->mol_nocc, sizeof(int) * b->nmol);
 #endif
   for (int m = 0; m < b->nmol; ++m) { hm[m].mat0 = m0[m]; hm[m].n = 4 * nh[m] + ny[m]; hm[m].nocc = no[m]; }
-  delete[] m0; delete[] nh; delete[] ny; delete[] no;
   return SEQM_OK;
 }
 static int fetch_host_ints(const int32_t* dev, int32_t* host, int n, cudaStream_t st) {
@@ -638,6 +660,7 @@ int seqm_fock(const seqm_batch_t* b, const double* P, const double* H, const dou
 
 int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const double* Cguess,
                      const int32_t* active, void* stream) {
+  SEQM_SERIAL;
   int rc = check_batch(b);
   if (rc) return rc;
   rc = check_small(b, "seqm_eig_density");
@@ -667,7 +690,8 @@ int seqm_sp2_density_large(const seqm_batch_t* b, const double* F, double* P, do
   int rc = check_batch(b);
   if (rc) return rc;
   cudaStream_t st = SEQM_STREAM(stream);
-  HostMol* hm = new HostMol[b->nmol];
+  std::vector<HostMol> hmv(b->nmol);
+  HostMol* hm = hmv.data();
   rc = fetch_host_mols(b, hm, st);
   unsigned char* base = (unsigned char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   const size_t big = (sizeof(double) * (size_t)b->nmax * b->nmax + 255) & ~(size_t)255;
@@ -679,7 +703,6 @@ int seqm_sp2_density_large(const seqm_batch_t* b, const double* F, double* P, do
     rc = sp2_large_one(hm[m].n, hm[m].nocc, F + hm[m].mat0, P + hm[m].mat0, eps, X, X2, stt, &it, st);
     if (niter_host) niter_host[m] = it;
   }
-  delete[] hm;
   return rc;
 }
 
@@ -916,6 +939,18 @@ static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, c
     cudaStreamWaitEvent(hs[0], g_ev_fork, 0);
     cudaStreamWaitEvent(hs[1], g_ev_fork, 0);
   }
+  // every exit path (errors included) re-joins the caller's stream behind whatever is queued on the half streams
+  struct PipeJoin {
+    cudaStream_t st, *hs;
+    bool on;
+    ~PipeJoin() {
+      if (!on) return;
+      for (int h = 0; h < 2; ++h) {
+        cudaEventRecord(g_ev_join[h], hs[h]);
+        cudaStreamWaitEvent(st, g_ev_join[h], 0);
+      }
+    }
+  } pipe_join{st, hs, nh == 2};
 #endif
   // half-batch views: same arrays, own processing order / size-class ranges / control block
   seqm_batch_t bh[2] = {*b, *b};
@@ -1038,20 +1073,13 @@ static int scf_diis_pipelined(const seqm_batch_t* b, const seqm_scf_opts_t* o, c
     }
   }
 #undef CHKP
-#ifndef SEQM_HOSTEMU
-  if (nh == 2) {
-    for (int h = 0; h < 2; ++h) {
-      cudaEventRecord(g_ev_join[h], hs[h]);
-      cudaStreamWaitEvent(st, g_ev_join[h], 0);
-    }
-  }
-#endif
   *n_iter = (done_at >= 0) ? done_at : max_iter + 1;
   return SEQM_OK;
 }
 
 int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, const double* w, double* P, double* F,
              double* Eelec, int32_t* notconverged, void* workspace, int32_t* n_iter_out, double* C_last, void* stream) {
+  SEQM_SERIAL;
   int rc = check_batch(b);
   if (rc) return rc;
   if (o->converger < 0 || o->converger > 2) {
@@ -1074,6 +1102,8 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   CHK("scf_init_kernel");
   // F(P0), Eelec(P0)
   const bool large = b->nmax > SEQM_MAX_ORB;
+  std::vector<HostMol> hmv;
+  std::vector<int32_t> h_activev;
   HostMol* hm = nullptr;
   int32_t* h_active = nullptr;
   if (large) {
@@ -1082,8 +1112,10 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
                      "is shared-memory resident", SEQM_MAX_ORB);
       return SEQM_ERR_TOO_LARGE;
     }
-    hm = new HostMol[b->nmol];
-    h_active = new int32_t[b->nmol];
+    hmv.resize(b->nmol);
+    h_activev.resize(b->nmol);
+    hm = hmv.data();
+    h_active = h_activev.data();
     rc = fetch_host_mols(b, hm, st);
     if (rc) return rc;
     for (int m = 0; m < b->nmol; ++m) h_active[m] = 1;
@@ -1254,8 +1286,6 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   }
   if (o->converger == 2 && !pipelined) printed = (k > k_last) ? k_last + 1 : k;
   if (n_iter_out) *n_iter_out = printed;
-  delete[] hm;
-  delete[] h_active;
 #ifndef SEQM_HOSTEMU
   cudaError_t e = cudaMemcpyAsync(Eelec, W.Eel_new, sizeof(double) * b->nmol, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess && C_last && have_C)

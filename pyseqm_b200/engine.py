@@ -254,6 +254,9 @@ def op_fock(plan, P, H, w, active=None, out=None):
 def op_eig_density(plan, F, want_P=True, want_C=False, Cguess=None, active=None, want_e=True):
     """want_e=False asks for the density only: the eigensolver may then finish with its first-order
     occupied-virtual correction instead of a last sweep (eig_kernels.cuh); eigenvalues are not returned."""
+    if Cguess is not None and (Cguess.numel() != plan.mat_total or Cguess.device != plan.device):
+        raise SeqmError(f"op_eig_density: warm-start eigenvectors hold {Cguess.numel()} elements on {Cguess.device}, the "
+                        f"plan has {plan.mat_total} on {plan.device} (a guess from another batch plan?)")
     P = plan.new_mat() if (want_P or Cguess is not None) else None
     Cm = plan.new_mat() if (want_C or Cguess is not None) else None  # the warm start needs both scratch slots
     e = torch.zeros((plan.nmol, plan.nmax), dtype=torch.float64, device=plan.device) if want_e else None

@@ -156,6 +156,29 @@ def test_full_size_properties(lib, dev):
     assert float((a.Etot.cpu() - mol.Etot[idx].cpu()).abs().max()) < 1e-5  # different convergers, same fixed point
 
 
+def test_baseline_size_sub_batch_against_reference(lib, dev):
+    """configs[1] at BASELINE scale: the first 512 molecules of the bench batch as their own batch (the batch-global
+    DIIS reset then sees the same set on both sides) against the unmodified reference (oracle/_ref) when the install
+    travelled with the snapshot, else against the numpy oracle.  north_star tolerances, equal iteration count."""
+    import ref_runner
+    import seqm_oracle as so
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    species, coords = qm9_like_batch(512, seed=0)
+    sp = {"method": "PM3", "scf_eps": 1e-7, "scf_converger": [2], "sp2": [False], "analytical_gradient": [True]}
+    if ref_runner.reference_available():
+        ref, _ = ref_runner.run_reference(species, coords, sp)
+    else:
+        ref = so.single_point(species, coords, sp)
+    mol, es = run_molecule(lib, dev, species, coords, sp)
+    assert not bool(es.notconverged.any()) and not np.asarray(ref["notconverged"]).any()
+    assert mol.n_scf_iter == ref["n_scf_iter"]
+    assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < TOL_E
+    assert np.abs(mol.Hf.cpu().numpy() - ref["Hf"]).max() < TOL_E
+    assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < TOL_DM
+    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F
+
+
 def test_rotation_and_translation_invariance(lib, dev):
     from pyseqm_b200.synthetic import qm9_like_batch
 

@@ -157,3 +157,17 @@ def test_rotation_invariance():
     b = so.single_point(s, c @ R.T, sp)
     assert abs(a["Etot"][0] - b["Etot"][0]) < 1e-7
     assert np.abs(a["force"] @ R.T - b["force"]).max() < 1e-5
+
+
+def test_installed_reference_reproduces_its_golden():
+    """oracle/_ref (the unmodified reference installed by oracle/ref_runner.py) is what bench.py's reference arm and
+    parity-at-size check run: it must reproduce the fixture the same code generated from /root/reference."""
+    import ref_runner
+
+    if not ref_runner.reference_available():
+        pytest.skip("oracle/_ref not installed (build() installs it where /root/reference exists)")
+    g = load_golden("cfg1_AM1_c2")
+    out, _ = ref_runner.run_reference(g["species"], g["coordinates"], g["seqm_parameters"])
+    assert out["n_scf_iter"] == int(g["n_scf_iter"])
+    assert np.abs(out["Etot"] - g["Etot"]).max() < 1e-9
+    assert np.abs(out["force"] - g["force"]).max() < 1e-8

@@ -63,6 +63,40 @@ def test_two_rank_sharded_forward(tmp_path):
     assert np.abs(got["force"] - g["force"]).max() < 1e-5
 
 
+def _gather_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyseqm_b200.sharding import gather_results, shard_indices
+
+    n = 11
+    ok = True
+    # two shardings of the same size with different cost orders, gathered back to back from freshly allocated index
+    # tensors (the round-1 cache keyed on data_ptr could serve the first plan to the second call), plus an uneven one
+    for trial, cost in enumerate([torch.arange(n, dtype=torch.float64), torch.arange(n, dtype=torch.float64).flip(0) ** 2,
+                                  torch.tensor([3.0, 1, 4, 1, 5, 9, 2, 6, 5, 3, 5])]):
+        idx = shard_indices(cost, world, rank)
+        vals = {"a": idx.to(torch.float64) * 10.0 + trial, "b": torch.stack((idx, 2 * idx), dim=1).to(torch.float64),
+                "flag": (idx % 2).to(torch.int32)}
+        out = gather_results(vals, idx, n, nmax=None if trial == 2 else -(-n // world))
+        g = torch.arange(n)
+        ok &= bool(torch.equal(out["a"], g.to(torch.float64) * 10.0 + trial))
+        ok &= bool(torch.equal(out["b"], torch.stack((g, 2 * g), dim=1).to(torch.float64)))
+        ok &= bool(torch.equal(out["flag"], (g % 2).to(torch.int32)))
+        del idx
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_two_orderings_back_to_back(tmp_path):
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert bool(np.load(os.path.join(str(tmp_path), f"ok{r}.npy"))[0])
+
+
 def test_shard_indices_balance_and_cover():
     from pyseqm_b200.sharding import shard_indices
 

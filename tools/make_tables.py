@@ -15,7 +15,7 @@ import os
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "h5py_stub"))
+sys.path.insert(0, os.path.join(HERE, "..", "oracle", "h5py_stub"))
 sys.path.insert(0, "/root/reference")
 OUT = os.path.join(HERE, "..", "pyseqm_b200", "data")
 

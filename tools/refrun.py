@@ -8,7 +8,7 @@ import sys
 import warnings
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "h5py_stub"))
+sys.path.insert(0, os.path.join(HERE, "..", "oracle", "h5py_stub"))
 sys.path.insert(0, "/root/reference")
 warnings.filterwarnings("ignore", category=SyntaxWarning)
 
