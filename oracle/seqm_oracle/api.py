@@ -54,7 +54,11 @@ def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True, 
         d_shell = (((s > 12) & (s < 18)) | ((s > 20) & (s < 30)) | ((s > 32) & (s < 36)) | ((s > 38) & (s < 48))
                    | ((s > 50) & (s < 54)) | ((s > 70) & (s < 80)) | (s == 57))  # fmt: skip
         if d_shell.any():
-            raise NotImplementedError("oracle covers PM6 only for elements without a d shell")
+            from .pm6d import single_point_pm6d
+
+            if learned_parameters:
+                raise NotImplementedError("oracle: learned parameters with PM6 d-shell elements are not covered")
+            return single_point_pm6d(species, coordinates, seqm_parameters, P0=P0, do_force=do_force, charges=charges)
         method = "PM6_SP"
     if method not in ("MNDO", "AM1", "PM3", "PM6_SP"):
         raise NotImplementedError(f"oracle covers MNDO/AM1/PM3/PM6_SP, not {method}")

@@ -88,26 +88,31 @@ def _diis_coeff(EVEC, cF):
     return coeff, cond
 
 
-def run_scf(P, par, H, w, D0, eps, converger=(2,), sp2=(False,), verbose=False):
-    """Returns (D, notconverged, n_iter).  D0 is not modified."""
+def run_scf(P, par, H, w, D0, eps, converger=(2,), sp2=(False,), verbose=False, fock_fn=None, density_fn=None, msize=None):
+    """Returns (D, notconverged, n_iter).  D0 is not modified.
+    fock_fn(Pm) / density_fn(F, mask) / msize: the PM6 d-orbital path (pm6d.py) plugs its 9-slot Fock build, packed
+    eigensolver and matrix_size_sqrt = 9 nSH + 4 nHeavy + 4 nHydro (scf_loop.py:245) into the same loop."""
+    build = fock_fn if fock_fn is not None else (lambda Pm_: build_fock(P, par, H, w, Pm_))
     nmol = P.nmol
     N = H.shape[1]
     S = _State()
     S.err = np.ones(nmol)
     S.dm_err = np.ones(nmol)
     S.dm_elem = np.ones(nmol)
-    S.msize = (4 * P.nHeavy + 4 * P.nHydro).astype(np.float64)  # scf_loop.py:728 ("sqrt of size")
+    S.msize = (4 * P.nHeavy + 4 * P.nHydro).astype(np.float64) if msize is None else np.asarray(msize, dtype=np.float64)  # scf_loop.py:728
     Pm = D0.copy()
     Pold = np.zeros_like(Pm)
     Pnew = np.zeros_like(Pm)
     nc = np.ones(nmol, dtype=bool)
 
     def make_pnew(F, mask):
+        if density_fn is not None:
+            return density_fn(F, mask)
         if sp2[0]:
             return sp2_density(F, P.nHeavy, P.nHydro, P.nocc, sp2[1], mask)
         return density_from_fock(F, P.nHeavy, P.nHydro, P.nocc, mask)[0]
 
-    F = build_fock(P, par, H, w, Pm)
+    F = build(Pm)
     S.Eel = elec_energy(Pm, F, H)
     Eel_new = np.zeros(nmol)
     kind = converger[0]
@@ -126,7 +131,7 @@ def run_scf(P, par, H, w, D0, eps, converger=(2,), sp2=(False,), verbose=False):
                 Pmix, dprev = _adaptive_mix(k, Pm[nc], Pnew[nc], old2[nc])
                 Pm[nc] = Pmix
                 old2[nc] = dprev
-            F = build_fock(P, par, H, w, Pm)
+            F = build(Pm)
             Eel_new[nc] = elec_energy(Pm[nc], F[nc], H[nc])
             nc_new = _get_error(S, Pold, Pm, nc, Eel_new, eps)
             nc = nc_new
@@ -176,7 +181,7 @@ def run_scf(P, par, H, w, D0, eps, converger=(2,), sp2=(False,), verbose=False):
             Pm[nc] = 0.5 * Pm[nc] + 0.5 * Pnew[nc]
         else:
             Pm[nc] = Pnew[nc]
-        F = build_fock(P, par, H, w, Pm)
+        F = build(Pm)
         Eel_new[nc] = elec_energy(Pm[nc], F[nc], H[nc])
         nc = _get_error(S, Pold, Pm, nc, Eel_new, eps, diis_error)
         S.Eel[nc] = Eel_new[nc]

@@ -10,9 +10,14 @@ import hashlib
 
 import numpy as np
 
-_VALENCE = {6: 4, 7: 3, 8: 2}
+_VALENCE = {6: 4, 7: 3, 8: 2, 15: 3, 16: 2, 17: 1}
+_NVAL_E = {1: 1, 6: 4, 7: 5, 8: 6, 15: 5, 16: 6, 17: 7}
 _BOND = {(6, 6): 1.53, (6, 7): 1.47, (6, 8): 1.43, (7, 7): 1.45, (7, 8): 1.40, (8, 8): 1.48,
-         (1, 6): 1.09, (1, 7): 1.01, (1, 8): 0.96}  # fmt: skip
+         (1, 6): 1.09, (1, 7): 1.01, (1, 8): 0.96,
+         # third-row substituents of BASELINE configs[4] (PM6 with d orbitals on P / S / Cl)
+         (6, 15): 1.84, (6, 16): 1.82, (6, 17): 1.77, (7, 15): 1.70, (7, 16): 1.68, (7, 17): 1.75, (8, 15): 1.63,
+         (8, 16): 1.60, (8, 17): 1.70, (15, 15): 2.21, (15, 16): 2.10, (15, 17): 2.04, (16, 16): 2.05, (16, 17): 2.01,
+         (17, 17): 1.99, (1, 15): 1.42, (1, 16): 1.34, (1, 17): 1.27}  # fmt: skip
 _TET = np.array([[1.0, 1.0, 1.0], [1.0, -1.0, -1.0], [-1.0, 1.0, -1.0], [-1.0, -1.0, 1.0]]) / np.sqrt(3.0)
 
 
@@ -44,11 +49,15 @@ def _frame(rng, back=None):
     return d @ Rm.T
 
 
-def _one_molecule(rng, max_atoms):
+def _one_molecule(rng, max_atoms, hetero=None):
     for _attempt in range(200):
         nheavy = int(rng.integers(4, 10))
         Z = [int(rng.choice([6, 7, 8], p=[0.7, 0.15, 0.15])) for _ in range(nheavy)]
         Z[0] = 6
+        if hetero:  # configs[4]: one or two heavy sites (never the root) carry an element of `hetero`
+            nsub = 1 + int(rng.integers(2))
+            for site in rng.choice(np.arange(1, nheavy), size=min(nsub, nheavy - 1), replace=False):
+                Z[int(site)] = int(rng.choice(list(hetero)))
         pos = [np.zeros(3)]
         dirs = [list(_frame(rng))]  # unused bond directions per heavy atom
         nb = [0]
@@ -78,7 +87,7 @@ def _one_molecule(rng, max_atoms):
                 allZ.append(1)
                 bonded.add((i, len(allZ) - 1))
         n = len(allZ)
-        if n > max_atoms or (sum({6: 4, 7: 5, 8: 6, 1: 1}[z] for z in allZ) % 2):
+        if n > max_atoms or (sum(_NVAL_E[z] for z in allZ) % 2):
             continue
         X = np.asarray(allpos)
         dist = np.linalg.norm(X[:, None] - X[None], axis=-1)
@@ -88,6 +97,8 @@ def _one_molecule(rng, max_atoms):
                 if (a, b) in bonded:
                     continue
                 lim = 2.0 if (allZ[a] > 1 and allZ[b] > 1) else 1.6
+                if allZ[a] > 10 or allZ[b] > 10:
+                    lim += 0.3
                 if dist[a, b] < lim:
                     good = False
                     break
@@ -101,13 +112,15 @@ def _one_molecule(rng, max_atoms):
     raise RuntimeError("synthetic generator failed to place a molecule")
 
 
-def qm9_like_batch(nmol, seed=0, molsize=29, start=0):
-    """Returns (species int64 (nmol, molsize), coordinates float64 (nmol, molsize, 3))."""
+def qm9_like_batch(nmol, seed=0, molsize=29, start=0, hetero=None):
+    """Returns (species int64 (nmol, molsize), coordinates float64 (nmol, molsize, 3)).
+    hetero: e.g. (15, 16, 17) substitutes P / S / Cl at one or two heavy sites of every molecule (BASELINE configs[4]);
+    None (default) leaves the CHNO stream of configs[1] bit-for-bit unchanged."""
     species = np.zeros((nmol, molsize), dtype=np.int64)
     coords = np.zeros((nmol, molsize, 3), dtype=np.float64)
     for i in range(nmol):
         rng = np.random.default_rng([seed, start + i])
-        z, x = _one_molecule(rng, molsize)
+        z, x = _one_molecule(rng, molsize, hetero)
         species[i, : z.shape[0]] = z
         coords[i, : z.shape[0]] = x
     return species, coords

@@ -171,3 +171,61 @@ def test_installed_reference_reproduces_its_golden():
     assert out["n_scf_iter"] == int(g["n_scf_iter"])
     assert np.abs(out["Etot"] - g["Etot"]).max() < 1e-9
     assert np.abs(out["force"] - g["force"]).max() < 1e-8
+
+
+# ---- PM6 with d orbitals: oracle/seqm_oracle/pm6d.py against tools/make_golden_pm6d.py fixtures -------------
+PM6D_CASES = ["pm6d_organics_c1", "pm6d_organics_c2", "pm6d_organics_c0", "pm6d_diatomics_rotated", "pm6d_cfg5_16",
+              "pm6d_notebook_diatomics"]  # fmt: skip
+
+
+def _pm6d_setup(g):
+    from seqm_oracle import pm6d
+    from seqm_oracle.tables import method_parameters
+
+    P = so.parse(g["species"], g["coordinates"])
+    par = method_parameters("PM6", P.Z)
+    mpd = pm6d.atom_multipoles_spd(P.Z, par, so.atom_multipoles(P.Z, par))
+    return pm6d, P, par, mpd
+
+
+@pytest.mark.parametrize("name", ["pm6d_organics_c1", "pm6d_diatomics_rotated", "pm6d_notebook_diatomics"])
+def test_pm6d_operators_match_reference(name):
+    """45 x 45 two-centre integrals (generic point-charge multipole engine vs the reference's unrolled formulas), spd
+    overlaps, Hcore and the 9 x 9 Fock build incl. the one-centre d integrals derived from Slater-Condon factors."""
+    g = load_golden(name)
+    pm6d, P, par, mpd = _pm6d_setup(g)
+    hc = pm6d.build_hcore_spd(P, par, mpd)
+    assert np.abs(hc["w"] - g["op_w"].transpose(0, 2, 1)).max() < 1e-9  # the reference stores [j-pair, i-pair]
+    assert np.abs(hc["di"] - g["op_di"]).max() < 1e-12
+    m = P.molsize
+    Mref = g["op_M"].reshape(P.nmol, m, m, 9, 9).transpose(0, 1, 3, 2, 4).reshape(P.nmol, 9 * m, 9 * m)
+    Href = np.triu(Mref) + np.triu(Mref, 1).transpose(0, 2, 1)
+    live = (np.arange(9)[None, None, :] < pm6d.norb_of(P.species)[:, :, None]).reshape(P.nmol, 9 * m)
+    msk = live[:, :, None] & live[:, None, :]  # the reference leaves garbage in the phantom p/d slots of H and sp atoms
+    assert np.abs((hc["H"] - Href) * msk).max() < 1e-9
+    F = pm6d.build_fock_spd(P, par, hc["H"], hc["w"], g["op_X"])
+    assert np.abs((F - g["op_F"]) * msk).max() < 1e-9
+
+
+@pytest.mark.parametrize("name", PM6D_CASES)
+def test_pm6d_single_point_matches_reference(name):
+    g = load_golden(name)
+    out = so.single_point(g["species"], g["coordinates"], g["seqm_parameters"])
+    assert out["n_scf_iter"] == g["n_scf_iter"]
+    assert not out["notconverged"].any()
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "Eiso", "e_gap"):
+        assert np.abs(out[k] - g[k]).max() < 1e-9, k
+    assert np.abs(out["q"] - g["q"]).max() < 1e-9
+    if name != "pm6d_notebook_diatomics":  # Ti2 / S2 on an axis: degenerate frontier orbitals, P is not unique
+        assert np.abs(out["dm"] - g["dm"]).max() < 1e-8
+    assert np.abs(out["force"] - g["force"]).max() < 2e-6  # oracle: central differences; reference: autograd
+
+
+def test_pm6d_reference_own_golden():
+    """tests/reference/pm6_batch_notebook.json of the reference (S2, Ti2, TiS, BrCl, CrTi), its tolerances (1e-5)."""
+    with open(os.path.join(GOLDEN, "ref_json", "pm6_batch_notebook.json")) as f:
+        ref = json.load(f)
+    g = load_golden("pm6d_notebook_diatomics")
+    out = so.single_point(g["species"], g["coordinates"], g["seqm_parameters"])
+    assert np.allclose(out["Etot"], ref["Etot"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(out["force"], np.asarray(ref["force"]), rtol=1e-5, atol=1e-5)
