@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SEQM_ABI_VERSION 2
+#define SEQM_ABI_VERSION 3
 
 /* rows of the per-atom parameter table atom_par[row * nat + atom] */
 enum seqm_par_row {
@@ -37,10 +37,18 @@ enum seqm_par_row {
   SEQM_P_TORE, SEQM_P_QN, SEQM_P_RHOCORE, SEQM_P_ATNUM,
   /* filled by seqm_atom_multipoles(): */
   SEQM_P_DD, SEQM_P_QQ, SEQM_P_RHO0, SEQM_P_RHO1, SEQM_P_RHO2,
+  /* PM6 d-shell rows, all from the per-element table (zero for sp-only elements).  UDD, ZD, BD: U_dd, zeta_d, beta_d of
+   * the parameter file; QND: principal quantum number of the d shell (constants.py qnD_int); DP, DS, DDQ: charge
+   * separations of the p-d dipole, s-d and d-d quadrupoles; RHO3..RHO6: additive terms of the d-d monopole, p-d
+   * dipole, s-d and d-d quadrupoles; RHO2D: the p-p quadrupole term used wherever a d orbital takes part
+   * (two_elec_two_center_int.py:31-97, 204-247; host-side preparation in pyseqm_b200/seqm_functions/pm6d_tables.py) */
+  SEQM_P_UDD, SEQM_P_ZD, SEQM_P_BD, SEQM_P_QND, SEQM_P_DP, SEQM_P_DS, SEQM_P_DDQ, SEQM_P_RHO3, SEQM_P_RHO4, SEQM_P_RHO5,
+  SEQM_P_RHO6, SEQM_P_RHO2D,
   SEQM_NPAR
 };
 
-enum seqm_method { SEQM_MNDO = 0, SEQM_AM1 = 1, SEQM_PM3 = 2, SEQM_PM6_SP = 3 };
+/* SEQM_PM6_D: method="PM6" on a batch that contains d-shell elements (9 orbitals on those atoms) */
+enum seqm_method { SEQM_MNDO = 0, SEQM_AM1 = 1, SEQM_PM3 = 2, SEQM_PM6_SP = 3, SEQM_PM6_D = 4 };
 
 typedef struct seqm_batch {
   int32_t nmol, nat, npairs, method;
@@ -80,6 +88,26 @@ typedef struct seqm_batch {
    * are dropped from the pair list).  Here the dense triangular pair list is kept and such a pair contributes
    * exactly nothing: w, its overlap block, its core-core energy and its gradient are zero.  <= 0: no cutoff. */
   double pair_outer_cutoff;
+  /* ---- PM6 with d orbitals (method SEQM_PM6_D; every pointer NULL / count 0 otherwise) -----------------------------
+   * Atoms are sorted by descending Z and the reference's packd() (packd.py:195-218) requires the d-shell atoms to be
+   * the FIRST mol_nsh atoms of their molecule; mol_nheavy keeps counting every atom with Z > 1.  Packed orbital
+   * order: [9 per d atom][4 per sp heavy atom][1 per hydrogen], n = 5 mol_nsh + 4 mol_nheavy + mol_nhyd.
+   * Pairs with a d atom ("Y pairs") carry a ragged block wd[pair_wd0[p] .. ) of (np_i x np_j) integrals
+   * (kl on i | mn on j), np = 45 / 10 / 1 orbital products for a d / sp heavy / hydrogen atom; their sp x sp
+   * sub-block repeats the dense w.  hab_d: (n_ypairs, 9, 9) beta-scaled overlap blocks of the Y pairs. */
+  const int32_t* mol_nsh;     /* [nmol] */
+  const int64_t* pair_wd0;    /* [npairs+1] */
+  const int32_t* ypairs;      /* [n_ypairs] pair ids of the Y pairs, ascending */
+  const int32_t* ypair_slot;  /* [npairs] index into ypairs / hab_d, -1 for pairs without a d atom */
+  int32_t n_ypairs;
+  int32_t oc_dim;             /* rows of onecenter_d (zmax + 1) */
+  const double* onecenter_d;  /* [oc_dim][45*45] one-centre (kl|mn) containing a d orbital, per element */
+  const double* mp_coef;      /* [45][7][5] multipole coefficients of the 45 local orbital products */
+  const double* mp_coef_yx;   /* the same for the d atom of a (d, sp-heavy) pair */
+  const double* ovl_poly;     /* [4][4][14][9][9] overlap polynomials in (xi, eta) by (n_a, n_b, kind) */
+  /* set per geometry by the caller after seqm_pair_integrals_d(): */
+  const double* wd;
+  const double* hab_d;
 } seqm_batch_t;
 
 int seqm_abi_version(void);
@@ -111,6 +139,8 @@ int seqm_plan_count(const int64_t* species, int32_t nmol, int32_t molsize, const
                     const double* elem_rows, int32_t nz, int32_t* mol_atom0, int32_t* mol_pair0, int64_t* mol_mat0,
                     int32_t* mol_nheavy, int32_t* mol_nhyd, int32_t* mol_nocc, int32_t* mol_order,
                     int32_t* mol_cls_pair0 /* 3*nmol */, seqm_plan_counts_t* counts_dev, seqm_plan_counts_t* counts_host,
+                    int32_t* mol_nsh /* [nmol] out, or NULL: non-NULL selects method="PM6" counting (d-shell atoms carry 9
+                    orbitals; `unsorted` is also raised when a d-shell atom follows an sp-only heavy atom) */,
                     void* stream);
 /* atom_par: (SEQM_NPAR, nat), rows [0, nrows) are written; real_atoms: (nat) int64 flat index mol*molsize + pos */
 int seqm_plan_fill(const int64_t* species, int32_t nmol, int32_t molsize, const seqm_plan_counts_t* counts_host,
@@ -125,6 +155,14 @@ int seqm_atom_multipoles(const seqm_batch_t* b, void* stream);
 /* hcore() pair part -- two_elec_two_center_int.py:98-283 (w), diat_overlap_PM6_SP.py:6-444 (di) and the
  * beta scaling of hcore.py:155-173.  xyz [nat*3] Angstrom; w [npairs*100]; hab [npairs*16] = di*(beta_i+beta_j)/2 */
 int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, double* hab, void* stream);
+
+/* PM6 d-orbital pair integrals (method SEQM_PM6_D), one CTA per Y pair: 45 x 45 local-frame integrals as point-charge
+ * multipole interactions (two_elec_two_center_int_local_frame_d_orbitals.py:23-4164), rotation to the molecular frame
+ * (RotationMatrixD.py:5-310), spd Slater overlaps (diat_overlapD.py:4-5148) with the beta scaling of hcore.py:155-173.
+ * w: the dense (npairs,10,10) tensor of seqm_pair_integrals (source of the sp x sp sub-blocks);
+ * wd [pair_wd0[npairs]] and hab_d [n_ypairs*81] are written; the caller then stores them in b->wd / b->hab_d. */
+int seqm_pair_integrals_d(const seqm_batch_t* b, const double* xyz, const double* w, double* wd, double* hab_d,
+                          void* stream);
 
 /* hcore() assembly -- hcore.py:124-173: packed symmetric Hcore (U_ss/U_pp + core attraction, beta*S blocks) */
 int seqm_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, void* stream);

@@ -88,18 +88,15 @@ class Molecule(torch.nn.Module):
         self.method = seqm_parameters["method"]
         if callable(learned_parameters):
             raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
-        # method="PM6" on elements without a d shell is numerically PM6_SP with the PM6 parameter file; the results
-        # are widened to the reference's 9-slot layout.  d-shell elements (a17) are not on the B200 path yet.
+        # method="PM6": a batch with d-shell elements (the reference's nSuperHeavy set) runs the spd kernels with 9 orbitals on
+        # those atoms; a batch without any is numerically PM6_SP with the PM6 parameter file, its results widened to the
+        # reference's 9-slot layout.
         self.orbital_stride = 9 if self.method == "PM6" else 4
         kernel_method, table = self.method, None
         if self.method == "PM6":
-            if bool(pm6_d_shell(species).any()):
-                bad = sorted(set(species[pm6_d_shell(species)].tolist()))
-                raise NotImplementedError(
-                    f"method 'PM6' with d-shell elements Z={bad} is not implemented by the B200 path yet "
-                    "(sp-only elements are; 'PM6_SP' treats every element with an sp basis)"
-                )
-            kernel_method, table = "PM6_SP", "PM6"
+            kernel_method, table = ("PM6_D", "PM6") if bool(pm6_d_shell(species).any()) else ("PM6_SP", "PM6")
+            if kernel_method == "PM6_D" and seqm_parameters.get("learned"):
+                raise NotImplementedError("learned parameters with PM6 d-shell elements are not on the B200 path")
         lib = _lib if _lib is not None else get_lib()
         # basics.py:442-448: only the names listed in seqm_parameters["learned"] are taken from learned_parameters,
         # everything else comes from the method's table.  Values only: no gradients flow back to them.
@@ -118,6 +115,9 @@ class Molecule(torch.nn.Module):
         self.nmol, self.molsize = plan.nmol, plan.molsize
         self.nHeavy, self.nHydro, self.nocc = plan.nheavy, plan.nhyd, plan.nocc
         self.nSuperHeavy = torch.zeros_like(plan.nheavy)
+        if plan.d_mode:  # basics.py:239-269: nHeavy counts the sp-only heavy atoms, nSuperHeavy the d-shell ones
+            self.nSuperHeavy = plan.nsh
+            self.nHeavy = plan.nheavy - plan.nsh
         self.Z = plan.Z
         self.atom_molid = plan.atom_mol
         self.idxi, self.idxj = plan.pair_i, plan.pair_j
@@ -136,6 +136,11 @@ class Molecule(torch.nn.Module):
         zeros = torch.zeros_like(self.parameters["zeta_s"])
         for k in ("zeta_d", "s_orb_exp_tail", "p_orb_exp_tail", "d_orb_exp_tail", "U_dd", "F0SD", "G2SD", "rho_core"):
             self.parameters[k] = zeros
+        if plan.d_mode:
+            for k in ("zeta_d", "U_dd", "beta_d"):
+                self.parameters[k] = plan.parameter(k)
+            self.parameters["beta"] = torch.stack((self.parameters["beta_s"], self.parameters["beta_p"],
+                                                   self.parameters["beta_d"]), dim=1)  # fmt: skip
         self.parameters["Kbeta"] = None
         zmax = plan.zmax
         if plan.pw is not None:
@@ -143,7 +148,7 @@ class Molecule(torch.nn.Module):
         else:
             self.alp = torch.zeros((zmax + 1, zmax + 1), dtype=torch.float64, device=dev)
             self.chi = torch.zeros_like(self.alp)
-        self.norb = self.nHydro + 4 * self.nHeavy
+        self.norb = self.nHydro + 4 * self.nHeavy + 9 * self.nSuperHeavy
         non_zero = species != 0
         self.num_atoms = non_zero.sum(dim=1).to(coordinates.dtype)
         self.mass = const.mass[species].unsqueeze(2)
@@ -170,13 +175,19 @@ class Molecule(torch.nn.Module):
         self.cis_amplitudes = None
         self.n_scf_iter: Optional[int] = None  # the count the reference only prints (scf_loop.py:975-992)
 
-    _LAZY = ("maskd", "mask", "mask_l", "ni", "nj", "pair_molid", "xij", "rij")
+    _LAZY = ("maskd", "mask", "mask_l", "ni", "nj", "pair_molid", "xij", "rij", "w")
 
     def __getattr__(self, name):
         if name in Molecule._LAZY and "_plan" in self.__dict__:
             plan = self.__dict__["_plan"]
             ms, pos = plan.molsize, plan.atom_local
             d = self.__dict__
+            if name == "w":  # method="PM6": the (npairs, 45, 45) tensor of the reference is assembled on first access
+                parts = d.get("_w_parts")
+                if parts is None:
+                    raise AttributeError(name)
+                d["w"] = engine.dense_w45(plan, *parts)
+                return d["w"]
             if name in ("xij", "rij"):  # unit vector i->j and distance in bohr (basics.py:737-746)
                 xyz = plan.real_xyz(self.coordinates)
                 dv = xyz[plan.pair_j] - xyz[plan.pair_i]

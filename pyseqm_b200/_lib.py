@@ -20,9 +20,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
 PAR_ROWS = ["U_ss", "U_pp", "zeta_s", "zeta_p", "beta_s", "beta_p", "g_ss", "g_sp", "g_pp", "g_p2", "h_sp", "alpha",
             "Gaussian1_K", "Gaussian2_K", "Gaussian3_K", "Gaussian4_K", "Gaussian1_L", "Gaussian2_L", "Gaussian3_L",
             "Gaussian4_L", "Gaussian1_M", "Gaussian2_M", "Gaussian3_M", "Gaussian4_M", "tore", "qn", "rho_core", "atomic_num",
-            "dd", "qq", "rho0", "rho1", "rho2"]  # fmt: skip
+            "dd", "qq", "rho0", "rho1", "rho2",
+            # PM6 d-shell rows (per element, pyseqm_b200/seqm_functions/pm6d_tables.py)
+            "U_dd", "zeta_d", "beta_d", "qnd", "dp", "ds", "ddq", "rho3", "rho4", "rho5", "rho6", "rho2d"]  # fmt: skip
 NPAR = len(PAR_ROWS)
-METHOD_ID = {"MNDO": 0, "AM1": 1, "PM3": 2, "PM6_SP": 3}
+N_ELEM_ROWS = 28  # rows 0..27 come from the element table; 28..32 are written by seqm_atom_multipoles
+METHOD_ID = {"MNDO": 0, "AM1": 1, "PM3": 2, "PM6_SP": 3, "PM6_D": 4}
 
 
 class SeqmBatchStruct(C.Structure):
@@ -36,6 +39,9 @@ class SeqmBatchStruct(C.Structure):
         ("pw_alpha", C.c_void_p), ("pw_chi", C.c_void_p), ("pw_dim", C.c_int32),
         ("pair_cls_off", C.c_int32 * 4), ("pair_perm", C.c_void_p), ("fock_scratch", C.c_int32),
         ("pair_outer_cutoff", C.c_double),
+        ("mol_nsh", C.c_void_p), ("pair_wd0", C.c_void_p), ("ypairs", C.c_void_p), ("ypair_slot", C.c_void_p),
+        ("n_ypairs", C.c_int32), ("oc_dim", C.c_int32), ("onecenter_d", C.c_void_p), ("mp_coef", C.c_void_p),
+        ("mp_coef_yx", C.c_void_p), ("ovl_poly", C.c_void_p), ("wd", C.c_void_p), ("hab_d", C.c_void_p),
     ]  # fmt: skip
 
 JACOBI_NP = (4, 8, 12, 16, 20, 24, 28, 32, 40, 48, 56, 64)
@@ -58,16 +64,30 @@ class SeqmError(RuntimeError):
     pass
 
 
+SOURCES = ("seqm_b200.cu", "seqm_spd.cu")  # translation units, compiled in parallel
+
+
 def build_library(verbose=False):
     """Compile pyseqm_b200/csrc for sm_100a into pyseqm_b200/lib/libseqm_b200.so (nvcc cross-compiles without a GPU)."""
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    src = os.path.join(CSRC, "seqm_b200.cu")
     newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))
     hdr = os.path.join(_HERE, "..", "include", "seqm_b200.h")
     newest = max(newest, os.path.getmtime(hdr))
     if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH, src]
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(os.path.dirname(LIB_PATH), src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = ["nvcc"] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
@@ -90,11 +110,12 @@ class SeqmLib:
             "seqm_last_error": ([], C.c_char_p),
             "seqm_max_orbitals": ([], C.c_int),
             "seqm_plan_count": ([P, C.c_int32, C.c_int32, P, P, C.c_int32, P, P, P, P, P, P, P, P, P,
-                                 C.POINTER(SeqmPlanCounts), P], C.c_int),
+                                 C.POINTER(SeqmPlanCounts), P, P], C.c_int),
             "seqm_plan_fill": ([P, C.c_int32, C.c_int32, C.POINTER(SeqmPlanCounts), P, P, P, P, P, C.c_int32, C.c_int32,
                                 P, P, P, P, P, P, P, P], C.c_int),
             "seqm_atom_multipoles": ([B, P], C.c_int),
             "seqm_pair_integrals": ([B, P, P, P, P], C.c_int),
+            "seqm_pair_integrals_d": ([B, P, P, P, P, P], C.c_int),
             "seqm_hcore": ([B, P, P, P, P], C.c_int),
             "seqm_fock": ([B, P, P, P, P, P, P], C.c_int),
             "seqm_eig_density": ([B, P, P, P, P, P, P, P], C.c_int),
@@ -128,7 +149,7 @@ class SeqmLib:
             fn.argtypes = args
             fn.restype = res
         self.symbols = list(sig)
-        if self.dll.seqm_abi_version() != 2:
+        if self.dll.seqm_abi_version() != 3:
             raise SeqmError("libseqm_b200 ABI version mismatch")
 
     def jacobi_stats(self, reset=True):

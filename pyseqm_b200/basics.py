@@ -65,7 +65,8 @@ class Energy(torch.nn.Module):
         H = engine.op_hcore(plan, w, hab)
         t0 = _timing(molecule, "Hcore + STO Integrals", t0)
         # density: initial guess or the caller's P0 (overwritten in place, ElectronicStructure.py:78)
-        wide = molecule.orbital_stride != 4  # method="PM6": 9 orbital slots per atom in every dense tensor
+        # method="PM6" without d-shell elements runs the 4-slot kernels: dense tensors are widened to 9 slots per atom
+        wide = molecule.orbital_stride != 4 and not plan.d_mode
         if P0 is None:
             P = engine.op_initial_density(plan)
         else:
@@ -88,9 +89,11 @@ class Energy(torch.nn.Module):
             warnings.warn("SCF for %d/%d molecules doesn't converge after %d iterations" % (nnot, plan.nmol, 1000))
         t0 = _timing(molecule, "SCF", t0)
         self.notconverged = notconv
-        if wide:  # (npairs, 45, 45), sp pairs first, the roles of the two atoms swapped (hcore.py:143-146)
-            molecule.w = torch.zeros((w.shape[0], 45, 45), dtype=w.dtype, device=w.device)
-            molecule.w[:, :10, :10] = w.transpose(1, 2)
+        if wide or plan.d_mode:
+            # (npairs, 45, 45) with the roles of the two atoms swapped (hcore.py:143-146): 16 KB per pair, so it is
+            # assembled only if somebody reads molecule.w (Molecule.__getattr__)
+            molecule.__dict__.pop("w", None)
+            molecule.__dict__["_w_parts"] = (w, plan._wd[0] if plan.d_mode else None)
         else:
             molecule.w = w
         molecule._gam = w[:, 0, 0]
@@ -132,7 +135,8 @@ class Energy(torch.nn.Module):
             molecule.analytical_gradient = grad
             t0 = _timing(molecule, "Force", t0)
         Pd = engine.op_unpack(plan, P, out=P0 if (P0 is not None and P0.is_contiguous() and not wide) else None)
-        _ground_dipole(molecule, Pd)
+        if not plan.d_mode:  # basics.py:966-969: no ground-state dipole for PM6 with d orbitals
+            _ground_dipole(molecule, Pd)
         if wide:
             Pd = widen_orbitals(Pd, plan.molsize, molecule.orbital_stride)
         if P0 is not None and Pd is not P0:
@@ -193,6 +197,8 @@ class ForceXL(torch.nn.Module):
     def forward_packed(self, molecule, Pp, want_e=True, learned_parameters=None):
         plan = molecule._plan
         const = molecule.const
+        if plan.d_mode:
+            raise NotImplementedError("XL-BOMD with PM6 d-shell elements is not on the B200 path")
         if learned_parameters:  # xlbomd.py:90-116 re-packs the parameters on every step
             if callable(learned_parameters):
                 raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")

@@ -7,6 +7,9 @@
 
 #define SEQM_MAX_ORB 118  // two n x n fp64 matrices must fit the 227 KB shared memory of one SM
 
+// The library is built from two translation units (seqm_b200.cu and seqm_spd.cu, compiled in parallel): the second one
+// defines SEQM_SECONDARY_TU and only sees declarations of the process-wide state.
+#ifndef SEQM_SECONDARY_TU
 static char g_seqm_err[512] = "";
 long long g_seqm_launches = 0;
 void seqm_set_error(const char* fmt, ...) {
@@ -39,10 +42,12 @@ void seqm_hostemu_ensure_smem(size_t bytes) {
   }
 }
 #endif
+#endif  // SEQM_SECONDARY_TU
 
 // ---- per-molecule geometry of the packed layout ---------------------------------------------------
 struct MolView {
   int m, a0, na, nheavy, nhyd, n, nocc, p0, npair;
+  int nsh;  // PM6 d-shell atoms (9 orbitals): the first nsh of the nheavy heavy atoms; 0 for the sp methods
   long long mat0;
 };
 SEQM_HD MolView mol_view(const seqm_batch_t& b, int m) {
@@ -52,7 +57,8 @@ SEQM_HD MolView mol_view(const seqm_batch_t& b, int m) {
   v.na = b.mol_atom0[m + 1] - v.a0;
   v.nheavy = b.mol_nheavy[m];
   v.nhyd = b.mol_nhyd[m];
-  v.n = 4 * v.nheavy + v.nhyd;
+  v.nsh = b.mol_nsh ? b.mol_nsh[m] : 0;
+  v.n = 5 * v.nsh + 4 * v.nheavy + v.nhyd;
   v.nocc = b.mol_nocc[m];
   v.p0 = b.mol_pair0[m];
   v.npair = b.mol_pair0[m + 1] - v.p0;
@@ -60,12 +66,16 @@ SEQM_HD MolView mol_view(const seqm_batch_t& b, int m) {
   return v;
 }
 // local atom index a (0..na-1, heavy atoms first) -> first packed orbital / number of orbitals
-SEQM_HD int orb_off(const MolView& v, int a) { return a < v.nheavy ? 4 * a : 4 * v.nheavy + (a - v.nheavy); }
-SEQM_HD int orb_cnt(const MolView& v, int a) { return a < v.nheavy ? 4 : 1; }
+SEQM_HD int orb_off(const MolView& v, int a) {
+  return a < v.nsh ? 9 * a : (a < v.nheavy ? 5 * v.nsh + 4 * a : 5 * v.nsh + 4 * v.nheavy + (a - v.nheavy));
+}
+SEQM_HD int orb_cnt(const MolView& v, int a) { return a < v.nsh ? 9 : (a < v.nheavy ? 4 : 1); }
+SEQM_HD int prod_cnt(const MolView& v, int a) { return a < v.nsh ? 45 : (a < v.nheavy ? 10 : 1); }  // orbital products
 // index of pair (a<b) inside the molecule's dense triangular pair list
 SEQM_HD int pair_local(const MolView& v, int a, int b) { return a * (2 * v.na - a - 1) / 2 + (b - a - 1); }
 SEQM_HD double par(const seqm_batch_t& b, int row, int atom) { return b.atom_par[(long long)row * b.nat + atom]; }
 
+#ifndef SEQM_SECONDARY_TU
 // ---- overlap polynomial tables (host-built, device constant) --------------------------------------
 SEQM_CONSTANT OverlapTables c_ovl;
 
@@ -127,6 +137,8 @@ static int ensure_tables() {
   g_tables_ready = 1;
   return SEQM_OK;
 }
+
+#endif  // SEQM_SECONDARY_TU
 
 // block-wide sum of one double per thread (blockDim.x <= 1024, multiple of 32); result valid in all threads
 SEQM_D double block_sum(double v, double* scratch /* >= 33 doubles */) {

@@ -339,6 +339,7 @@ SEQM_HD void overlap_block(const OverlapTables& tab, int na, int nb, bool heavyA
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) S[i][j] = T(0.0);
   if (val(r) > SEQM_OVERLAP_CUTOFF) return;
+  if (na < 1 || na > 3 || nb < 1 || nb > 3) return;  // tables cover n <= 3; PM6 pairs with a d atom (n up to 4) are redone by spd_pair_kernel
   S[0][0] = sto_overlap(tab, na, nb, 0, zsa, zsb, r);
   if (heavyA) {
     const T os = sto_overlap(tab, na, nb, 1, zpa, zsb, r);
@@ -371,7 +372,7 @@ SEQM_HD T core_core(int method, int ni, int nj, const CorePar& A, const CorePar&
                     double chi) {
   const T ra = r * SEQM_A0;
   T E;
-  if (method == 3) {
+  if (method >= 3) {  // PM6_SP and PM6 with d orbitals share the core-core function (energy.py:140-171)
     // PM6 core-core (energy.py:140-171): Voityuk-type unpolarisable-core term + scaled (ss|ss)-like interaction
     const double za3 = pow(A.atnum, 1.0 / 3.0) + pow(B.atnum, 1.0 / 3.0);
     const T q = za3 / ra;

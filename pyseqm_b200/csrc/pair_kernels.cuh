@@ -7,6 +7,7 @@
 //   atom_gradient_kernel     per atom    deterministic +/- gather of the pair gradients
 #pragma once
 #include "common.cuh"
+#include "pair_helpers.cuh"
 
 SEQM_GLOBAL void atom_multipoles_kernel(seqm_batch_t b) {
   for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < b.nat; a += gridDim.x * blockDim.x) {
@@ -19,95 +20,6 @@ SEQM_GLOBAL void atom_multipoles_kernel(seqm_batch_t b) {
     b.atom_par[(long long)SEQM_P_RHO1 * b.nat + a] = m.rho1;
     b.atom_par[(long long)SEQM_P_RHO2 * b.nat + a] = m.rho2;
   }
-}
-
-SEQM_HD AtomMultipole load_multipole(const seqm_batch_t& b, int a) {
-  AtomMultipole m;
-  m.dd = par(b, SEQM_P_DD, a);
-  m.qq = par(b, SEQM_P_QQ, a);
-  m.rho0 = par(b, SEQM_P_RHO0, a);
-  m.rho1 = par(b, SEQM_P_RHO1, a);
-  m.rho2 = par(b, SEQM_P_RHO2, a);
-  return m;
-}
-SEQM_HD CorePar load_core(const seqm_batch_t& b, int a) {
-  CorePar c;
-  c.tore = par(b, SEQM_P_TORE, a);
-  c.alpha = par(b, SEQM_P_ALPHA, a);
-  for (int k = 0; k < 4; ++k) {
-    c.gK[k] = par(b, SEQM_P_K1 + k, a);
-    c.gL[k] = par(b, SEQM_P_L1 + k, a);
-    c.gM[k] = par(b, SEQM_P_M1 + k, a);
-  }
-  const double rc = par(b, SEQM_P_RHOCORE, a);
-  c.rho0eff = (rc != 0.0) ? rc : par(b, SEQM_P_RHO0, a);  // two_elec_two_center_int.py:273-281
-  c.atnum = par(b, SEQM_P_ATNUM, a);
-  return c;
-}
-SEQM_HD void pair_pw(const seqm_batch_t& b, int i, int j, double& alp, double& chi) {
-  alp = chi = 0.0;
-  if (b.pw_alpha) {
-    const long long k = (long long)b.atom_Z[i] * b.pw_dim + b.atom_Z[j];
-    alp = b.pw_alpha[k];
-    chi = b.pw_chi[k];
-  }
-}
-
-// Geometry of a pair as scalars of type T.  For T = Dual3 the derivative slots are d/dR_i.
-template <class T>
-struct PairGeom {
-  T r;     // bohr
-  T e[3];  // unit vector i -> j
-};
-SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<double>& g) {
-  const double dx = xyz[3 * j] - xyz[3 * i], dy = xyz[3 * j + 1] - xyz[3 * i + 1], dz = xyz[3 * j + 2] - xyz[3 * i + 2];
-  const double d = sqrt(dx * dx + dy * dy + dz * dz);
-  g.e[0] = dx / d;
-  g.e[1] = dy / d;
-  g.e[2] = dz / d;
-  g.r = d * (1.0 / SEQM_A0);
-}
-SEQM_HD void pair_geom(const double* xyz, int i, int j, PairGeom<Dual3>& g) {
-  // X = R_j - R_i ; dX/dR_i = -1
-  const Dual3 dx(xyz[3 * j] - xyz[3 * i], -1.0, 0.0, 0.0);
-  const Dual3 dy(xyz[3 * j + 1] - xyz[3 * i + 1], 0.0, -1.0, 0.0);
-  const Dual3 dz(xyz[3 * j + 2] - xyz[3 * i + 2], 0.0, 0.0, -1.0);
-  const Dual3 d = sq_root(dx * dx + dy * dy + dz * dz);
-  g.e[0] = dx / d;
-  g.e[1] = dy / d;
-  g.e[2] = dz / d;
-  g.r = d * (1.0 / SEQM_A0);
-}
-
-// Parser's outer cutoff (basics.py:326: a pair is kept when |R_i - R_j|^2 < cutoff^2).  The dense pair list keeps the
-// pair; every kernel that evaluates pair physics from the geometry returns zero for it instead.
-SEQM_HD bool pair_cut(const seqm_batch_t& b, double r_bohr) {
-  return b.pair_outer_cutoff > 0.0 && r_bohr * SEQM_A0 >= b.pair_outer_cutoff;
-}
-
-// w of one pair in the molecular frame (only the entries that exist for the pair class are non-zero)
-// Only the entries that exist for the pair class are written: [0][0] (H-H), [0..9][0] (X-H), all (X-X).
-template <class T>
-SEQM_HD void pair_w(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T w[10][10], int nint) {
-  T ri[22];
-  local_integrals(g.r, load_multipole(b, i), load_multipole(b, j), nint, ri);
-  if (nint == 1) {
-    w[0][0] = ri[0];
-    return;
-  }
-  T v[3] = {-g.e[0], -g.e[1], -g.e[2]};
-  T rot[3][3];
-  rotation_rows(v, rot);
-  T Tm[10][10];
-  pair_transform(rot, Tm);
-  rotate_to_molecular(ri, nint, Tm, w);
-}
-
-template <class T>
-SEQM_HD void pair_overlap(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T S[4][4]) {
-  const bool hi = b.atom_Z[i] > 1, hj = b.atom_Z[j] > 1;
-  overlap_block(c_ovl, (int)par(b, SEQM_P_QN, i), (int)par(b, SEQM_P_QN, j), hi, hj, par(b, SEQM_P_ZS, i),
-                par(b, SEQM_P_ZP, i), par(b, SEQM_P_ZS, j), par(b, SEQM_P_ZP, j), g.r, g.e, S);
 }
 
 // CLS: 0 H-H, 1 X-H, 2 X-X -- the kernel walks the class's pair list, so every warp is divergence-free and the
@@ -240,6 +152,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
     const double* Pm = P + v.mat0;
     const double* Dm = D + v.mat0;
     const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
+    if (i - v.a0 < v.nsh) continue;  // pair with a d atom: spd_pair_gradient_kernel owns gpair[p]
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
     if (pair_cut(b, g.r)) {

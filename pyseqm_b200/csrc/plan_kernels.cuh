@@ -15,11 +15,19 @@
 
 struct PlanBounds { int np2[SEQM_PLAN_NCLS]; };  // 2*NP of the eigensolver size classes
 
-struct PlanRow { int na, nhyd, zmax, sorted; long long nel2; };  // nel2 = 2 x electron count (tore is integral)
+struct PlanRow { int na, nhyd, nsh, zmax, sorted; long long nel2; };  // nel2 = 2 x electron count (tore is integral)
 
-SEQM_D PlanRow plan_scan_row(const long long* __restrict__ sp, int molsize, const double* __restrict__ tore, int nz, int* elem_flags) {
+// The reference's nSuperHeavy set (basics.py:258-269): elements that carry 9 orbitals under method="PM6"
+SEQM_HD bool plan_d_shell(long long z) {
+  return (z > 12 && z < 18) || (z > 20 && z < 30) || (z > 32 && z < 36) || (z > 38 && z < 48) || (z > 50 && z < 54) ||
+         (z > 70 && z < 80) || z == 57;
+}
+
+SEQM_D PlanRow plan_scan_row(const long long* __restrict__ sp, int molsize, const double* __restrict__ tore, int nz, int* elem_flags,
+                             int d_mode) {
   PlanRow r;
-  r.na = 0; r.nhyd = 0; r.zmax = 0; r.sorted = 1; r.nel2 = 0;
+  r.na = 0; r.nhyd = 0; r.nsh = 0; r.zmax = 0; r.sorted = 1; r.nel2 = 0;
+  int seen_sp_heavy = 0;
   long long prev = 0x7fffffffffffffffLL;
   double nel = 0.0;
   for (int t = 0; t < molsize; ++t) {
@@ -29,6 +37,12 @@ SEQM_D PlanRow plan_scan_row(const long long* __restrict__ sp, int molsize, cons
     if (z > 0) {
       ++r.na;
       if (z == 1) ++r.nhyd;
+      if (d_mode && plan_d_shell(z)) {
+        ++r.nsh;
+        if (seen_sp_heavy) r.sorted = 0;  // a d-shell atom after an sp-only heavy atom: packd.py:195-218 cannot hold it
+      } else if (z > 1) {
+        seen_sp_heavy = 1;
+      }
       if (z > r.zmax) r.zmax = (int)z;
       if (z < nz) nel += tore[z];
       if (elem_flags && z < 128) elem_flags[z] = 1;  // benign race: every writer stores 1
@@ -43,7 +57,7 @@ SEQM_GLOBAL void plan_count_kernel(const long long* __restrict__ species, int nm
                                    PlanBounds bounds, int32_t* __restrict__ atom0, int32_t* __restrict__ pair0,
                                    long long* __restrict__ mat0, int32_t* __restrict__ nheavy_o, int32_t* __restrict__ nhyd_o,
                                    int32_t* __restrict__ nocc_o, int32_t* __restrict__ order, int32_t* __restrict__ cls_pair0,
-                                   seqm_plan_counts_t* __restrict__ out) {
+                                   seqm_plan_counts_t* __restrict__ out, int d_mode, int32_t* __restrict__ nsh_o) {
   __shared__ long long part[SEQM_PLAN_THREADS][6];
   __shared__ int s_elem[128];
   __shared__ int s_cls[SEQM_PLAN_NCLS + 1];
@@ -52,7 +66,7 @@ SEQM_GLOBAL void plan_count_kernel(const long long* __restrict__ species, int nm
   __shared__ int s_keys[SEQM_PLAN_THREADS];
   SEQM_DYN_SMEM(int, dyn);   // hist[nbins] | add[nbins]
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int nbins = 4 * molsize + 2;
+  const int nbins = (d_mode ? 9 : 4) * molsize + 2;
   int* hist = dyn;
   int* add = dyn + nbins;
   for (int i = tid; i < 128; i += nthr) s_elem[i] = 0;
@@ -65,8 +79,9 @@ SEQM_GLOBAL void plan_count_kernel(const long long* __restrict__ species, int nm
   long long s[6] = {0, 0, 0, 0, 0, 0};
   int mx_n = 0, mx_z = 0, mx_f = 0, odd = 0, uns = 0;
   for (int m = lo; m < hi; ++m) {
-    const PlanRow r = plan_scan_row(species + (long long)m * molsize, molsize, tore, nz, s_elem);
-    const int nh = r.na - r.nhyd, ny = r.nhyd, n = 4 * nh + ny;
+    const PlanRow r = plan_scan_row(species + (long long)m * molsize, molsize, tore, nz, s_elem, d_mode);
+    const int nh = r.na - r.nhyd, ny = r.nhyd, n = 4 * nh + ny + 5 * r.nsh;
+    if (nsh_o) nsh_o[m] = r.nsh;
     long long nel = r.nel2 - (charges ? charges[m] : 0);
     if (nel & 1) odd = 1;
     if (!r.sorted) uns = 1;
@@ -130,7 +145,7 @@ SEQM_GLOBAL void plan_count_kernel(const long long* __restrict__ species, int nm
   long long run[6];
   for (int q = 0; q < 6; ++q) run[q] = part[tid][q];
   for (int m = lo; m < hi; ++m) {
-    const int nh = nheavy_o[m], ny = nhyd_o[m], na = nh + ny, n = 4 * nh + ny;
+    const int nh = nheavy_o[m], ny = nhyd_o[m], na = nh + ny, n = 4 * nh + ny + (nsh_o ? 5 * nsh_o[m] : 0);
     atom0[m] = (int32_t)run[0];
     pair0[m] = (int32_t)run[1];
     mat0[m] = run[2];
@@ -147,7 +162,7 @@ SEQM_GLOBAL void plan_count_kernel(const long long* __restrict__ species, int nm
     const int m = base + tid;
     int key = -1;
     if (m < nmol) {
-      key = 4 * nheavy_o[m] + nhyd_o[m];
+      key = 4 * nheavy_o[m] + nhyd_o[m] + (nsh_o ? 5 * nsh_o[m] : 0);
       if (key >= nbins) key = nbins - 1;
     }
     s_keys[tid] = key;

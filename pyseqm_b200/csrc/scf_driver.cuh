@@ -497,7 +497,7 @@ SEQM_D void finalize_error(const seqm_batch_t& b, const ScfWork& W, int mol, dou
   bool bad = fabs(err) > eps;
   if (use_diis) bad = bad || (W.diis_err[mol] > 50.0 * eps);
   if (!bad) {
-    W.dm_err[mol] = sqrt(d2) / (double)(4 * v.nheavy + 4 * v.nhyd);
+    W.dm_err[mol] = sqrt(d2) / (double)(5 * v.nsh + 4 * v.nheavy + 4 * v.nhyd);  // scf_loop.py:245: 9 nSH + 4 nHeavy + 4 nHydro
     W.dm_elem[mol] = dmax;
   }
   const bool nc = bad || (W.dm_err[mol] > 2.0 * eps) || (W.dm_elem[mol] > 15.0 * eps);

@@ -7,6 +7,14 @@
 #include "scf_driver.cuh"
 #include "plan_kernels.cuh"
 
+// PM6 d-orbital kernels: second translation unit (seqm_spd.cu)
+int spd_set_attributes(int smem_optin);
+int spd_launch_pair(const seqm_batch_t* b, const double* xyz, const double* w, double* wd, double* hab_d, cudaStream_t st);
+int spd_launch_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, cudaStream_t st);
+int spd_launch_fock(const seqm_batch_t* b, const double* P, const double* H, const double* w, double* F,
+                    const int32_t* active, int smem_limit, cudaStream_t st);
+int spd_launch_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* gp, cudaStream_t st);
+
 #ifndef SEQM_HOSTEMU
 #define SEQM_STREAM(s) ((cudaStream_t)(s))
 #else
@@ -91,6 +99,7 @@ static int ensure_device() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e == cudaSuccess && spd_set_attributes(g_smem_optin) != SEQM_OK) return SEQM_ERR_CUDA;
   if (e != cudaSuccess) {
     seqm_set_error("cudaFuncSetAttribute(max dynamic shared memory %d): %s", dyn, cudaGetErrorString(e));
     cudaGetLastError();
@@ -105,8 +114,10 @@ static int check_batch(const seqm_batch_t* b) {
     seqm_set_error("empty batch");
     return SEQM_ERR_ARG;
   }
-  if (b->method < 0 || b->method > 3 || (b->method == 3 && !b->pw_alpha)) {
-    seqm_set_error("method %d not supported by this build (MNDO=0, AM1=1, PM3=2, PM6_SP=3 with pairwise tables)", b->method);
+  if (b->method < 0 || b->method > 4 || (b->method >= 3 && !b->pw_alpha) ||
+      (b->method == SEQM_PM6_D && (!b->mol_nsh || !b->pair_wd0 || !b->mp_coef || !b->ovl_poly || !b->onecenter_d))) {
+    seqm_set_error("method %d not supported by this build (MNDO=0, AM1=1, PM3=2, PM6_SP=3 and PM6_D=4 with pairwise tables; "
+                   "PM6_D also needs the d-orbital plan arrays)", b->method);
     return SEQM_ERR_UNSUPPORTED;
   }
   return ensure_device();
@@ -142,7 +153,7 @@ static int fetch_host_mols(const seqm_batch_t* b, HostMol* hm, cudaStream_t st) 
   memcpy(ny, b->mol_nhyd, sizeof(int) * b->nmol);
   memcpy(no, b->mol_nocc, sizeof(int) * b->nmol);
 #endif
-  for (int m = 0; m < b->nmol; ++m) { hm[m].mat0 = m0[m]; hm[m].n = 4 * nh[m] + ny[m]; hm[m].nocc = no[m]; }
+  for (int m = 0; m < b->nmol; ++m) { hm[m].mat0 = m0[m]; hm[m].n = 4 * nh[m] + ny[m]; hm[m].nocc = no[m]; }  // large path: sp methods only
   return SEQM_OK;
 }
 static int fetch_host_ints(const int32_t* dev, int32_t* host, int n, cudaStream_t st) {
@@ -212,6 +223,15 @@ static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, 
   if (fused) *fused = false;
   FockErr none;
   memset(&none, 0, sizeof(none));
+  if (b->method == SEQM_PM6_D) {  // 9 x 9 atom blocks, ragged integral blocks of the pairs with a d atom
+    if (!b->wd && b->n_ypairs > 0) {
+      seqm_set_error("PM6 with d orbitals: b->wd is not set (seqm_pair_integrals_d comes first)");
+      return SEQM_ERR_ARG;
+    }
+    int rcf = SEQM_OK;
+    PROF(PK_FOCK, st, rcf = spd_launch_fock(b, P, H, w, F, active, g_smem_optin - 2048, st));
+    return rcf;
+  }
   if (b->nmax > SEQM_MAX_ORB) {  // matrices in global memory, grid over all pairs / atoms
     if (b->npairs > 0)
       PROF(PK_FOCK, st, SEQM_LAUNCH(fock_large_offdiag_kernel, grid1d((long long)b->npairs * 16, 256), 256, 0, st, *b, P, H, w, F, active));
@@ -324,25 +344,36 @@ static int grid1d(long long n, int block) {
 }
 
 // ---- layout conversion kernels ---------------------------------------------------------------------
-// dense (nmol, 4*molsize, 4*molsize) <-> packed.  Real atoms occupy the first na positions of a molecule.
-SEQM_HD int dense_index(const MolView& v, int orb) {  // packed orbital -> row in the dense padded matrix
-  return orb < 4 * v.nheavy ? orb : 4 * v.nheavy + 4 * (orb - 4 * v.nheavy);
+// dense (nmol, S*molsize, S*molsize) <-> packed, S = 4 orbital slots per atom (9 for method="PM6" with d orbitals).
+// Real atoms occupy the first na positions of a molecule.
+SEQM_HD int dense_stride(const seqm_batch_t& b) { return b.method == SEQM_PM6_D ? 9 : 4; }
+SEQM_HD int orb_atom(const MolView& v, int orb, int* slot) {  // packed orbital -> (local atom, orbital slot on it)
+  const int nd = 9 * v.nsh, np_ = nd + 4 * (v.nheavy - v.nsh);
+  if (orb < nd) { *slot = orb % 9; return orb / 9; }
+  if (orb < np_) { *slot = (orb - nd) & 3; return v.nsh + ((orb - nd) >> 2); }
+  *slot = 0;
+  return v.nheavy + (orb - np_);
+}
+SEQM_HD int dense_index(const MolView& v, int orb, int S) {  // packed orbital -> row in the dense padded matrix
+  int k;
+  const int a = orb_atom(v, orb, &k);
+  return S * a + k;
 }
 SEQM_GLOBAL void pack_kernel(seqm_batch_t b, const double* __restrict__ dense, double* __restrict__ packed) {
   const MolView v = mol_view(b, blockIdx.x);
-  const int n = v.n, N = 4 * b.molsize;
+  const int S = dense_stride(b), n = v.n, N = S * b.molsize;
   const double* D = dense + (long long)v.m * N * N;
   for (int t = threadIdx.x; t < n * n; t += blockDim.x)
-    packed[v.mat0 + t] = D[(long long)dense_index(v, t / n) * N + dense_index(v, t % n)];
+    packed[v.mat0 + t] = D[(long long)dense_index(v, t / n, S) * N + dense_index(v, t % n, S)];
 }
 SEQM_GLOBAL void unpack_kernel(seqm_batch_t b, const double* __restrict__ packed, double* __restrict__ dense) {
   const MolView v = mol_view(b, blockIdx.x);
-  const int n = v.n, N = 4 * b.molsize;
+  const int S = dense_stride(b), n = v.n, N = S * b.molsize;
   double* D = dense + (long long)v.m * N * N;
   for (int t = threadIdx.x; t < N * N; t += blockDim.x) D[t] = 0.0;
   SEQM_SYNC();
   for (int t = threadIdx.x; t < n * n; t += blockDim.x)
-    D[(long long)dense_index(v, t / n) * N + dense_index(v, t % n)] = packed[v.mat0 + t];
+    D[(long long)dense_index(v, t / n, S) * N + dense_index(v, t % n, S)] = packed[v.mat0 + t];
 }
 // packed eigenvector matrices -> (nmol, nmax, nmax) with the identity on the padding (diag.py:110-241 `v`)
 SEQM_GLOBAL void orbitals_dense_kernel(seqm_batch_t b, const double* __restrict__ C, double* __restrict__ V) {
@@ -475,9 +506,10 @@ SEQM_GLOBAL void initial_density_kernel(seqm_batch_t b, double* __restrict__ P) 
   for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
     const int i = t / n, j = t % n;
     double x = 0.0;
-    if (i == j) {
-      const int a = (i < 4 * v.nheavy) ? i / 4 : v.nheavy + (i - 4 * v.nheavy);
-      x = (a < v.nheavy) ? par(b, SEQM_P_TORE, v.a0 + a) / 4.0 : 1.0;
+    if (i == j) {  // tore/4 on s and p of heavy atoms (d shells start empty), 1 on hydrogen (scf_loop.py:2066-2081)
+      int k;
+      const int a = orb_atom(v, i, &k);
+      x = (a < v.nheavy) ? (k < 4 ? par(b, SEQM_P_TORE, v.a0 + a) / 4.0 : 0.0) : 1.0;
     }
     P[v.mat0 + t] = x;
   }
@@ -577,20 +609,21 @@ int seqm_profile_collect(double* ms, int32_t* counts) {
 int seqm_plan_count(const int64_t* species, int32_t nmol, int32_t molsize, const int64_t* charges, const double* elem_rows,
                     int32_t nz, int32_t* mol_atom0, int32_t* mol_pair0, int64_t* mol_mat0, int32_t* mol_nheavy,
                     int32_t* mol_nhyd, int32_t* mol_nocc, int32_t* mol_order, int32_t* mol_cls_pair0,
-                    seqm_plan_counts_t* counts_dev, seqm_plan_counts_t* counts_host, void* stream) {
+                    seqm_plan_counts_t* counts_dev, seqm_plan_counts_t* counts_host, int32_t* mol_nsh, void* stream) {
   int rc = ensure_device();
   if (rc) return rc;
+  const int d_mode = mol_nsh ? 1 : 0;  // method="PM6": count the d-shell atoms, n = 5 nsh + 4 nheavy + nhyd
   if (nmol <= 0 || molsize <= 0 || !species || !counts_dev || !counts_host) {
     seqm_set_error("seqm_plan_count: empty batch or null pointer");
     return SEQM_ERR_ARG;
   }
   PlanBounds pb;
   for (int c = 0; c < SEQM_PLAN_NCLS; ++c) pb.np2[c] = 2 * g_jacobi_np[c];
-  const size_t dyn = sizeof(int) * 2 * (size_t)(4 * molsize + 2);
+  const size_t dyn = sizeof(int) * 2 * (size_t)((d_mode ? 9 : 4) * molsize + 2);
   cudaStream_t st = SEQM_STREAM(stream);
   SEQM_LAUNCH(plan_count_kernel, 1, SEQM_PLAN_THREADS, dyn, st, (const long long*)species, nmol, molsize, (const long long*)charges,
               elem_rows + (size_t)SEQM_P_TORE * nz, nz, pb, mol_atom0, mol_pair0, (long long*)mol_mat0, mol_nheavy, mol_nhyd,
-              mol_nocc, mol_order, mol_cls_pair0, counts_dev);
+              mol_nocc, mol_order, mol_cls_pair0, counts_dev, d_mode, mol_nsh);
   rc = seqm_check_launch("plan_count_kernel");
   if (rc) return rc;
 #ifndef SEQM_HOSTEMU
@@ -644,9 +677,31 @@ int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, dou
   return seqm_check_launch("pair_integrals_kernel");
 }
 
+int seqm_pair_integrals_d(const seqm_batch_t* b, const double* xyz, const double* w, double* wd, double* hab_d,
+                          void* stream) {
+  int rc = check_batch(b);
+  if (rc) return rc;
+  if (b->method != SEQM_PM6_D) {
+    seqm_set_error("seqm_pair_integrals_d: the batch plan is not a PM6 d-orbital plan");
+    return SEQM_ERR_ARG;
+  }
+  if (b->n_ypairs == 0) return SEQM_OK;
+  cudaStream_t st = SEQM_STREAM(stream);
+  PROF(PK_PAIR, st, rc = spd_launch_pair(b, xyz, w, wd, hab_d, st));
+  return rc;
+}
+
 int seqm_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, void* stream) {
   int rc = check_batch(b);
   if (rc) return rc;
+  if (b->method == SEQM_PM6_D) {
+    if ((!b->wd || !b->hab_d) && b->n_ypairs > 0) {
+      seqm_set_error("PM6 with d orbitals: b->wd / b->hab_d are not set (seqm_pair_integrals_d comes first)");
+      return SEQM_ERR_ARG;
+    }
+    PROF(PK_HCORE, SEQM_STREAM(stream), rc = spd_launch_hcore(b, w, hab, H, SEQM_STREAM(stream)));
+    return rc;
+  }
   PROF(PK_HCORE, SEQM_STREAM(stream), SEQM_LAUNCH(hcore_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, w, hab, H));
   return seqm_check_launch("hcore_kernel");
 }
@@ -734,6 +789,11 @@ int seqm_gradient(const seqm_batch_t* b, const double* xyz, const double* P, dou
   if (b->npairs > 0) {
     rc = launch_pair_gradient(b, xyz, P, P, pair_scratch, SEQM_STREAM(stream));
     if (rc) return rc;
+    if (b->method == SEQM_PM6_D && b->n_ypairs > 0) {
+      cudaStream_t st = SEQM_STREAM(stream);
+      PROF(PK_GRAD, st, rc = spd_launch_gradient(b, xyz, P, pair_scratch, st));
+      if (rc) return rc;
+    }
   }
   PROF(PK_GRAD, SEQM_STREAM(stream), SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad));
   return seqm_check_launch("atom_gradient_kernel");

@@ -10,8 +10,8 @@ import os
 
 import torch
 
-from ._lib import (JACOBI_NP, METHOD_ID, NPAR, PAR_ROWS, SeqmBatchStruct, SeqmError, SeqmPlanCounts, SeqmScfOpts, ptr,
-                   stream_of)  # fmt: skip
+from ._lib import (JACOBI_NP, METHOD_ID, N_ELEM_ROWS, NPAR, PAR_ROWS, SeqmBatchStruct, SeqmError, SeqmPlanCounts,
+                   SeqmScfOpts, ptr, stream_of)  # fmt: skip
 
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
 _TABLE_CACHE = {}
@@ -59,14 +59,46 @@ def check_input(species):
         raise ValueError(f"species must be non-increasing along each row, but {row_word} {rows} {verb} not sorted.")
 
 
-def _device_tables(method, dev):
-    """Per-element tables resident on `dev` (cached): rows 0..27 of `atom_par` as (28, zmax+1), tore, class bounds."""
-    key = ("dev", method, str(dev))
-    if key not in _TABLE_CACHE:
-        tab, cols, pw = method_table(method)
+def _pm6d_host_tables():
+    """Element-level tables of the PM6 d-orbital path (seqm_functions/pm6d_tables.py), built once per process:
+    d rows of the element table, one-centre d integrals per element, multipole coefficients, overlap polynomials."""
+    if "pm6d" not in _TABLE_CACHE:
+        from .seqm_functions import pm6d_tables as T
+
+        tab, cols, _ = method_table("PM6")
         el = element_tables()
         nz = max(tab.shape[0], len(el["tore"]))
-        rows = torch.zeros((28, nz), dtype=torch.float64)
+        drows = torch.zeros((len(T.D_ROWS), nz), dtype=torch.float64)
+        onec = torch.zeros((nz, 45 * 45), dtype=torch.float64)
+        supported = set()
+        for z in range(1, min(tab.shape[0], len(el["qn_int"]))):
+            row = {c: float(tab[z, j]) for j, c in enumerate(cols)}
+            if not any(row.values()) or row["zeta_s"] <= 0.0:
+                continue
+            qn, qnd = int(el["qn_int"][z]), int(el["qnD_int"][z])
+            d = T.d_rows(z, qn, qnd, row)
+            for r, name in enumerate(T.D_ROWS):
+                drows[r, z] = d[name]
+            if T.d_shell(z) and row["zeta_d"] != 0.0 and row["rho_core"] == 0.0 and qnd > 0:
+                onec[z] = torch.as_tensor(T.one_center_integrals(qn, qnd, row["s_orb_exp_tail"], row["p_orb_exp_tail"],
+                                                                 row["d_orb_exp_tail"], row["F0SD"], row["G2SD"]).reshape(-1))
+                supported.add(z)
+        c, cyx = T.multipole_coefficients()
+        _TABLE_CACHE["pm6d"] = dict(drows=drows, onecenter=onec, supported=supported, mp_coef=torch.as_tensor(c).reshape(-1),
+                                    mp_coef_yx=torch.as_tensor(cyx).reshape(-1),
+                                    ovl_poly=torch.as_tensor(T.overlap_polynomials()).reshape(-1))  # fmt: skip
+    return _TABLE_CACHE["pm6d"]
+
+
+def _device_tables(method, dev):
+    """Per-element tables resident on `dev` (cached): the rows of `atom_par` that come from the element (NPAR, zmax+1),
+    tore, class bounds; method "PM6_D" adds the d-shell rows and the constant tables of the spd kernels."""
+    key = ("dev", method, str(dev))
+    if key not in _TABLE_CACHE:
+        tab, cols, pw = method_table("PM6" if method == "PM6_D" else method)
+        el = element_tables()
+        nz = max(tab.shape[0], len(el["tore"]))
+        rows = torch.zeros((NPAR, nz), dtype=torch.float64)
         for r, name in enumerate(PAR_ROWS[:24]):
             if name in cols:
                 rows[r, : tab.shape[0]] = tab[:, cols.index(name)]
@@ -75,6 +107,12 @@ def _device_tables(method, dev):
         if "rho_core" in cols:
             rows[26, : tab.shape[0]] = tab[:, cols.index("rho_core")]
         rows[27, : len(el["atomic_num"])] = torch.tensor(el["atomic_num"], dtype=torch.float64)
+        extra = {}
+        if method == "PM6_D":
+            h = _pm6d_host_tables()
+            rows[PAR_ROWS.index("U_dd") :, : h["drows"].shape[1]] = h["drows"]
+            extra = {k: h[k].to(dev).contiguous() for k in ("onecenter", "mp_coef", "mp_coef_yx", "ovl_poly")}
+            extra["supported_d"] = h["supported"]
         T = {
             "rows": rows.to(dev).contiguous(),
             "tore": rows[24].to(dev).contiguous(),
@@ -82,6 +120,7 @@ def _device_tables(method, dev):
             "cls_ids": torch.arange(len(JACOBI_NP) + 1, device=dev).unsqueeze(0),
             "ones": torch.ones(1, dtype=torch.int64, device=dev),
         }
+        T.update(extra)
         _TABLE_CACHE[key] = (T, cols, pw)
     return _TABLE_CACHE[key]
 
@@ -99,7 +138,9 @@ class BatchPlan:
         self.device = dev
         nmol, molsize = species.shape
         self.nmol, self.molsize, self.method = nmol, molsize, method
-        T, cols, pw = _device_tables(table or method, dev)
+        self.d_mode = method == "PM6_D"  # method="PM6" with d-shell elements: 9 orbitals on those atoms
+        self.stride = 9 if self.d_mode else 4  # orbital slots per atom in the dense API layout
+        T, cols, pw = _device_tables("PM6_D" if self.d_mode else (table or method), dev)
         sp64 = species.to(torch.int64).contiguous()
         ch = None
         if torch.is_tensor(charges):
@@ -114,17 +155,21 @@ class BatchPlan:
         cls_pair0 = mi[o + 4 * nmol : o + 7 * nmol]
         counts_dev = mi[o + 7 * nmol + (o + 7 * nmol) % 2 :]  # 8-byte aligned tail (>= sizeof(seqm_plan_counts_t))
         mat0 = torch.empty(nmol + 1, dtype=torch.int64, device=dev)
+        nsh32 = torch.zeros(nmol, dtype=torch.int32, device=dev) if self.d_mode else None
         cnt = SeqmPlanCounts()
         st = stream_of(mi)
         nz = T["rows"].shape[1]
         lib.check(lib.dll.seqm_plan_count(ptr(sp64), nmol, molsize, ptr(ch), ptr(T["rows"]), nz, ptr(atom0), ptr(pair0),
                                           ptr(mat0), ptr(nheavy32), ptr(nhyd32), ptr(nocc32), ptr(order), ptr(cls_pair0),
-                                          ptr(counts_dev), C.byref(cnt), st), "seqm_plan_count")  # fmt: skip
+                                          ptr(counts_dev), C.byref(cnt), ptr(nsh32), st), "seqm_plan_count")  # fmt: skip
         self.nat, self.npairs, self.mat_total, self.nmax = cnt.nat, cnt.npairs, cnt.mat_total, cnt.nmax
         self.zmax, self.sorted_ok = cnt.zmax, not cnt.unsorted
         self.elements = [0] + [z for z in range(1, 128) if cnt.elements[z]]
         if not self.sorted_ok:
             check_input(species)
+            # rows are sorted by Z, so the flag came from the d-shell ordering test of the PM6 plan
+            raise ValueError("method 'PM6': the d-shell elements of a molecule must precede its sp-only heavy elements in the "
+                             "Z-sorted order (the reference's packd layout, packd.py:195-218, cannot hold e.g. Ca before Cl)")
         if cnt.odd_electrons:
             raise ValueError("RHF setting requires closed shell systems (even number of electrons)")
         # ---- step 2 (seqm_plan_fill): atoms, per-atom parameters, pair list, class-sorted pair ids -----------
@@ -134,10 +179,10 @@ class BatchPlan:
         self.real_atoms = torch.empty(self.nat, dtype=torch.int64, device=dev)
         par = torch.zeros((NPAR, self.nat), dtype=torch.float64, device=dev)
         lib.check(lib.dll.seqm_plan_fill(ptr(sp64), nmol, molsize, C.byref(cnt), ptr(atom0), ptr(pair0), ptr(nheavy32),
-                                         ptr(cls_pair0), ptr(T["rows"]), 28, nz, ptr(atom_Z32), ptr(atom_mol32),
+                                         ptr(cls_pair0), ptr(T["rows"]), NPAR, nz, ptr(atom_Z32), ptr(atom_mol32),
                                          ptr(self.real_atoms), ptr(par), ptr(pair_i32), ptr(pair_j32), ptr(self.pair_perm),
                                          st), "seqm_plan_fill")  # fmt: skip
-        self._keep = (mi, ai, sp64, ch)
+        self._keep = (mi, ai, sp64, ch, nsh32)
         self.real_mask = None
         self.t = dict(mol_atom0=atom0, mol_pair0=pair0, mol_mat0=mat0, mol_nheavy=nheavy32, mol_nhyd=nhyd32,
                       mol_nocc=nocc32, mol_order=order, atom_Z=atom_Z32, atom_mol=atom_mol32, pair_i=pair_i32,
@@ -188,10 +233,52 @@ class BatchPlan:
             s.cls_begin[c] = begin
             s.cls_count[c] = cls_cnt[c]
             begin += cls_cnt[c]
+        if self.d_mode:
+            self._init_d_mode(s, T, nsh32)
         self.struct = s
         self.ref = C.byref(s)
         self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path
+        if self.d_mode and self.large:
+            raise NotImplementedError(f"method 'PM6' with d orbitals: a molecule with {self.nmax} orbitals exceeds the "
+                                      f"shared-memory resident path ({lib.dll.seqm_max_orbitals()} orbitals)")
         lib.check(lib.dll.seqm_atom_multipoles(self.ref, stream_of(par)), "seqm_atom_multipoles")
+
+    def _init_d_mode(self, s, T, nsh32):
+        """Index arrays of the pairs that contain a d atom (torch index arithmetic, once per plan): ragged offsets of
+        their (np_i x np_j) integral blocks, the list of those pairs, and the constant tables of the spd kernels."""
+        dev = self.device
+        bad = sorted({int(z) for z in self.elements if z and _is_d_shell(z)} - T["supported_d"])
+        if bad:
+            raise NotImplementedError(f"method 'PM6': no usable d-orbital parameters for Z={bad} (no zeta_d in the parameter "
+                                      "file, or a rho_core element)")
+        elq = element_tables()["qn_int"]
+        big = sorted(int(z) for z in self.elements if z and not _is_d_shell(z) and z > 1 and elq[z] > 3)
+        if big:
+            raise ValueError("\nError from diat.py, overlap matrix\nSome elements are not supported yet")
+        nsh = nsh32.to(torch.int64)
+        mol = self.t["atom_mol"].to(torch.int64)
+        local = torch.arange(self.nat, device=dev) - self.t["mol_atom0"].to(torch.int64)[mol]
+        Z = self.t["atom_Z"].to(torch.int64)
+        is_d = local < nsh[mol]
+        nprod = torch.where(is_d, 45, torch.where(Z > 1, 10, 1))
+        pi, pj = self.t["pair_i"].to(torch.int64), self.t["pair_j"].to(torch.int64)
+        size = torch.where(is_d[pi], nprod[pi] * nprod[pj], 0)
+        wd0 = torch.zeros(self.npairs + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(size, 0, out=wd0[1:])
+        yp = torch.nonzero(size > 0, as_tuple=False).squeeze(1)
+        slot = torch.full((max(self.npairs, 1),), -1, dtype=torch.int32, device=dev)
+        slot[yp] = torch.arange(yp.numel(), dtype=torch.int32, device=dev)
+        self.nsh = nsh
+        self.n_ypairs = int(yp.numel())
+        self.wd_total = int(wd0[-1])
+        self.pair_wd0, self.ypairs, self.ypair_slot = wd0, yp.to(torch.int32).contiguous(), slot
+        self.pair_nprod = (nprod[pi], nprod[pj])
+        self._dkeep = (T["onecenter"], T["mp_coef"], T["mp_coef_yx"], T["ovl_poly"])
+        s.mol_nsh = nsh32.data_ptr()
+        s.pair_wd0, s.ypairs, s.ypair_slot = wd0.data_ptr(), self.ypairs.data_ptr(), slot.data_ptr()
+        s.n_ypairs, s.oc_dim = self.n_ypairs, T["onecenter"].shape[0]
+        s.onecenter_d, s.mp_coef = T["onecenter"].data_ptr(), T["mp_coef"].data_ptr()
+        s.mp_coef_yx, s.ovl_poly = T["mp_coef_yx"].data_ptr(), T["ovl_poly"].data_ptr()
 
     _LAZY64 = {"nheavy": "mol_nheavy", "nhyd": "mol_nhyd", "nocc": "mol_nocc", "Z": "atom_Z", "atom_mol": "atom_mol",
                "pair_i": "pair_i", "pair_j": "pair_j"}  # fmt: skip
@@ -203,7 +290,7 @@ class BatchPlan:
         elif name == "na" and "t" in d:
             d["na"] = self.nheavy + self.nhyd
         elif name == "norb" and "t" in d:
-            d["norb"] = 4 * self.nheavy + self.nhyd
+            d["norb"] = 4 * self.nheavy + self.nhyd + (5 * d["nsh"] if d.get("d_mode") else 0)
         elif name == "atom_local" and "t" in d:
             d["atom_local"] = torch.arange(self.nat, device=self.device) - d["t"]["mol_atom0"].to(torch.int64)[self.atom_mol]
         else:
@@ -232,11 +319,47 @@ class BatchPlan:
         return self.par[PAR_ROWS.index(name)]
 
 
+def _is_d_shell(z):
+    return (12 < z < 18) or (20 < z < 30) or (32 < z < 36) or (38 < z < 48) or (50 < z < 54) or (70 < z < 80) or z == 57
+
+
 def op_pair_integrals(plan, xyz):
     w = torch.empty((plan.npairs, 10, 10), dtype=torch.float64, device=plan.device)
     hab = torch.empty((plan.npairs, 4, 4), dtype=torch.float64, device=plan.device)
     plan.lib.check(plan.lib.dll.seqm_pair_integrals(plan.ref, ptr(xyz), ptr(w), ptr(hab), stream_of(xyz)), "seqm_pair_integrals")
+    if plan.d_mode:
+        op_pair_integrals_d(plan, xyz, w)
     return w, hab
+
+
+def op_pair_integrals_d(plan, xyz, w):
+    """PM6 with d orbitals: the ragged integral blocks and 9 x 9 overlap blocks of the pairs with a d atom.  They belong
+    to the current geometry and are attached to the plan's batch struct (b->wd, b->hab_d) for the kernels that follow."""
+    wd = torch.empty(max(plan.wd_total, 1), dtype=torch.float64, device=plan.device)
+    hab_d = torch.empty((max(plan.n_ypairs, 1), 9, 9), dtype=torch.float64, device=plan.device)
+    plan.lib.check(plan.lib.dll.seqm_pair_integrals_d(plan.ref, ptr(xyz), ptr(w), ptr(wd), ptr(hab_d), stream_of(xyz)),
+                   "seqm_pair_integrals_d")
+    plan._wd = (wd, hab_d)  # keeps the buffers alive as long as the struct points at them
+    plan.struct.wd, plan.struct.hab_d = wd.data_ptr(), hab_d.data_ptr()
+    return wd, hab_d
+
+
+def dense_w45(plan, w, wd):
+    """The reference's `molecule.w` for method="PM6": (npairs, 45, 45) with the roles of the two atoms swapped
+    (w[p, mn on j, kl on i]; hcore.py:143-146, fock.py:277), assembled from the dense sp blocks and the ragged d blocks."""
+    out = torch.zeros((plan.npairs, 45, 45), dtype=torch.float64, device=plan.device)
+    out[:, :10, :10] = w.transpose(1, 2)
+    if plan.d_mode and plan.n_ypairs:
+        yp = plan.ypairs.to(torch.int64)
+        npj = plan.pair_nprod[1][yp]
+        off = plan.pair_wd0[yp]
+        for n in (45, 10, 1):
+            sel = torch.nonzero(npj == n, as_tuple=False).squeeze(1)
+            if sel.numel() == 0:
+                continue
+            idx = off[sel].unsqueeze(1) + torch.arange(45 * n, device=plan.device).unsqueeze(0)
+            out[yp[sel], :n, :] = wd[idx].reshape(-1, 45, n).transpose(1, 2)
+    return out
 
 
 def op_hcore(plan, w, hab):
@@ -354,7 +477,7 @@ def op_pack(plan, dense):
 
 
 def op_unpack(plan, packed, out=None):
-    N = 4 * plan.molsize
+    N = plan.stride * plan.molsize
     if out is None:
         out = torch.empty((plan.nmol, N, N), dtype=torch.float64, device=plan.device)
     plan.lib.check(plan.lib.dll.seqm_unpack(plan.ref, ptr(packed), ptr(out), stream_of(out)), "seqm_unpack")

@@ -110,7 +110,7 @@ def check_operator_level(lib, device, method):
 
 def check_pm6_sp_elements(lib, device):
     """method="PM6" on elements without a d shell: the reference's 9-slot layout of dm / e_mo / w and its
-    `charge=None`, P0 accepted in that layout; d-shell elements are refused loudly."""
+    `charge=None`, P0 accepted in that layout; d-shell elements without usable parameters are refused loudly."""
     mol = check_golden_case(lib, device, "pm6_sp_elements_c2")
     g = load_golden("pm6_sp_elements_c2")
     ms = g["species"].shape[1]
@@ -131,9 +131,72 @@ def check_pm6_sp_elements(lib, device):
         assert np.abs(getattr(mol3, k).cpu().numpy() - g[k]).max() < TOL_E, k
     assert np.abs(mol3.dm.diagonal(dim1=1, dim2=2).cpu().numpy() - g["dm_diag"]).max() < TOL_DM
     assert np.abs(mol3.force.cpu().numpy() - g["force"]).max() < TOL_F
-    with pytest.raises(NotImplementedError, match="d-shell"):
-        run_molecule(lib, device, np.array([[16, 1, 1]]), np.array([[[0.0, 0, 0], [0.96, 0.9, 0], [-0.96, 0.9, 0]]]),
+    with pytest.raises(NotImplementedError, match="d-orbital parameters"):  # Se: in the reference's d-shell set, no zeta_d
+        run_molecule(lib, device, np.array([[34, 1, 1]]), np.array([[[0.0, 0, 0], [1.0, 1.0, 0], [-1.0, 1.0, 0]]]),
                      {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2]})
+    with pytest.raises(ValueError, match="must precede"):  # Ca (sp only) sorts before Cl (d shell): packd cannot hold it
+        run_molecule(lib, device, np.array([[20, 17, 17]]), np.array([[[0.0, 0, 0], [2.4, 0, 0], [-2.4, 0, 0]]]),
+                     {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2]})
+
+
+PM6D_CASES = ["pm6d_organics_c1", "pm6d_organics_c2", "pm6d_organics_c0", "pm6d_diatomics_rotated", "pm6d_cfg5_16",
+              "pm6d_notebook_diatomics"]  # fmt: skip
+
+
+def check_pm6d_case(lib, device, name):
+    """method="PM6" with d-shell elements end to end against the reference-generated fixture."""
+    g = load_golden(name)
+    mol, es = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"])
+    assert mol.n_scf_iter == g["n_scf_iter"], (mol.n_scf_iter, g["n_scf_iter"])
+    assert not bool(es.notconverged.any()) and es.charge is None
+    loose = name == "pm6d_notebook_diatomics"  # the reference's own test settings: scf_eps 1e-5, degenerate frontier orbitals
+    for k in ("Etot", "Hf", "Eelec", "Enuc", "Eiso"):
+        assert np.abs(getattr(mol, k).cpu().numpy() - g[k]).max() < (1e-5 if loose else TOL_E), k
+    assert np.abs(mol.force.cpu().numpy() - g["force"]).max() < TOL_F
+    ms = g["species"].shape[1]
+    assert tuple(mol.dm.shape) == (g["species"].shape[0], 9 * ms, 9 * ms)
+    if not loose:
+        assert np.abs(mol.dm.cpu().numpy() - g["dm"]).max() < TOL_DM
+        assert np.abs(mol.q.cpu().numpy() - g["q"]).max() < TOL_DM
+        assert np.abs(mol.e_gap.cpu().numpy() - g["e_gap"]).max() < TOL_E
+        if "e_mo" in g:
+            assert np.abs(mol.e_mo.cpu().numpy() - g["e_mo"]).max() < TOL_E
+    return mol
+
+
+def check_pm6d_operators(lib, device, name):
+    """w (45 x 45 blocks), Hcore and the 9 x 9 Fock build of the spd kernels against the reference's operator outputs."""
+    import seqm_oracle as so
+    from seqm_oracle import pm6d as opm6d
+
+    g = load_golden(name)
+    species = torch.as_tensor(g["species"], device=device)
+    coords = torch.as_tensor(g["coordinates"], device=device)
+    plan = engine.BatchPlan(lib, species, "PM6_D")
+    xyz = plan.real_xyz(coords)
+    w, hab = engine.op_pair_integrals(plan, xyz)
+    w45 = engine.dense_w45(plan, w, plan._wd[0]).cpu().numpy()
+    nob = opm6d.norb_of(g["species"])
+    # the reference leaves unspecified values in product slots of orbitals an atom does not carry: compare the real ones
+    P = so.parse(g["species"], g["coordinates"])
+    npi = np.where(nob.reshape(-1)[P.real_atoms][P.idxi] == 9, 45, np.where(P.ni > 1, 10, 1))
+    npj = np.where(nob.reshape(-1)[P.real_atoms][P.idxj] == 9, 45, np.where(P.nj > 1, 10, 1))
+    live = (np.arange(45)[None, :, None] < npj[:, None, None]) & (np.arange(45)[None, None, :] < npi[:, None, None])
+    assert np.abs((w45 - g["op_w"]) * live).max() < 1e-9
+    H = engine.op_hcore(plan, w, hab)
+    Hd = engine.op_unpack(plan, H).cpu().numpy()
+    nmol, ms = plan.nmol, plan.molsize
+    Mref = g["op_M"].reshape(nmol, ms, ms, 9, 9).transpose(0, 1, 3, 2, 4).reshape(nmol, 9 * ms, 9 * ms)
+    lv = (np.arange(9)[None, None, :] < nob[:, :, None]).reshape(nmol, 9 * ms)
+    msk = lv[:, :, None] & lv[:, None, :]
+    assert np.abs((np.triu(Hd) - np.triu(Mref)) * msk).max() < 1e-9
+    X = engine.op_pack(plan, torch.as_tensor(g["op_X"], device=device))
+    F = engine.op_fock(plan, X, H, w)
+    assert np.abs((engine.op_unpack(plan, F).cpu().numpy() - g["op_F"]) * msk).max() < 1e-9
+    # pack / unpack round trip in the 9-slot layout, initial density
+    assert torch.equal(engine.op_pack(plan, engine.op_unpack(plan, X)), X)
+    P0 = engine.op_unpack(plan, engine.op_initial_density(plan)).cpu().numpy()
+    assert np.abs(P0 - opm6d.initial_density_spd(P)).max() == 0.0
 
 
 def check_level_b_signatures(lib, device, method):

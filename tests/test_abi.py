@@ -30,7 +30,7 @@ def test_cuda_library_exports_all_declared_symbols():
     for name in declared_symbols():
         assert hasattr(dll, name), name
     dll.seqm_abi_version.restype = ctypes.c_int
-    assert dll.seqm_abi_version() == 2
+    assert dll.seqm_abi_version() == 3
     # the host-emulation build exposes the same ABI
     emu = ctypes.CDLL(ge.build_hostemu())
     for name in declared_symbols():
@@ -59,9 +59,10 @@ def test_option_matrix_rejections():
 
     species = torch.tensor([[6, 1, 1, 1, 1]])
     coords = torch.randn(1, 5, 3, dtype=torch.float64)
-    with pytest.raises(NotImplementedError, match="d-shell"):  # PM6 is served only for elements without a d shell
-        seqm.Molecule(seqm.Constants(), {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2]},
-                      torch.randn(1, 3, 3, dtype=torch.float64), torch.tensor([[16, 1, 1]]))  # fmt: skip
+    with pytest.raises(NotImplementedError, match="learned parameters with PM6 d-shell"):
+        seqm.Molecule(seqm.Constants(), {"method": "PM6", "scf_eps": 1e-6, "scf_converger": [2], "learned": ["U_ss"]},
+                      torch.randn(1, 3, 3, dtype=torch.float64), torch.tensor([[16, 1, 1]]),
+                      learned_parameters={"U_ss": torch.zeros(3, dtype=torch.float64)})  # fmt: skip
     for bad in ({"method": "PM7"}, {"UHF": True}, {"excited_states": {"n_states": 2}}, {"scf_backward": 1},
                 {"scf_converger": [3, 0.1]}, {"dispersion": True}):  # fmt: skip
         sp = {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2]}

@@ -25,7 +25,7 @@ def dev():
 
 def test_cuda_library_is_the_one_loaded(lib):
     assert lib.path.endswith("pyseqm_b200/lib/libseqm_b200.so")
-    assert lib.dll.seqm_abi_version() == 2
+    assert lib.dll.seqm_abi_version() == 3
 
 
 @pytest.mark.parametrize("method", ["AM1", "PM3", "MNDO", "PM6_SP"])
@@ -49,6 +49,53 @@ def test_reference_operator_signatures(lib, dev, method):
 )  # fmt: skip
 def test_single_point_golden(lib, dev, name):
     check_golden_case(lib, dev, name)
+
+
+@pytest.mark.parametrize("name", ["pm6d_organics_c1", "pm6d_diatomics_rotated", "pm6d_notebook_diatomics"])
+def test_pm6_d_orbital_operators(lib, dev, name):
+    """45 x 45 integral blocks, spd overlaps / Hcore, 9 x 9 Fock incl. one-centre d integrals."""
+    from helpers import check_pm6d_operators
+
+    check_pm6d_operators(lib, dev, name)
+
+
+@pytest.mark.parametrize("name", ["pm6d_organics_c1", "pm6d_organics_c2", "pm6d_organics_c0", "pm6d_diatomics_rotated",
+                                  "pm6d_cfg5_16", "pm6d_notebook_diatomics"])  # fmt: skip
+def test_pm6_d_orbital_single_point(lib, dev, name):
+    from helpers import check_pm6d_case
+
+    check_pm6d_case(lib, dev, name)
+
+
+def test_pm6_d_reference_own_golden(lib, dev):
+    """tests/reference/pm6_batch_notebook.json of the reference (S2, Ti2, TiS, BrCl, CrTi) at its own tolerances."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+
+    with open(os.path.join(GOLDEN, "ref_json", "pm6_batch_notebook.json")) as f:
+        ref = json.load(f)
+    g = load_golden("pm6d_notebook_diatomics")
+    mol, _ = run_molecule(lib, dev, g["species"], g["coordinates"], g["seqm_parameters"])
+    assert np.allclose(mol.Etot.cpu().numpy(), ref["Etot"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(mol.force.cpu().numpy(), np.asarray(ref["force"]), rtol=1e-5, atol=1e-5)
+
+
+def test_pm6_d_batch_against_oracle(lib, dev):
+    """configs[4] sample: 96 synthetic organics with P / S / Cl, PM6, adaptive mixing -- CUDA path vs the numpy oracle."""
+    import seqm_oracle as so
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    s, c = qm9_like_batch(96, seed=3, hetero=(15, 16, 17))
+    sp = {"method": "PM6", "scf_eps": 1e-7, "scf_converger": [1], "sp2": [False]}
+    ref = so.single_point(s, c, sp)
+    mol, es = run_molecule(lib, dev, s, c, sp)
+    assert mol.n_scf_iter == ref["n_scf_iter"]
+    assert not bool(es.notconverged.any())
+    assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < TOL_E
+    assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < TOL_DM
+    assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < TOL_F
 
 
 @pytest.mark.parametrize("name", ["op_momatch_mixed", "op_momatch_uniform"])

@@ -55,6 +55,20 @@ def test_pm6_on_elements_without_d_shell(lib):
     check_pm6_sp_elements(lib, CPU)
 
 
+@pytest.mark.parametrize("name", ["pm6d_organics_c1", "pm6d_diatomics_rotated", "pm6d_notebook_diatomics"])
+def test_pm6_d_orbital_operators(lib, name):
+    from helpers import check_pm6d_operators
+
+    check_pm6d_operators(lib, CPU, name)
+
+
+def test_pm6_d_orbital_single_points(lib):
+    from helpers import PM6D_CASES, check_pm6d_case
+
+    for name in PM6D_CASES:
+        check_pm6d_case(lib, CPU, name)
+
+
 def test_sp2_route(lib):
     # mixed batch: the reference zero-pads packed matrices inside SP2 (pack.py:76-77), we purify at native
     # size, so agreement is at the SP2 tolerance; the unpadded (largest) molecule agrees tightly.
