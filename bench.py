@@ -13,6 +13,8 @@ host cores: exactly K timed + W warm-up steps, each step one reference forward o
 REF_SAMPLE molecules of the same batch), and reports the steps / sample it actually ran.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -333,15 +335,34 @@ def c380_run(seqm, lib, dev, const):
             "reference_cpu": "84-131 s wall on 8 host threads (BASELINE.md section 2; not re-run here: one forward exceeds the bench budget)"}  # fmt: skip
 
 
-def pm6_run(seqm, dev, const, nmol, steps):
+def pm6_run(seqm, lib, dev, const, nmol, steps):
     """configs[4]: PM6 sp+d batch of 2048 organics with S/P/Cl, scf_converger [1], energies + forces."""
     import numpy as np
     import torch
 
     from pyseqm_b200.synthetic import qm9_like_batch
 
-    species, coords = qm9_like_batch(nmol, seed=0, start=0, hetero=(15, 16, 17))
+    # SURVEY 8(d): "accept only molecules the reference converges".  Adaptive mixing (scf_converger [1], the configs[4]
+    # setting) stalls on a few percent of the synthetic P/S/Cl organics, so candidates are screened once, untimed, with
+    # a 150-iteration cap (iteration counts equal the reference's, see parity_64) and the first `nmol` survivors kept.
+    import warnings
+
+    ncand = int(nmol * 1.25) + 32
+    cs, cc = qm9_like_batch(ncand, seed=0, start=0, hetero=(15, 16, 17))
     sp = {"method": "PM6", "scf_eps": 1.0e-7, "scf_converger": [1], "sp2": [False]}
+    sp_screen = dict(sp, b200_scf_max_iter=150)
+    ms_ = seqm.Molecule(const, dict(sp_screen), torch.as_tensor(cc, device=dev), torch.as_tensor(cs, device=dev))
+    ms_.verbose = False
+    es_ = seqm.Electronic_Structure(dict(sp_screen))
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        es_(ms_)
+    keep = (~es_.notconverged).nonzero(as_tuple=False).squeeze(1).cpu().numpy()
+    dropped = ncand - keep.size
+    if keep.size < nmol:
+        raise RuntimeError(f"only {keep.size} of {ncand} PM6 candidates converge")
+    species, coords = cs[keep[:nmol]], cc[keep[:nmol]]
+    del ms_, es_
     mol = seqm.Molecule(const, dict(sp), torch.as_tensor(coords, device=dev), torch.as_tensor(species, device=dev))
     mol.verbose = False
     es = seqm.Electronic_Structure(dict(sp))
@@ -357,9 +378,18 @@ def pm6_run(seqm, dev, const, nmol, steps):
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
     t = sum(ms) / len(ms)
-    out = {"workload": f"configs[4]: PM6 (d orbitals on P/S/Cl), {nmol} synthetic organics (<=29 atoms), scf_eps 1e-7, scf_converger [1], energies + forces",
+    lib.profile_enable(True)
+    es(mol)
+    prof = lib.profile_collect()
+    lib.profile_enable(False)
+    out = {"workload": f"configs[4]: PM6 (d orbitals on P/S/Cl), {nmol} synthetic organics (<=29 atoms), scf_eps 1e-7, scf_converger [1], "
+                       f"energies + forces; the first {nmol} of {ncand} generated molecules that adaptive mixing converges within 150 iterations "
+                       f"({dropped} candidates dropped)",
            "value": nmol / (t * 1e-3), "unit": UNIT, "ms_per_step": t, "steps": steps, "n_scf_iter": int(mol.n_scf_iter),
-           "not_converged": int(es.notconverged.sum()), "molecules_with_d_shell": int((np.isin(species, (15, 16, 17))).any(axis=1).sum())}  # fmt: skip
+           "not_converged": int(es.notconverged.sum()), "molecules_with_d_shell": int((np.isin(species, (15, 16, 17))).any(axis=1).sum()),
+           "orbitals_max": int(mol._plan.nmax), "pairs_with_d_atom": int(mol._plan.n_ypairs), "pairs": int(mol._plan.npairs),
+           "d_integral_doubles": int(mol._plan.wd_total),
+           "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]}}  # fmt: skip
     if have_reference():
         n = 64
         rate, dt, ref = reference_rate(species[:n], coords[:n], sp, steps=1, warmup=0)
@@ -611,7 +641,7 @@ def main():
             c380 = c380_run(seqm, lib, dev, const)
         if "pm6" in extras:
             try:
-                pm6 = pm6_run(seqm, dev, const, args.pm6_nmol, 5)
+                pm6 = pm6_run(seqm, lib, dev, const, args.pm6_nmol, 5)
             except Exception as e:  # configs[4] must never take the configs[1] line down with it
                 pm6 = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 

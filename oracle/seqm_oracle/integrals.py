@@ -278,10 +278,12 @@ def _aintgs(x, kmax):
     return a
 
 
-def _bintgs(x, kmax):
+def _bintgs(x, kmax, x_regime=None):
     """B_k(x) = int_-1^1 t^k exp(-x t) dt with the reference's three regimes
-    (|x|>0.5 recurrence, 1e-6<|x|<=0.5 four-term series, else x=0 limit) -- diat_overlap_PM6_SP.py:522-670."""
-    absx = np.abs(x)
+    (|x|>0.5 recurrence, 1e-6<|x|<=0.5 four-term series, else x=0 limit) -- diat_overlap_PM6_SP.py:522-670.
+    x_regime: the argument that selects the regime (finite-difference gradients freeze the choice at the undisplaced
+    geometry: the truncated series and the recurrence differ by ~1e-7 at |x| = 0.5, which a stencil must not straddle)."""
+    absx = np.abs(x if x_regime is None else x_regime)
     big = absx > 0.5
     mid = (absx <= 0.5) & (absx > 1.0e-6)
     b = []

@@ -477,7 +477,7 @@ def _sigma_pi_delta_poly(na, la, nb, lb, m):
     return phi * ka * kb, poly
 
 
-def _sto_overlap_general(na, la, za, nb, lb, zb, m, r):
+def _sto_overlap_general(na, la, za, nb, lb, zb, m, r, r_regime=None):
     from .integrals import _aintgs, _bintgs
 
     c, poly = _sigma_pi_delta_poly(na, la, nb, lb, m)
@@ -485,7 +485,7 @@ def _sto_overlap_general(na, la, za, nb, lb, zb, m, r):
     beta = 0.5 * r * (za - zb)
     kmax = max(poly.shape) - 1
     A = _aintgs(alpha, kmax)
-    B = _bintgs(beta, kmax)
+    B = _bintgs(beta, kmax, None if r_regime is None else 0.5 * r_regime * (za - zb))
     tot = 0.0
     for k in range(poly.shape[0]):
         for l in range(poly.shape[1]):
@@ -496,8 +496,9 @@ def _sto_overlap_general(na, la, za, nb, lb, zb, m, r):
     return c * norm * tot
 
 
-def overlap_spd(ni, nj, xij, rij, zeta_a, zeta_b):
-    """di (npairs, 9, 9) = <mu on i | nu on j>, molecular frame (diat_overlapD.py:4-5148); zeta_* (npairs, 3) = s, p, d."""
+def overlap_spd(ni, nj, xij, rij, zeta_a, zeta_b, rij_regime=None):
+    """di (npairs, 9, 9) = <mu on i | nu on j>, molecular frame (diat_overlapD.py:4-5148); zeta_* (npairs, 3) = s, p, d.
+    rij_regime: distances that select the B-integral regime (see integrals._bintgs), default rij."""
     T = Tables.get()
     qn, qnd = _qn_tables()
     npairs = rij.shape[0]
@@ -529,7 +530,8 @@ def overlap_spd(ni, nj, xij, rij, zeta_a, zeta_b):
             if key not in cache:
                 za = zeta_a[msk, la]
                 zb = zeta_b[msk, lb]
-                cache[key] = _sto_overlap_general(na[a], la, za, nb[b], lb, zb, m, r)
+                cache[key] = _sto_overlap_general(na[a], la, za, nb[b], lb, zb, m, r,
+                                                  None if rij_regime is None else rij_regime[msk])
             Sl[:, a, b] = cache[key]
         Rm = R[msk]
         blk = np.matmul(Rm, np.matmul(Sl, Rm.transpose(0, 2, 1)))
@@ -779,13 +781,13 @@ def density_from_fock_spd(F, species, nocc, mols=None, want_eig=False):
     return (D, E, V) if want_eig else (D, E)
 
 
-def _pair_energy_spd(P, par, mpd, xij, rij, PAi, PBj, Dab):
+def _pair_energy_spd(P, par, mpd, xij, rij, PAi, PBj, Dab, rij_regime=None):
     from .energy import pair_nuclear_energy
     from .integrals import rho0_eff
 
     w, e_i, e_j = two_center_integrals_spd(P.ni, P.nj, P.idxi, P.idxj, xij, rij, mpd)
     zeta = np.stack([par["zeta_s"], par["zeta_p"], par["zeta_d"]], axis=1)
-    di = overlap_spd(P.ni, P.nj, xij, rij, zeta[P.idxi], zeta[P.idxj])
+    di = overlap_spd(P.ni, P.nj, xij, rij, zeta[P.idxi], zeta[P.idxj], rij_regime)
     bA = np.stack([par["beta_s"]] + [par["beta_p"]] * 3 + [par["beta_d"]] * 5, axis=1)
     bsum = bA[P.idxi][:, :, None] + bA[P.idxj][:, None, :]
     E = np.sum(Dab * di * bsum, axis=(1, 2))
@@ -818,7 +820,7 @@ def hf_gradient_spd(P, par, mpd, Dm, delta=1.0e-4):
             X = Xij.copy()
             X[:, c] -= s * delta
             d = np.sqrt(np.sum(X * X, axis=1))
-            Es[s] = _pair_energy_spd(P, par, mpd, X / d[:, None], d / T.a0, *args)
+            Es[s] = _pair_energy_spd(P, par, mpd, X / d[:, None], d / T.a0, *args, rij_regime=P.rij)
         g[:, c] = (8.0 * (Es[1.0] - Es[-1.0]) - (Es[2.0] - Es[-2.0])) / (12.0 * delta)
     nat = P.Z.shape[0]
     ga = np.zeros((nat, 3))

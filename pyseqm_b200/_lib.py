@@ -65,6 +65,10 @@ class SeqmError(RuntimeError):
 
 
 SOURCES = ("seqm_b200.cu", "seqm_spd.cu")  # translation units, compiled in parallel
+# files that only one translation unit includes (everything else is shared): an edit there recompiles that unit alone
+_ONLY = {"seqm_spd.cu": {"seqm_spd.cu", "spd_kernels.cuh"},
+         "seqm_b200.cu": {"seqm_b200.cu", "pair_kernels.cuh", "scf_driver.cuh", "plan_kernels.cuh", "eig_kernels.cuh",
+                          "fock_kernels.cuh", "large_kernels.cuh"}}  # fmt: skip
 
 
 def build_library(verbose=False):
@@ -80,6 +84,10 @@ def build_library(verbose=False):
     for src in SOURCES:
         obj = os.path.join(os.path.dirname(LIB_PATH), src.replace(".cu", ".o"))
         objs.append(obj)
+        others = set().union(*(v for k, v in _ONLY.items() if k != src))
+        deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f not in others] + [hdr]
+        if os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(d) for d in deps):
+            continue
         cmd = ["nvcc"] + flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
         if verbose:
             print(" ".join(cmd))

@@ -43,6 +43,7 @@ class Energy(torch.nn.Module):
         self.sp2 = seqm_parameters.get("sp2", [False])
         self.scf_converger = seqm_parameters.get("scf_converger", [2])
         self.warm_start = bool(seqm_parameters.get("b200_eig_warm_start", True))
+        self.max_iter = int(seqm_parameters.get("b200_scf_max_iter", 1000))  # reference: MAX_ITER = 1000 (scf_loop.py:29)
         self.notconverged = None
 
     def forward(self, molecule, learned_parameters=dict(), all_terms=False, P0=None, do_force=False, *args, **kwargs):
@@ -77,7 +78,8 @@ class Energy(torch.nn.Module):
         if C0 is not None and C0.numel() != plan.mat_total:
             C0 = None
         F, Eelec, notconv, n_iter, Clast = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
-                                                         warm_start=self.warm_start, want_C=True, C0=C0)  # fmt: skip
+                                                         warm_start=self.warm_start, want_C=True, C0=C0,
+                                                         max_iter=self.max_iter)  # fmt: skip
         molecule.__dict__["_C_last"] = Clast
         molecule.n_scf_iter = n_iter
         if molecule.verbose:
@@ -86,7 +88,7 @@ class Energy(torch.nn.Module):
         if bool(notconv.any()):
             nnot = int(notconv.sum())
             print("did not converge", nnot)
-            warnings.warn("SCF for %d/%d molecules doesn't converge after %d iterations" % (nnot, plan.nmol, 1000))
+            warnings.warn("SCF for %d/%d molecules doesn't converge after %d iterations" % (nnot, plan.nmol, self.max_iter))
         t0 = _timing(molecule, "SCF", t0)
         self.notconverged = notconv
         if wide or plan.d_mode:

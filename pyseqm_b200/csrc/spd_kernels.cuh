@@ -165,7 +165,29 @@ SEQM_HD void spd_kind(int kind, int* la, int* lb, int* m) {
   const int MM[14] = {0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 2};
   *la = LA[kind]; *lb = LB[kind]; *m = MM[kind];
 }
-SPD_NOINLINE double spd_local_overlap(const seqm_batch_t& b, const SpdAtom& A, const SpdAtom& B, int kind, double r) {
+// B_k(x) with the regime (recurrence | four-term series | x = 0 limit, diat_overlapD.py:5222-5370) selected by xr: the
+// stencil of the gradient kernel freezes the choice at the undisplaced geometry, because the truncated series and the
+// recurrence differ by ~1e-7 at |x| = 0.5 and a finite difference must not straddle that step (the reference's
+// autograd differentiates inside the branch the geometry is in).
+SEQM_HD void spd_aux_B(double x, double xr, int kmax, double* B) {
+  const double ax = fabs(xr);
+  if (ax > 0.5) {
+    const double tx = exp(x) / x, tmx = -(exp(-x) / x);
+    B[0] = tx + tmx;
+    for (int k = 1; k <= kmax; ++k) B[k] = ((k & 1) ? (tmx - tx) : (tx + tmx)) + (double)k * B[k - 1] / x;
+  } else if (ax > 1.0e-6) {
+    const double x2 = x * x;
+    for (int k = 0; k <= kmax; ++k) {
+      if ((k & 1) == 0)
+        B[k] = 2.0 / (k + 1.0) + x2 / (k + 3.0) + x2 * x2 / ((k + 5.0) * 12.0) + x2 * x2 * x2 / ((k + 7.0) * 360.0);
+      else
+        B[k] = (-2.0 / (k + 2.0)) * x - x2 * x / ((k + 4.0) * 3.0) - x2 * x2 * x / ((k + 6.0) * 60.0);
+    }
+  } else {
+    for (int k = 0; k <= kmax; ++k) B[k] = (k & 1) ? 0.0 : 2.0 / (k + 1.0);
+  }
+}
+SPD_NOINLINE double spd_local_overlap(const seqm_batch_t& b, const SpdAtom& A, const SpdAtom& B, int kind, double r, double r_regime) {
   int la, lb, m;
   spd_kind(kind, &la, &lb, &m);
   const int na = A.n[la], nb = B.n[lb];
@@ -174,7 +196,7 @@ SPD_NOINLINE double spd_local_overlap(const seqm_batch_t& b, const SpdAtom& A, c
   double Ak[10], Bk[10];
   const int kmax = 8;
   aux_A((0.5 * (za + zb)) * r, kmax, Ak);
-  aux_B((0.5 * (za - zb)) * r, kmax, Bk);
+  spd_aux_B((0.5 * (za - zb)) * r, (0.5 * (za - zb)) * r_regime, kmax, Bk);
   const double* poly = b.ovl_poly + ((long long)((na - 1) * 4 + (nb - 1)) * 14 + kind) * 81;
   double tot = 0.0;
   for (int k = 0; k <= kmax; ++k)
@@ -205,7 +227,7 @@ SPD_NOINLINE double spd_local_overlap(const seqm_batch_t& b, const SpdAtom& A, c
 // i (a d atom) and j at positions Ri, Rj (Angstrom).  wsp: the pair's 10 x 10 block of the sp path at this geometry.
 // All threads of the CTA call it; it ends with a barrier.
 SPD_NOINLINE void spd_pair_block(const seqm_batch_t& b, int i, int j, bool dj, const double* Ri, const double* Rj,
-                           const double* wsp, double* sm) {
+                           const double* wsp, double* sm, double r_regime) {
   const int tid = threadIdx.x, nthr = blockDim.x;
   SpdAtom A, B;
   spd_load_atom(b, i, true, A);
@@ -253,7 +275,7 @@ SPD_NOINLINE void spd_pair_block(const seqm_batch_t& b, int i, int j, bool dj, c
       spd_kind(kind, &la, &lb, &m);
       const int oa = (la == 0) ? 0 : (la == 1 ? 1 : 4), ob = (lb == 0) ? 0 : (lb == 1 ? 1 : 4);
       if (oa >= A.norb || ob >= B.norb) continue;
-      const double sv = spd_local_overlap(b, A, B, kind, r);
+      const double sv = spd_local_overlap(b, A, B, kind, r, r_regime > 0.0 ? r_regime : r);
       // local orbital of (l, m): p: sigma 1, pi 2,3 ; d: sigma 4, pi 5,6, delta 7,8.  Reflection z -> -z: (-1)^(l+m)
       const double sg = (((la + m) & 1) ? -1.0 : 1.0) * (((lb + m) & 1) ? -1.0 : 1.0);
       const int ia = (m == 0) ? oa : (la == 1 ? 2 : (m == 1 ? 5 : 7));
@@ -352,7 +374,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_kernel(seqm_batch_t b,
   const int i = b.pair_i[p], j = b.pair_j[p];
   const int mol = b.atom_mol[i];
   const bool dj = (j - b.mol_atom0[mol]) < b.mol_nsh[mol];
-  spd_pair_block(b, i, j, dj, xyz + 3 * (long long)i, xyz + 3 * (long long)j, w10 + (long long)p * 100, sm);
+  spd_pair_block(b, i, j, dj, xyz + 3 * (long long)i, xyz + 3 * (long long)j, w10 + (long long)p * 100, sm, -1.0);
   const long long o0 = b.pair_wd0[p], cnt = b.pair_wd0[p + 1] - o0;
   for (int t = threadIdx.x; t < cnt; t += blockDim.x) wd[o0 + t] = sm[SPD_OFF_L + t];
   for (int t = threadIdx.x; t < 81; t += blockDim.x) hab_d[(long long)slot * 81 + t] = sm[SPD_OFF_S + t];
@@ -577,6 +599,11 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_gradient_kernel(seqm_b
   SEQM_SYNC();
   const double delta = 1.0e-4;
   double Rj[3] = {xyz[3 * (long long)j], xyz[3 * (long long)j + 1], xyz[3 * (long long)j + 2]};
+  double r0;  // undisplaced distance (bohr): selects the B-integral regime of every stencil point
+  {
+    const double dx = Rj[0] - xyz[3 * (long long)i], dy = Rj[1] - xyz[3 * (long long)i + 1], dz = Rj[2] - xyz[3 * (long long)i + 2];
+    r0 = sqrt(dx * dx + dy * dy + dz * dz) * (1.0 / SEQM_A0);
+  }
   double g[3];
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
@@ -601,7 +628,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_gradient_kernel(seqm_b
           for (int q = 0; q < 10; ++q) wsp[a * 10 + q] = (noj > 1 || q == 0) ? wl[a][q] : 0.0;
       }
       SEQM_SYNC();
-      spd_pair_block(b, i, j, dj, Ri, Rj, wsp, sm);
+      spd_pair_block(b, i, j, dj, Ri, Rj, wsp, sm, r0);
       const double dx = Rj[0] - Ri[0], dy = Rj[1] - Ri[1], dz = Rj[2] - Ri[2];
       const double rb = sqrt(dx * dx + dy * dy + dz * dz) * (1.0 / SEQM_A0);
       E[k] = pair_cut(b, rb) ? 0.0 : spd_pair_energy(b, i, j, npi, npj, noi, noj, rb, sm, red);
