@@ -115,6 +115,10 @@ const char* seqm_last_error(void);
 /* largest orbital count for the shared-memory resident solvers (Jacobi eigensolver, in-SM SP2, in-SM DIIS);
  * larger molecules run the global-memory Fock / GEMM-SP2 / GEMM-DIIS path and need sp2=[True, eps] */
 int seqm_max_orbitals(void);
+/* largest orbital count of the eigensolver route: above seqm_max_orbitals() the density / eigenpairs of sym_eig_trunc
+ * (diag.py:110-241) come from a one-sided Jacobi kernel (one CTA per molecule, matrix in shared memory or L2) up to this
+ * size (256); beyond it only the SP2 density is available */
+int seqm_max_orbitals_eig(void);
 
 /* ---- batch plan construction on the device ---------------------------------------------------------------------
  * Replaces Parser.forward (seqm/basics.py:219-403: real-atom compaction, pair list i<j, molecule ids, nHeavy /

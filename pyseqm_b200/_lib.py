@@ -64,9 +64,10 @@ class SeqmError(RuntimeError):
     pass
 
 
-SOURCES = ("seqm_b200.cu", "seqm_spd.cu")  # translation units, compiled in parallel
+SOURCES = ("seqm_b200.cu", "seqm_spd.cu", "seqm_eigh.cu")  # translation units, compiled in parallel
 # files that only one translation unit includes (everything else is shared): an edit there recompiles that unit alone
 _ONLY = {"seqm_spd.cu": {"seqm_spd.cu", "spd_kernels.cuh"},
+         "seqm_eigh.cu": {"seqm_eigh.cu", "hestenes_kernels.cuh"},
          "seqm_b200.cu": {"seqm_b200.cu", "pair_kernels.cuh", "scf_driver.cuh", "plan_kernels.cuh", "eig_kernels.cuh",
                           "fock_kernels.cuh", "large_kernels.cuh"}}  # fmt: skip
 
@@ -117,6 +118,7 @@ class SeqmLib:
             "seqm_abi_version": ([], C.c_int),
             "seqm_last_error": ([], C.c_char_p),
             "seqm_max_orbitals": ([], C.c_int),
+            "seqm_max_orbitals_eig": ([], C.c_int),
             "seqm_plan_count": ([P, C.c_int32, C.c_int32, P, P, C.c_int32, P, P, P, P, P, P, P, P, P,
                                  C.POINTER(SeqmPlanCounts), P, P], C.c_int),
             "seqm_plan_fill": ([P, C.c_int32, C.c_int32, C.POINTER(SeqmPlanCounts), P, P, P, P, P, C.c_int32, C.c_int32,

@@ -54,10 +54,10 @@ class Energy(torch.nn.Module):
                 raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
             plan.set_parameters({k: learned_parameters[k] for k in self.seqm_parameters.get("learned", [])})
         const = molecule.const
-        if plan.large and not self.sp2[0]:
+        if plan.large and not self.sp2[0] and not plan.eig_ok:
             raise NotImplementedError(
-                f"a molecule with {plan.nmax} orbitals exceeds the shared-memory resident eigensolver "
-                f"({plan.lib.dll.seqm_max_orbitals()} orbitals): use the SP2 density, sp2=[True, eps]"
+                f"a molecule with {plan.nmax} orbitals exceeds the eigensolver route "
+                f"({plan.lib.dll.seqm_max_orbitals_eig()} orbitals): use the SP2 density, sp2=[True, eps]"
             )
         t0 = time.time()
         xyz = molecule._refresh_geometry()
@@ -100,8 +100,9 @@ class Energy(torch.nn.Module):
             molecule.w = w
         molecule._gam = w[:, 0, 0]
         prev_mos = molecule.molecular_orbitals  # basics.py:846: the orbitals of the previous forward on this molecule
-        if self.eig and plan.large:
-            # final eigenpairs of a large molecule: one cuSOLVER call outside the SCF hot loop
+        if self.eig and plan.large and not plan.eig_ok:
+            # final eigenpairs of a molecule beyond the one-sided Jacobi kernel (e.g. C380): one cuSOLVER call per
+            # molecule outside the SCF hot loop
             Fd = engine.op_unpack(plan, F)
             N = molecule.orbital_stride * plan.molsize
             e_mo = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)

@@ -140,6 +140,36 @@ static int ensure_tables() {
 
 #endif  // SEQM_SECONDARY_TU
 
+// ---- bulk asynchronous copies (TMA engine, 1-D) and their mbarriers ------------------------------------------------------
+// cp.async.bulk.shared::cluster.global (SASS UBLKCP) moves a contiguous, 16-byte aligned block whose size is a multiple
+// of 16 bytes from global to shared memory without passing through registers; completion is counted in bytes on an
+// mbarrier in shared memory.  One thread arms the barrier (arrive.expect_tx) and issues the copy, consumers spin on
+// try_wait with the phase parity.  (The host emulation has no equivalent: its kernels keep the plain copy loops.)
+#ifndef SEQM_HOSTEMU
+SEQM_D unsigned seqm_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SEQM_D void seqm_mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(seqm_smem_u32(bar)), "r"(count) : "memory");
+}
+SEQM_D void seqm_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+SEQM_D void seqm_bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(seqm_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   seqm_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(seqm_smem_u32(bar))
+               : "memory");
+}
+SEQM_D void seqm_mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  const unsigned a = seqm_smem_u32(bar);
+  while (!ok) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  }
+}
+#endif
+
 // block-wide sum of one double per thread (blockDim.x <= 1024, multiple of 32); result valid in all threads
 SEQM_D double block_sum(double v, double* scratch /* >= 33 doubles */) {
 #ifndef SEQM_HOSTEMU

@@ -95,7 +95,11 @@ SEQM_GLOBAL void fock_kernel(seqm_batch_t b, const double* __restrict__ P, const
 // (w staged in a per-warp shared tile, lanes own the 16 exchange + 10 + 10 Coulomb outputs), X-H and H-H pairs one
 // thread per pair -- writes the exchange blocks F_AB and parks the Coulomb vectors J_A, J_B in shared memory;
 // pass 2 sums them per atom in a fixed order (no atomics) together with the one-centre terms.
-// shared: sP[n*n] | sJ[fock_scratch] | wbuf[warps][100]
+// On the device the density of the molecule and the w blocks of the X-X pairs arrive by bulk asynchronous copies
+// (cp.async.bulk / UBLKCP): P in one transfer, the 800-byte w blocks through a per-warp double buffer whose next block is
+// in flight while the current one is contracted (the kernel was bound by the latency of those dependent loads: long
+// scoreboard 8.9 stalled warps per issue, profiles/others_r01_final.txt).
+// shared: sP[n*n] | sJ[fock_scratch] | wbuf[warps][2][100] | mbarriers[warps][2] + 1
 SEQM_D void tri_decode(int t, int m, int& i, int& j) {  // t-th pair (i<j) of m items, row-major
   i = 0;
   while (t >= m - 1 - i) {
@@ -110,6 +114,7 @@ SEQM_D int tri_index(int i, int j, int m) { return i * (2 * m - i - 1) / 2 + (j 
 // (scf_loop.py:106-147) + the update of the active mask, for the molecule this CTA has just finished.
 struct FockErr {
   int on, use_diis;
+  int bulk;  // stage P and the X-X w blocks by bulk asynchronous copies (default; SEQM_B200_FOCK_BULK=0 keeps the plain loads)
   double eps;
   const double* Pold;
   const double* diis_err;
@@ -133,24 +138,66 @@ SEQM_GLOBAL void fock_pair_kernel(seqm_batch_t b, const double* __restrict__ P, 
   double* JHA = JXB + 10 * nXX;           // [nXH][10] onto the heavy atom
   double* JHB = JHA + 10 * nXH;           // [nXH]     onto the hydrogen
   double* JHH = JHB + nXH;                // [nHH][2]
-  double* wbuf = sP + ((n * n + 1) & ~1) + b.fock_scratch;
+  double* wbuf = sP + ((n * n + 1) & ~1) + ((b.fock_scratch + 1) & ~1);  // 16-byte aligned: destination of bulk copies
   const double* Pm = P + v.mat0;
   const double* Hm = H + v.mat0;
   double* Fm = F + v.mat0;
   const int tid = threadIdx.x, nthr = blockDim.x;
+#ifndef SEQM_HOSTEMU
+  const bool bulk = fe.bulk != 0;
+  const int nwarp = nthr / 32;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbuf + (nwarp + 1) * 200);  // [warp][2], then the P barrier
+  unsigned long long* barP = bars + 2 * (nwarp + 1);
+  if (bulk) {
+    if (tid < 2 * nwarp) seqm_mbar_init(&bars[tid], 1);
+    if (tid == 0) seqm_mbar_init(barP, 1);
+    seqm_mbar_fence_init();
+    SEQM_SYNC();
+    if (tid == 0) seqm_bulk_load(sP, Pm, (unsigned)(sizeof(double) * ((n * n + 1) & ~1)), barP);  // the slot is padded to even
+    seqm_mbar_wait(barP, 0);
+  } else {
+    for (int t = tid; t < n * n; t += nthr) sP[t] = Pm[t];
+    SEQM_SYNC();
+  }
+#else
   for (int t = tid; t < n * n; t += nthr) sP[t] = Pm[t];
   SEQM_SYNC();
+#endif
   // ---- pass 1a: X-X pairs, one warp per pair
   {
     const int L = (nthr >= 32) ? 32 : 1;
     const int lane = tid % L, wid = tid / L, nw = nthr / L;
-    double* wb = wbuf + wid * 100;
-    for (int t = wid; t < nXX; t += nw) {
+    double* wb2 = wbuf + wid * 200;  // this warp's two w tiles
+#ifndef SEQM_HOSTEMU
+    unsigned long long* bar = bars + 2 * wid;
+    if (bulk && lane == 0 && wid < nXX) {
+      int i0, j0;
+      tri_decode(wid, nh, i0, j0);
+      seqm_bulk_load(wb2, w + (long long)(v.p0 + pair_local(v, i0, j0)) * 100, 800u, &bar[0]);
+    }
+#endif
+    int it = 0;
+    for (int t = wid; t < nXX; t += nw, ++it) {
       int i, j;
       tri_decode(t, nh, i, j);
-      const double* wp = w + (long long)(v.p0 + pair_local(v, i, j)) * 100;
-      for (int q = lane; q < 100; q += L) wb[q] = wp[q];
-      SEQM_SYNCWARP();
+      const double* wb = wb2;
+#ifndef SEQM_HOSTEMU
+      if (bulk) {
+        const int cur = it & 1;
+        if (lane == 0 && t + nw < nXX) {  // next block of this warp into the other tile (its readers passed the syncwarp below)
+          int i1, j1;
+          tri_decode(t + nw, nh, i1, j1);
+          seqm_bulk_load(wb2 + (cur ^ 1) * 100, w + (long long)(v.p0 + pair_local(v, i1, j1)) * 100, 800u, &bar[cur ^ 1]);
+        }
+        seqm_mbar_wait(&bar[cur], (unsigned)((it >> 1) & 1));
+        wb = wb2 + cur * 100;
+      } else
+#endif
+      {
+        const double* wp = w + (long long)(v.p0 + pair_local(v, i, j)) * 100;
+        for (int q = lane; q < 100; q += L) wb2[q] = wp[q];
+        SEQM_SYNCWARP();
+      }
       const int oi = 4 * i, oj = 4 * j;
       for (int o = lane; o < 36; o += L) {
         if (o < 16) {  // exchange
@@ -290,7 +337,8 @@ SEQM_GLOBAL void fock_pair_kernel(seqm_batch_t b, const double* __restrict__ P, 
   }
 }
 static inline size_t fock_pair_smem_bytes(int nmax, int scratch, int threads) {
-  return sizeof(double) * ((size_t)((nmax * nmax + 1) & ~1) + scratch + (size_t)(threads / 32 + 1) * 100);
+  const size_t nw1 = (size_t)(threads / 32 + 1);  // per warp: two 100-double w tiles and two mbarriers; + the P barrier
+  return sizeof(double) * ((size_t)((nmax * nmax + 1) & ~1) + (size_t)((scratch + 1) & ~1) + nw1 * 200 + nw1 * 2 + 2);
 }
 
 SEQM_GLOBAL void elec_energy_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,

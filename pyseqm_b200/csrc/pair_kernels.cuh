@@ -152,7 +152,10 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
     const double* Pm = P + v.mat0;
     const double* Dm = D + v.mat0;
     const int n = v.n, oi = orb_off(v, i - v.a0), oj = orb_off(v, j - v.a0);
-    if (i - v.a0 < v.nsh) continue;  // pair with a d atom: spd_pair_gradient_kernel owns gpair[p]
+    // PM6 pair with a d atom: this kernel differentiates its sp x sp part only (two-electron sp block, core attraction
+    // of the sp products, core-core); the resonance term (9 x 9 overlaps) and everything with a d orbital is added by
+    // spd_pair_gradient_kernel
+    const bool ypair = (i - v.a0) < v.nsh;
     PairGeom<double> g;
     pair_geom(xyz, i, j, g);
     if (pair_cut(b, g.r)) {
@@ -164,7 +167,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(128, (CLS >= 1) ? SEQM_PG_MINB : 0) pair_gr
     double dEdr = 0.0, dEde[3] = {0.0, 0.0, 0.0};
 
     // ---- resonance integrals: Q_mu,nu = D_mu,nu (beta_mu^A + beta_nu^B)
-    if (g.r <= SEQM_OVERLAP_CUTOFF) {
+    if (!ypair && g.r <= SEQM_OVERLAP_CUTOFF) {
       const double bsi = par(b, SEQM_P_BS, i), bpi = par(b, SEQM_P_BP, i);
       const double bsj = par(b, SEQM_P_BS, j), bpj = par(b, SEQM_P_BP, j);
       const int na = (int)par(b, SEQM_P_QN, i), nb = (int)par(b, SEQM_P_QN, j);

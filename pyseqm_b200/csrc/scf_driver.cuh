@@ -103,6 +103,7 @@ SEQM_GLOBAL void scf_init_kernel(seqm_batch_t b, ScfWork W, int converger) {
         W.ctrl[h].reset = 0;
         W.ctrl[h].counter = -1;
         W.ctrl[h].cF = 0;
+        for (int q = 0; q < 4; ++q) W.ctrl[h].pad[q] = 0;  // pad[0..1]: pass counters of the adaptive mixing
       }
       for (int i = 0; i < 4; ++i) W.rflag[i] = 0;
     }
@@ -381,19 +382,52 @@ SEQM_GLOBAL void mix_linear_kernel(seqm_batch_t b, ScfWork W, double* __restrict
   }
 }
 
-// adaptive mixing, diagonal part (scf_loop.py:350-415).  ONE CTA for the whole batch because the
-// renormalisation loop of the reference stops only when EVERY active molecule is normalised
-// (`if torch.all(done): break`, scf_loop.py:404), and until then it rescales all of them.
-// Molecules are statically assigned to threads; per-molecule state lives in W.fac / W.sum0 / W.dnew.
-SEQM_GLOBAL void adaptive_diag_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ P, int k) {
-  __shared__ int s_flag;
+// adaptive mixing, diagonal part (scf_loop.py:350-415).  The renormalisation loop of the reference stops only when
+// EVERY active molecule is normalised (`if torch.all(done): break`, scf_loop.py:404) and until then it rescales all of
+// them, so the number of rescaling passes K is a batch-global quantity.  Two kernels, one thread per molecule:
+//   adaptive_diag_a_kernel  FAC, the capped / extrapolated diagonal, SUM0, and the passes this molecule needs on its own
+//                           (they are applied in place); K = max over the batch by atomicMax into ctrl->pad[k & 1]
+//   adaptive_diag_b_kernel  the K - own further passes every molecule still owes (same arithmetic, same order)
+// (round 1 ran this as ONE 1024-thread CTA for the whole batch: 0.12 ms per SCF iteration at 2048 molecules.)
+SEQM_D bool adaptive_pass(double* dn, int n, double* sum0) {  // one pass of scf_loop.py:396-412; true = this molecule is done
+  double sum2 = 0.0;
+  for (int i = 0; i < n; ++i) sum2 += dn[i];
+  const bool large = sum2 > 1.0e-3;
+  const double sum3 = large ? *sum0 / sum2 : 0.0;
+  if (!(large && !(fabs(sum3 - 1.0) <= 1.0e-5))) return true;
+  int nfull = 0;
+  for (int i = 0; i < n; ++i) {
+    double s = fmax(dn[i] * sum3, 0.0);
+    if (s > 2.0) {
+      s = 2.0;
+      ++nfull;
+    }
+    dn[i] = s;
+  }
+  *sum0 -= 2.0 * nfull;
+  return false;
+}
+// a pass applied to a molecule that is already done on its own but rides along with the batch (rescales unconditionally)
+SEQM_D void adaptive_pass_forced(double* dn, int n, double* sum0) {
+  double sum2 = 0.0;
+  for (int i = 0; i < n; ++i) sum2 += dn[i];
+  const double sum3 = (sum2 > 1.0e-3) ? *sum0 / sum2 : 0.0;
+  int nfull = 0;
+  for (int i = 0; i < n; ++i) {
+    double s = fmax(dn[i] * sum3, 0.0);
+    if (s > 2.0) {
+      s = 2.0;
+      ++nfull;
+    }
+    dn[i] = s;
+  }
+  *sum0 -= 2.0 * nfull;
+}
+SEQM_GLOBAL void adaptive_diag_a_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ P, int k) {
   const bool third = (k % 3) == 0;
   const double DAMP = (k > 4) ? 0.05 : 1.0e10;
-  const int per = (b.nmol + blockDim.x - 1) / blockDim.x;
-  // FAC, capped / extrapolated diagonal, SUM0
-  for (int q = 0; q < per; ++q) {
-    const int mol = threadIdx.x + q * blockDim.x;
-    if (mol >= b.nmol || !W.active[mol]) continue;
+  for (int mol = blockIdx.x * blockDim.x + threadIdx.x; mol < b.nmol; mol += gridDim.x * blockDim.x) {
+    if (!W.active[mol]) continue;
     const MolView v = mol_view(b, mol);
     const int n = v.n;
     double* dn = W.dnew + (long long)mol * b.nmax;
@@ -424,48 +458,28 @@ SEQM_GLOBAL void adaptive_diag_kernel(seqm_batch_t b, ScfWork W, const double* _
       dn[i] = fmin(fmax(d, 0.0), 2.0);
       sum0 += dc;
     }
+    int own = 0;
+    while (own < 20 && !adaptive_pass(dn, n, &sum0)) ++own;
     W.sum0[mol] = sum0;
-  }
-  // renormalise sum(diag) to SUM0, at most 20 passes, batch-global exit test
-  for (int pass = 0; pass < 20; ++pass) {
-    if (threadIdx.x == 0) s_flag = 1;
-    SEQM_SYNC();
-    for (int q = 0; q < per; ++q) {
-      const int mol = threadIdx.x + q * blockDim.x;
-      if (mol >= b.nmol || !W.active[mol]) continue;
-      const int n = mol_view(b, mol).n;
-      const double* dn = W.dnew + (long long)mol * b.nmax;
-      double sum2 = 0.0;
-      for (int i = 0; i < n; ++i) sum2 += dn[i];
-      const bool large = sum2 > 1.0e-3;
-      const double sum3 = large ? W.sum0[mol] / sum2 : 0.0;
-      W.sum3[mol] = sum3;
-      if (large && !(fabs(sum3 - 1.0) <= 1.0e-5)) s_flag = 0;  // benign race: every writer stores 0
-    }
-    SEQM_SYNC();
-    const int alldone = s_flag;
-    SEQM_SYNC();
-    if (alldone) break;
-    for (int q = 0; q < per; ++q) {
-      const int mol = threadIdx.x + q * blockDim.x;
-      if (mol >= b.nmol || !W.active[mol]) continue;
-      const int n = mol_view(b, mol).n;
-      double* dn = W.dnew + (long long)mol * b.nmax;
-      const double sum3 = W.sum3[mol];
-      int nfull = 0;
-      for (int i = 0; i < n; ++i) {
-        double s = fmax(dn[i] * sum3, 0.0);
-        if (s > 2.0) {
-          s = 2.0;
-          ++nfull;
-        }
-        dn[i] = s;
-      }
-      W.sum0[mol] -= 2.0 * nfull;
-    }
-    SEQM_SYNC();
+    W.sum3[mol] = (double)own;  // passes already applied to this molecule
+    seqm_atomic_max(&W.ctrl->pad[k & 1], own);
   }
 }
+SEQM_GLOBAL void adaptive_diag_b_kernel(seqm_batch_t b, ScfWork W, int k) {
+  const int K = W.ctrl->pad[k & 1];
+  for (int mol = blockIdx.x * blockDim.x + threadIdx.x; mol < b.nmol; mol += gridDim.x * blockDim.x) {
+    if (!W.active[mol]) continue;
+    const int own = (int)W.sum3[mol];
+    if (own >= K) continue;
+    const int n = mol_view(b, mol).n;
+    double* dn = W.dnew + (long long)mol * b.nmax;
+    double sum0 = W.sum0[mol];
+    for (int q = own; q < K; ++q) adaptive_pass_forced(dn, n, &sum0);
+    W.sum0[mol] = sum0;
+  }
+}
+// clears the pass counter of the NEXT iteration (runs after adaptive_diag_b_kernel on the same stream)
+SEQM_GLOBAL void adaptive_diag_reset_kernel(ScfWork W, int k) { W.ctrl->pad[(k + 1) & 1] = 0; }
 // adaptive mixing, matrix part (scf_loop.py:373-383, 417-420, 546-554)
 SEQM_GLOBAL void adaptive_apply_kernel(seqm_batch_t b, ScfWork W, double* __restrict__ P) {
   const int mol = b.mol_order[blockIdx.x];

@@ -14,6 +14,11 @@ int spd_launch_hcore(const seqm_batch_t* b, const double* w, const double* hab, 
 int spd_launch_fock(const seqm_batch_t* b, const double* P, const double* H, const double* w, double* F,
                     const int32_t* active, int smem_limit, cudaStream_t st);
 int spd_launch_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* gp, cudaStream_t st);
+// mid-size eigensolver (one-sided Jacobi, 119..256 orbitals): third translation unit (seqm_eigh.cu)
+int hestenes_set_attributes(int smem_optin);
+int hestenes_max_orbitals(void);
+int hestenes_launch(const seqm_batch_t* b, const double* F, double* P, double* evals, double* C, const int32_t* active,
+                    int smem_optin, cudaStream_t st);
 
 #ifndef SEQM_HOSTEMU
 #define SEQM_STREAM(s) ((cudaStream_t)(s))
@@ -100,6 +105,7 @@ static int ensure_device() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess && spd_set_attributes(g_smem_optin) != SEQM_OK) return SEQM_ERR_CUDA;
+  if (e == cudaSuccess && hestenes_set_attributes(g_smem_optin) != SEQM_OK) return SEQM_ERR_CUDA;
   if (e != cudaSuccess) {
     seqm_set_error("cudaFuncSetAttribute(max dynamic shared memory %d): %s", dyn, cudaGetErrorString(e));
     cudaGetLastError();
@@ -223,6 +229,8 @@ static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, 
   if (fused) *fused = false;
   FockErr none;
   memset(&none, 0, sizeof(none));
+  static const int fock_bulk = (getenv("SEQM_B200_FOCK_BULK") && atoi(getenv("SEQM_B200_FOCK_BULK")) == 0) ? 0 : 1;
+  none.bulk = fock_bulk;
   if (b->method == SEQM_PM6_D) {  // 9 x 9 atom blocks, ragged integral blocks of the pairs with a d atom
     if (!b->wd && b->n_ypairs > 0) {
       seqm_set_error("PM6 with d orbitals: b->wd is not set (seqm_pair_integrals_d comes first)");
@@ -241,7 +249,9 @@ static int launch_fock(const seqm_batch_t* b, const double* P, const double* H, 
   const int nt = threads_for(b->nmax);
   const size_t sm_pair = fock_pair_smem_bytes(b->nmax, b->fock_scratch, nt);
   if (b->fock_scratch > 0 && sm_pair <= (size_t)(g_smem_optin - 2048)) {  // pair-centric: w read once
-    PROF(PK_FOCK, st, SEQM_LAUNCH(fock_pair_kernel, b->nmol, nt, sm_pair, st, *b, P, H, w, F, active, fe ? *fe : none));
+    FockErr fe2 = fe ? *fe : none;
+    fe2.bulk = fock_bulk;
+    PROF(PK_FOCK, st, SEQM_LAUNCH(fock_pair_kernel, b->nmol, nt, sm_pair, st, *b, P, H, w, F, active, fe2));
     if (fused) *fused = (fe != nullptr);
     return seqm_check_launch("fock_pair_kernel");
   }
@@ -532,6 +542,7 @@ extern "C" {
 int seqm_abi_version(void) { return SEQM_ABI_VERSION; }
 const char* seqm_last_error(void) { return g_seqm_err; }
 int seqm_max_orbitals(void) { return SEQM_MAX_ORB; }
+int seqm_max_orbitals_eig(void) { return hestenes_max_orbitals(); }
 
 
 long long seqm_launch_count(void) { return g_seqm_launches; }
@@ -718,8 +729,10 @@ int seqm_eig_density(const seqm_batch_t* b, const double* F, double* P, double* 
   SEQM_SERIAL;
   int rc = check_batch(b);
   if (rc) return rc;
-  rc = check_small(b, "seqm_eig_density");
-  if (rc) return rc;
+  if (b->nmax > SEQM_MAX_ORB) {  // mid-size molecules: one-sided Jacobi in its own kernel (always a cold solve)
+    PROF(PK_JACOBI, SEQM_STREAM(stream), rc = hestenes_launch(b, F, P, evals, C, active, g_smem_optin, SEQM_STREAM(stream)));
+    return rc;
+  }
   PROF(PK_JACOBI, SEQM_STREAM(stream), rc = launch_jacobi(b, F, P, evals, C, Cguess, active, SEQM_STREAM(stream)));
   return rc;
 }
@@ -1167,9 +1180,9 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
   HostMol* hm = nullptr;
   int32_t* h_active = nullptr;
   if (large) {
-    if (!o->use_sp2) {
-      seqm_set_error("molecules above %d orbitals need the SP2 density (sp2=[True, eps]); the batched Jacobi eigensolver "
-                     "is shared-memory resident", SEQM_MAX_ORB);
+    if (!o->use_sp2 && b->nmax > hestenes_max_orbitals()) {
+      seqm_set_error("molecules above %d orbitals need the SP2 density (sp2=[True, eps]): the eigensolver route ends at %d "
+                     "orbitals (one-sided Jacobi)", hestenes_max_orbitals(), hestenes_max_orbitals());
       return SEQM_ERR_TOO_LARGE;
     }
     hmv.resize(b->nmol);
@@ -1265,7 +1278,11 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       }
     }
     // Pnew from F on the active molecules
-    if (large) {
+    if (large && !o->use_sp2) {  // eigensolver route of mid-size molecules (<= 256 orbitals): all active molecules, one launch
+      PROF(PK_JACOBI, st, rc = hestenes_launch(b, F, W.Pnew, (double*)nullptr, W.C, W.active, g_smem_optin, st));
+      if (rc) return rc;
+      have_C = 1;
+    } else if (large) {
       for (int m = 0; m < b->nmol; ++m) {
         if (!h_active[m]) continue;
         rc = sp2_large_one(hm[m].n, hm[m].nocc, F + hm[m].mat0, W.Pnew + hm[m].mat0, o->sp2_eps, W.Xl, W.X2l, W.sp2st,
@@ -1286,8 +1303,10 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
       PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(mix_linear_kernel, b->nmol, 256, 0, st, *b, W, P, o->alpha));
       CHK("mix_linear_kernel");
     } else if (o->converger == 1) {
-      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_diag_kernel, 1, 1024, 0, st, *b, W, P, k));
-      CHK("adaptive_diag_kernel");
+      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_diag_a_kernel, grid1d(b->nmol, 64), 64, 0, st, *b, W, (const double*)P, k));
+      PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_diag_b_kernel, grid1d(b->nmol, 64), 64, 0, st, *b, W, k));
+      SEQM_LAUNCH(adaptive_diag_reset_kernel, 1, 1, 0, st, W, k);
+      CHK("adaptive_diag kernels");
       PROF(PK_MIX, SEQM_STREAM(stream), SEQM_LAUNCH(adaptive_apply_kernel, b->nmol, 256, 0, st, *b, W, P));
       CHK("adaptive_apply_kernel");
     } else if (!large) {

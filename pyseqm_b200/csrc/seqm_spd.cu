@@ -9,7 +9,6 @@ int spd_set_attributes(int smem_optin) {
 #ifndef SEQM_HOSTEMU
   const int pair_smem = (int)(sizeof(double) * SPD_SMEM_DOUBLES);
   cudaError_t e = cudaFuncSetAttribute(spd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(spd_pair_gradient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(spd_fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 2048);
   if (e != cudaSuccess) {
     seqm_set_error("cudaFuncSetAttribute(spd kernels): %s", cudaGetErrorString(e));
@@ -41,6 +40,6 @@ int spd_launch_fock(const seqm_batch_t* b, const double* P, const double* H, con
   return seqm_check_launch("spd_fock_kernel");
 }
 int spd_launch_gradient(const seqm_batch_t* b, const double* xyz, const double* P, double* gp, cudaStream_t st) {
-  SEQM_LAUNCH(spd_pair_gradient_kernel, b->n_ypairs, SPD_THREADS, sizeof(double) * SPD_SMEM_DOUBLES, st, *b, xyz, P, gp);
+  SEQM_LAUNCH(spd_pair_gradient_kernel, b->n_ypairs, SPD_THREADS, sizeof(double) * SPG_SMEM_DOUBLES, st, *b, xyz, P, gp);
   return seqm_check_launch("spd_pair_gradient_kernel");
 }

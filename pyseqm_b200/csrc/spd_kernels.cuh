@@ -5,7 +5,7 @@
 //                          9 x 9 overlap block
 //   spd_hcore_kernel       one CTA per molecule: packed Hcore with 9 x 9 / 4 x 4 / 1 x 1 atom blocks
 //   spd_fock_kernel        one CTA per molecule: F = H + one-centre (sp parameters + Slater-Condon d integrals) + J - K/2
-//   spd_pair_gradient_kernel  one CTA per Y pair: dE_pair/dR_i by a five-point stencil through the same pair code
+//   spd_pair_gradient_kernel  one CTA per Y pair: five-point stencil of the d-dependent pair energy, evaluated in the local frame
 //
 // Replaces (reference file:line, lanl/PYSEQM v2.0.0):
 //   two_elec_two_center_int_local_frame_d_orbitals.py:23-4164   local-frame integrals with d orbitals
@@ -70,44 +70,59 @@ SEQM_HD void spd_load_atom(const seqm_batch_t& b, int a, bool has_d, SpdAtom& A)
   A.n[2] = (int)par(b, SEQM_P_QND, a);
 }
 
-// point charges (q, x, y, z) of the unit multipole (l, |m|) with separation D; returns their number (<= 6)
-SEQM_HD int spd_configuration(int l, int am, double D, double q[6], double x[6], double y[6], double z[6]) {
-  for (int k = 0; k < 6; ++k) q[k] = x[k] = y[k] = z[k] = 0.0;
-  if (l == 0) { q[0] = 1.0; return 1; }
-  if (l == 1) {
+// point charges (q, x, y, z) of the unit multipole (l, |m|) with separation D: 1 (monopole), 2 (dipole), 6 ((2,0)) or
+// 4 ((2,1), (2,2)) of them.  N is the compile-time count, so the arrays live in registers.
+SEQM_HD int spd_ncharge(int l, int am) { return l == 0 ? 1 : (l == 1 ? 2 : (am == 0 ? 6 : 4)); }
+template <int N>
+SEQM_D void spd_configuration(int am, double D, double* q, double* x, double* y, double* z) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) q[k] = x[k] = y[k] = z[k] = 0.0;
+  if (N == 1) {
+    q[0] = 1.0;
+  } else if (N == 2) {
     q[0] = 0.5; q[1] = -0.5;
     if (am == 0) { z[0] = D; z[1] = -D; } else { x[0] = D; x[1] = -D; }
-    return 2;
-  }
-  const double r2 = SPD_SQRT2 * D;
-  if (am == 0) {  // Q~zx + 1/2 Q~xy: +1/4 at z = +-sqrt2 D, -1/8 at x = +-sqrt2 D and y = +-sqrt2 D
+  } else if (N == 6) {  // Q~zx + 1/2 Q~xy: +1/4 at z = +-sqrt2 D, -1/8 at x = +-sqrt2 D and y = +-sqrt2 D
+    const double r2 = SPD_SQRT2 * D;
     q[0] = q[1] = 0.25; z[0] = r2; z[1] = -r2;
     q[2] = q[3] = -0.125; x[2] = r2; x[3] = -r2;
     q[4] = q[5] = -0.125; y[4] = r2; y[5] = -r2;
-    return 6;
+  } else if (am == 1) {  // (2,1): +-1/4 at (+-D, 0, +-D)
+    q[0] = 0.25; x[0] = D; z[0] = D;
+    q[1] = -0.25; x[1] = D; z[1] = -D;
+    q[2] = -0.25; x[2] = -D; z[2] = D;
+    q[3] = 0.25; x[3] = -D; z[3] = -D;
+  } else {  // (2,2): +1/4 at x = +-sqrt2 D, -1/4 at y = +-sqrt2 D
+    const double r2 = SPD_SQRT2 * D;
+    q[0] = q[1] = 0.25; x[0] = r2; x[1] = -r2;
+    q[2] = q[3] = -0.25; y[2] = r2; y[3] = -r2;
   }
-  if (am == 1) {  // +-1/4 at (+-D, 0, +-D)
-    int k = 0;
-    for (int sa = 1; sa >= -1; sa -= 2)
-      for (int sb = 1; sb >= -1; sb -= 2) { q[k] = 0.25 * sa * sb; x[k] = sa * D; z[k] = sb * D; ++k; }
-    return 4;
-  }
-  q[0] = q[1] = 0.25; x[0] = r2; x[1] = -r2;  // (2,2): +1/4 at x = +-sqrt2 D, -1/4 at y = +-sqrt2 D
-  q[2] = q[3] = -0.25; y[2] = r2; y[3] = -r2;
-  return 4;
+}
+template <int NA, int NB>
+SEQM_D double spd_interaction_t(int am, double Da, double Db, double add, double r) {
+  double qa[NA], xa[NA], ya[NA], za[NA], qb[NB], xb[NB], yb[NB], zb[NB];
+  spd_configuration<NA>(am, Da, qa, xa, ya, za);
+  spd_configuration<NB>(am, Db, qb, xb, yb, zb);
+  double tot = 0.0;
+#pragma unroll
+  for (int i = 0; i < NA; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const double dx = xa[i] - xb[j], dy = ya[i] - yb[j], dz = za[i] - zb[j] + r;
+      tot += qa[i] * qb[j] * seqm_rsqrt(dx * dx + dy * dy + dz * dz + add);
+    }
+  return tot;
 }
 // interaction (eV) of multipole (ls, am) of atom i at the origin with (lt, am) of atom j at z = -r
 SPD_NOINLINE double spd_interaction(int ls, int lt, int am, double Da, double Db, double add, double r) {
-  double qa[6], xa[6], ya[6], za[6], qb[6], xb[6], yb[6], zb[6];
-  const int na = spd_configuration(ls, am, Da, qa, xa, ya, za);
-  const int nb = spd_configuration(lt, am, Db, qb, xb, yb, zb);
-  double tot = 0.0;
-  for (int i = 0; i < na; ++i)
-    for (int j = 0; j < nb; ++j) {
-      const double dx = xa[i] - xb[j], dy = ya[i] - yb[j], dz = za[i] - zb[j] + r;
-      tot += qa[i] * qb[j] / sqrt(dx * dx + dy * dy + dz * dz + add);
-    }
-  return SEQM_EV * tot;
+  const int na = spd_ncharge(ls, am), nb = spd_ncharge(lt, am);
+  double t;
+#define SPD_CASE(A_, B_) if (na == A_ && nb == B_) t = spd_interaction_t<A_, B_>(am, Da, Db, add, r); else
+  SPD_CASE(1, 1) SPD_CASE(1, 2) SPD_CASE(1, 4) SPD_CASE(1, 6) SPD_CASE(2, 1) SPD_CASE(2, 2) SPD_CASE(2, 4) SPD_CASE(2, 6)
+  SPD_CASE(4, 1) SPD_CASE(4, 2) SPD_CASE(4, 4) SPD_CASE(4, 6) SPD_CASE(6, 1) SPD_CASE(6, 2) SPD_CASE(6, 4) SPD_CASE(6, 6)
+  t = 0.0;
+#undef SPD_CASE
+  return SEQM_EV * t;
 }
 
 // local axes of the reference (RotationMatrixD.py:11-45, MOPAC rotmat) for the unit vector w (local z):
@@ -126,36 +141,26 @@ SEQM_HD void spd_local_axes(const double w[3], double u[3], double v[3], double*
   if (ca_o) { *ca_o = ca; *sb_o = sb; *cb_o = cb; }
 }
 // R[a][b] (9 x 9, row-major in R81): molecular orbital a = sum_b R[a][b] local orbital b.
-// molecular order s, px, py, pz, d(x2-y2), d(xz), d(z2), d(yz), d(xy); local order s, p(z, x, y), d(z2, xz, yz, x2-y2, xy)
-SPD_NOINLINE void spd_orbital_rotation(const double u[3], const double v[3], const double w[3], double* R81) {
-  for (int k = 0; k < 81; ++k) R81[k] = 0.0;
-  R81[0] = 1.0;
-  for (int c = 0; c < 3; ++c) {
-    R81[(1 + c) * 9 + 1] = w[c];
-    R81[(1 + c) * 9 + 2] = u[c];
-    R81[(1 + c) * 9 + 3] = v[c];
-  }
-  const double is3 = 1.0 / SPD_SQRT3;
-  for (int bq = 0; bq < 5; ++bq) {  // quadratic form Q of the local d function bq in molecular components
-    double Q[3][3];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        double t;
-        if (bq == 0) t = (2.0 * w[i] * w[j] - u[i] * u[j] - v[i] * v[j]) * is3;
-        else if (bq == 1) t = u[i] * w[j] + w[i] * u[j];
-        else if (bq == 2) t = v[i] * w[j] + w[i] * v[j];
-        else if (bq == 3) t = u[i] * u[j] - v[i] * v[j];
-        else t = u[i] * v[j] + v[i] * u[j];
-        Q[i][j] = t;
-      }
-    R81[4 * 9 + 4 + bq] = 0.5 * (Q[0][0] - Q[1][1]);
-    R81[5 * 9 + 4 + bq] = Q[0][2];
-    R81[6 * 9 + 4 + bq] = 0.5 * SPD_SQRT3 * Q[2][2];
-    R81[7 * 9 + 4 + bq] = Q[1][2];
-    R81[8 * 9 + 4 + bq] = Q[0][1];
-  }
+// molecular order s, px, py, pz, d(x2-y2), d(xz), d(z2), d(yz), d(xy); local order s, p(z, x, y), d(z2, xz, yz, x2-y2, xy).
+// The d block expands the quadratic form Q of each local d function (in molecular components) in the molecular forms.
+SEQM_HD double spd_dform(int bq, int i, int j, const double u[3], const double v[3], const double w[3]) {
+  if (bq == 0) return (2.0 * w[i] * w[j] - u[i] * u[j] - v[i] * v[j]) * (1.0 / SPD_SQRT3);
+  if (bq == 1) return u[i] * w[j] + w[i] * u[j];
+  if (bq == 2) return v[i] * w[j] + w[i] * v[j];
+  if (bq == 3) return u[i] * u[j] - v[i] * v[j];
+  return u[i] * v[j] + v[i] * u[j];
 }
-
+SEQM_HD double spd_rotation_element(int a, int bq, const double u[3], const double v[3], const double w[3]) {
+  if (a == 0 || bq == 0) return (a == bq) ? 1.0 : 0.0;
+  if (a < 4) return (bq == 1) ? w[a - 1] : (bq == 2 ? u[a - 1] : (bq == 3 ? v[a - 1] : 0.0));
+  if (bq < 4) return 0.0;
+  const int d = bq - 4;
+  if (a == 4) return 0.5 * (spd_dform(d, 0, 0, u, v, w) - spd_dform(d, 1, 1, u, v, w));
+  if (a == 5) return spd_dform(d, 0, 2, u, v, w);
+  if (a == 6) return 0.5 * SPD_SQRT3 * spd_dform(d, 2, 2, u, v, w);
+  if (a == 7) return spd_dform(d, 1, 2, u, v, w);
+  return spd_dform(d, 0, 1, u, v, w);
+}
 // ---- Slater overlaps with d functions -------------------------------------------------------------------------------
 // 14 local overlaps (la, lb, m): the polynomial of the prolate-spheroidal integrand times its angular constant comes from
 // b.ovl_poly[na-1][nb-1][kind][k][l] (host-built, pm6d_tables.py), auxiliary integrals A_k, B_l as in the sp path.
@@ -211,6 +216,47 @@ SPD_NOINLINE double spd_local_overlap(const seqm_batch_t& b, const SpdAtom& A, c
   return pre * ipow(0.5 * r, na + nb + 1) * tot;
 }
 
+// Sparse form of the multipole coefficient tables in shared memory: per orbital product at most 4 (here: 3) non-zero
+// (source, m) entries.  cv[side][45][4] values, cc[side][45][4] codes s * 5 + m5 (-1 = unused); side 0 = atom i (the
+// "yx" table when the partner is an sp-only heavy atom: reference quirk), side 1 = atom j.  All threads call it.
+SEQM_D void spd_stage_coefficients(const seqm_batch_t& b, bool yx, double* cv, int* cc) {
+  const double* tab_i = yx ? b.mp_coef_yx : b.mp_coef;
+  for (int t = threadIdx.x; t < 90; t += blockDim.x) {
+    const int side = t / 45, kl = t % 45;
+    const double* tab = side ? b.mp_coef : tab_i;
+    int cnt = 0;
+    for (int q = 0; q < SPD_NSRC * 5 && cnt < 4; ++q) {
+      const double cval = tab[kl * SPD_NSRC * 5 + q];
+      if (cval != 0.0) {
+        cv[side * 180 + kl * 4 + cnt] = cval;
+        cc[side * 180 + kl * 4 + cnt] = q;
+        ++cnt;
+      }
+    }
+    for (; cnt < 4; ++cnt) cc[side * 180 + kl * 4 + cnt] = -1;
+  }
+}
+// local integral (kl | mn) from the staged coefficients and the unit multipole interactions V[s][t][|m|]
+SEQM_D double spd_local_integral(int kl, int mn, const double* cv, const int* cc, const double* V) {
+  double L = 0.0;
+  for (int x = 0; x < 4; ++x) {
+    const int ca_code = cc[kl * 4 + x];
+    if (ca_code < 0) break;
+    const int s = ca_code / 5, m5 = ca_code % 5;
+    const int am = (m5 == 0) ? 0 : (m5 < 3 ? 1 : 2);
+    double in = 0.0;
+    for (int y = 0; y < 4; ++y) {
+      const int cb_code = cc[180 + mn * 4 + y];
+      if (cb_code < 0) break;
+      if (cb_code % 5 == m5) in += V[(s * SPD_NSRC + cb_code / 5) * 3 + am] * cv[180 + mn * 4 + y];
+    }
+    L += cv[kl * 4 + x] * in;
+  }
+  // reference quirk: (d-sigma p-pi(y) | p-pi(y) s) carries -0.577350 where its neighbours carry -1/sqrt3
+  if (kl == 13 && mn == 6) L += (-0.577350 + 1.0 / SPD_SQRT3) * V[(4 * SPD_NSRC + 1) * 3 + 1];
+  return L;
+}
+
 // ---- the block of one Y pair in shared memory ---------------------------------------------------------------------------
 // layout of the CTA's dynamic shared memory (doubles)
 #define SPD_OFF_T 0       /* 45 x 45 pair-product transform */
@@ -219,19 +265,22 @@ SPD_NOINLINE double spd_local_overlap(const seqm_batch_t& b, const SpdAtom& A, c
 #define SPD_OFF_R 6075    /* 9 x 9 orbital rotation */
 #define SPD_OFF_V 6156    /* 7 x 7 x 3 unit multipole interactions */
 #define SPD_OFF_S 6303    /* 9 x 9 local overlaps, then beta-scaled molecular-frame block */
-#define SPD_OFF_SP 6384   /* 10 x 10 sp x sp block of the sp path (gradient kernel recomputes it per geometry) */
-#define SPD_OFF_X 6484    /* scratch: densities of the gradient kernel (81 + 45 + 45) + reductions */
-#define SPD_SMEM_DOUBLES 6720
+#define SPD_OFF_CV 6384   /* staged sparse coefficients: values [2][45][4] */
+#define SPD_OFF_CC 6744   /* and codes (ints) */
+#define SPD_SMEM_DOUBLES 6924
 
 // Fills sm[SPD_OFF_L ..] with w (np_i x np_j) and sm[SPD_OFF_S ..] with hab (9 x 9, beta-scaled overlaps) for atoms
 // i (a d atom) and j at positions Ri, Rj (Angstrom).  wsp: the pair's 10 x 10 block of the sp path at this geometry.
 // All threads of the CTA call it; it ends with a barrier.
 SPD_NOINLINE void spd_pair_block(const seqm_batch_t& b, int i, int j, bool dj, const double* Ri, const double* Rj,
-                           const double* wsp, double* sm, double r_regime) {
+                           const double* wsp, double* sm) {
   const int tid = threadIdx.x, nthr = blockDim.x;
-  SpdAtom A, B;
-  spd_load_atom(b, i, true, A);
-  spd_load_atom(b, j, dj, B);
+  __shared__ SpdAtom sAB[2];  // the two atoms' parameters: one copy per CTA instead of a stack copy per thread
+  if (tid == 0) spd_load_atom(b, i, true, sAB[0]);
+  if (tid == 1 || nthr == 1) spd_load_atom(b, j, dj, sAB[1]);
+  SEQM_SYNC();
+  const SpdAtom& A = sAB[0];
+  const SpdAtom& B = sAB[1];
   const int npi = A.nprod, npj = B.nprod;
   double e[3] = {Rj[0] - Ri[0], Rj[1] - Ri[1], Rj[2] - Ri[2]};
   const double dist = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
@@ -253,13 +302,14 @@ SPD_NOINLINE void spd_pair_block(const seqm_batch_t& b, int i, int j, bool dj, c
   const double w3[3] = {-e[0], -e[1], -e[2]};
   double u3[3], v3[3];
   spd_local_axes(w3, u3, v3, nullptr, nullptr, nullptr);
-  if (tid == 0) spd_orbital_rotation(u3, v3, w3, R);
+  for (int t = tid; t < 81; t += nthr) R[t] = spd_rotation_element(t / 9, t % 9, u3, v3, w3);
+  spd_stage_coefficients(b, !dj && B.norb == 4, sm + SPD_OFF_CV, reinterpret_cast<int*>(sm + SPD_OFF_CC));
   // unit multipole interactions
   for (int t = tid; t < SPD_NSRC * SPD_NSRC * 3; t += nthr) {
     const int s = t / (SPD_NSRC * 3), tt = (t / 3) % SPD_NSRC, am = t % 3;
     const int ls = spd_src_l(s), lt = spd_src_l(tt);
     double val = 0.0;
-    const bool have = (tt < 3 || dj) && (tt == 0 || B.norb > 1);  // sources the partner atom carries
+    const bool have = (tt < 3 || dj) && (tt == 0 || B.norb > 1) && (s >= 3 || tt >= 3);  // sources in play
     if (am <= ls && am <= lt && have) {
       const double add = (A.rho[s] + B.rho[tt]) * (A.rho[s] + B.rho[tt]);
       val = spd_interaction(ls, lt, am, A.D[s], B.D[tt], add, r);
@@ -275,7 +325,7 @@ SPD_NOINLINE void spd_pair_block(const seqm_batch_t& b, int i, int j, bool dj, c
       spd_kind(kind, &la, &lb, &m);
       const int oa = (la == 0) ? 0 : (la == 1 ? 1 : 4), ob = (lb == 0) ? 0 : (lb == 1 ? 1 : 4);
       if (oa >= A.norb || ob >= B.norb) continue;
-      const double sv = spd_local_overlap(b, A, B, kind, r, r_regime > 0.0 ? r_regime : r);
+      const double sv = spd_local_overlap(b, A, B, kind, r, r);
       // local orbital of (l, m): p: sigma 1, pi 2,3 ; d: sigma 4, pi 5,6, delta 7,8.  Reflection z -> -z: (-1)^(l+m)
       const double sg = (((la + m) & 1) ? -1.0 : 1.0) * (((lb + m) & 1) ? -1.0 : 1.0);
       const int ia = (m == 0) ? oa : (la == 1 ? 2 : (m == 1 ? 5 : 7));
@@ -294,28 +344,11 @@ SPD_NOINLINE void spd_pair_block(const seqm_batch_t& b, int i, int j, bool dj, c
   }
   SEQM_SYNC();
   // local integrals
-  const double* ci = (!dj && B.norb == 4) ? b.mp_coef_yx : b.mp_coef;  // reference quirk: sign of d-sigma d-delta in (d, sp) pairs
-  const double* cj = b.mp_coef;
+  const double* cv = sm + SPD_OFF_CV;
+  const int* cc = reinterpret_cast<const int*>(sm + SPD_OFF_CC);
   for (int t = tid; t < npi * npj; t += nthr) {
     const int kl = t / npj, mn = t % npj;
-    double acc = 0.0;
-    if (kl >= 10 || mn >= 10) {
-      for (int s = 0; s < SPD_NSRC; ++s)
-        for (int m5 = 0; m5 < 5; ++m5) {
-          const double ca = ci[(kl * SPD_NSRC + s) * 5 + m5];
-          if (ca == 0.0) continue;
-          const int am = (m5 == 0) ? 0 : (m5 < 3 ? 1 : 2);
-          double in = 0.0;
-          for (int tt = 0; tt < SPD_NSRC; ++tt) {
-            const double cb = cj[(mn * SPD_NSRC + tt) * 5 + m5];
-            if (cb != 0.0) in += V[(s * SPD_NSRC + tt) * 3 + am] * cb;
-          }
-          acc += ca * in;
-        }
-      // reference quirk: (d-sigma p-pi(y) | p-pi(y) s) carries -0.577350 where its neighbours carry -1/sqrt3
-      if (kl == 13 && mn == 6) acc += (-0.577350 + 1.0 / SPD_SQRT3) * V[(4 * SPD_NSRC + 1) * 3 + 1];
-    }
-    L[t] = acc;
+    L[t] = (kl >= 10 || mn >= 10) ? spd_local_integral(kl, mn, cv, cc, V) : 0.0;
   }
   SEQM_SYNC();
   // tmp[k'l'][mn] = sum_{m'n'} L[k'l'][m'n'] T[mn][m'n']
@@ -374,7 +407,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_kernel(seqm_batch_t b,
   const int i = b.pair_i[p], j = b.pair_j[p];
   const int mol = b.atom_mol[i];
   const bool dj = (j - b.mol_atom0[mol]) < b.mol_nsh[mol];
-  spd_pair_block(b, i, j, dj, xyz + 3 * (long long)i, xyz + 3 * (long long)j, w10 + (long long)p * 100, sm, -1.0);
+  spd_pair_block(b, i, j, dj, xyz + 3 * (long long)i, xyz + 3 * (long long)j, w10 + (long long)p * 100, sm);
   const long long o0 = b.pair_wd0[p], cnt = b.pair_wd0[p + 1] - o0;
   for (int t = threadIdx.x; t < cnt; t += blockDim.x) wd[o0 + t] = sm[SPD_OFF_L + t];
   for (int t = threadIdx.x; t < 81; t += blockDim.x) hab_d[(long long)slot * 81 + t] = sm[SPD_OFF_S + t];
@@ -531,79 +564,220 @@ SEQM_GLOBAL void spd_fock_kernel(seqm_batch_t b, const double* __restrict__ P, c
   }
 }
 
-// energy of one Y pair at fixed density from the block in shared memory (all threads; result valid in all threads)
-SPD_NOINLINE double spd_pair_energy(const seqm_batch_t& b, int i, int j, int npi, int npj, int noi, int noj, double r_bohr,
-                              const double* sm, double* red) {
-  const double* W = sm + SPD_OFF_L;
-  const double* S = sm + SPD_OFF_S;
-  const double* Dij = sm + SPD_OFF_X;        // 9 x 9 off-diagonal density block
-  const double* pki = sm + SPD_OFF_X + 81;   // weighted packed diagonal blocks
-  const double* pkj = sm + SPD_OFF_X + 126;
-  double e = 0.0;
-  const double ti = par(b, SEQM_P_TORE, i), tj = par(b, SEQM_P_TORE, j);
-  for (int t = threadIdx.x; t < 81; t += blockDim.x) e += 2.0 * Dij[t] * S[t];
-  for (int t = threadIdx.x; t < npi * npj; t += blockDim.x) {
-    const int kl = t / npj, mn = t % npj;
-    const double wv = W[t];
-    double c = pki[kl] * pkj[mn];
-    if (mn == 0) c -= pki[kl] * tj;
-    if (kl == 0) c -= pkj[mn] * ti;
-    int mu, nu, la, sg;
-    spd_unpack(kl, &mu, &nu);
-    spd_unpack(mn, &la, &sg);
-    // exchange: -1/2 sum over the ordered orbital quadruples that map onto (kl, mn)
-    double x = Dij[mu * 9 + la] * Dij[nu * 9 + sg];
-    if (mu != nu) x += Dij[nu * 9 + la] * Dij[mu * 9 + sg];
-    if (la != sg) {
-      x += Dij[mu * 9 + sg] * Dij[nu * 9 + la];
-      if (mu != nu) x += Dij[nu * 9 + sg] * Dij[mu * 9 + la];
-    }
-    c -= 0.5 * x;
-    e += c * wv;
-  }
-  e = block_sum(e, red);
-  double alp, chi;
-  pair_pw(b, i, j, alp, chi);
-  (void)noi; (void)noj;
-  return e + core_core(b.method, b.atom_Z[i], b.atom_Z[j], load_core(b, i), load_core(b, j), r_bohr, W[0], alp, chi);
-}
+// ---- gradient of the Y pairs -----------------------------------------------------------------------------------------------
+// dE_pair/dR_i of the part of a Y pair's energy that the sp gradient kernel does not cover: the resonance term over
+// the 9 x 9 overlap block and every two-electron / core-attraction term that contains a d orbital.  The reference has
+// no analytic PM6 gradient either (anal_grad.py:50-51: autograd through the same expression); here a five-point
+// stencil (delta = 1e-4 Angstrom, error O(delta^4)) runs through an evaluation that needs no 45 x 45 transform at all:
+// the energy is frame invariant, so the three density blocks are rotated INTO the local frame (9 x 9 x 9 products)
+// and contracted with the local integrals, which are assembled on the fly from the unit multipole interactions.
+// shared layout (doubles): Pi 81 | Pj 81 | Pij 81 | Ai 81 | Aj 81 | Aij 81 | tmp 243 | R 81 | V 147 | S 81 | pk 90 | red 40
+#define SPG_PI 0
+#define SPG_PJ 81
+#define SPG_PIJ 162
+#define SPG_AI 243
+#define SPG_AJ 324
+#define SPG_AIJ 405
+#define SPG_TMP 486
+#define SPG_R 729
+#define SPG_V 810
+#define SPG_S 957
+#define SPG_PK 1038
+#define SPG_RED 1128
+#define SPG_CV 1176    /* sparse multipole coefficients: values [2][45][4] (atom i table, atom j table) */
+#define SPG_CC 1536    /* their codes s * 5 + m5 (-1 = unused), ints stored in [2][45][4] int slots = 180 doubles */
+#define SPG_AB 1716    /* auxiliary integrals A_k, B_k (k <= 8) of the 9 (l_a, l_b) zeta combinations: [9][18] */
+#define SPG_PART 1878  /* partial sums of the overlap polynomials [14][9] */
+#define SPG_PRE 2004   /* geometry-independent overlap prefactors [14] */
+#define SPG_SMEM_DOUBLES 2020
 
-// dE_pair/dR_i of the Y pairs by the five-point stencil (delta = 1e-4 Angstrom, error O(delta^4)) through spd_pair_block:
-// the reference has no analytic PM6 gradient either (anal_grad.py:50-51; it differentiates the same expression by autograd).
-SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz,
-                                                                          const double* __restrict__ P, double* __restrict__ gp) {
-  SEQM_DYN_SMEM(double, sm);
-  __shared__ double red[33];
-  const int slot = blockIdx.x;
-  const int p = b.ypairs[slot];
-  const int i = b.pair_i[p], j = b.pair_j[p];
-  const int mol = b.atom_mol[i];
-  const MolView v = mol_view(b, mol);
-  const int li = i - v.a0, lj = j - v.a0;
-  const bool dj = lj < v.nsh;
-  const int noi = 9, noj = orb_cnt(v, lj), npi = 45, npj = prod_cnt(v, lj);
-  const int oi = orb_off(v, li), oj = orb_off(v, lj), n = v.n;
-  const double* Pm = P + v.mat0;
-  double* X = sm + SPD_OFF_X;
-  for (int t = threadIdx.x; t < 81; t += blockDim.x) {
-    const int mu = t / 9, la = t % 9;
-    X[t] = (mu < noi && la < noj) ? Pm[(oi + mu) * n + oj + la] : 0.0;
+SPD_NOINLINE double spd_pair_energy_local(const seqm_batch_t& b, int i, int j, bool dj, const SpdAtom& A, const SpdAtom& B,
+                                          const double* Ri, const double* Rj, double r_regime, double* sm) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  double e[3] = {Rj[0] - Ri[0], Rj[1] - Ri[1], Rj[2] - Ri[2]};
+  const double dist = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+  for (int c = 0; c < 3; ++c) e[c] /= dist;
+  const double r = dist * (1.0 / SEQM_A0);
+  if (pair_cut(b, r)) return 0.0;
+  double* R = sm + SPG_R;
+  double* V = sm + SPG_V;
+  double* S = sm + SPG_S;
+  double* pk = sm + SPG_PK;
+  double* tmp = sm + SPG_TMP;
+  const int npi = A.nprod, npj = B.nprod;
+  const double w3[3] = {-e[0], -e[1], -e[2]};
+  double u3[3], v3[3];
+  spd_local_axes(w3, u3, v3, nullptr, nullptr, nullptr);
+  for (int t = tid; t < 81; t += nthr) R[t] = spd_rotation_element(t / 9, t % 9, u3, v3, w3);
+  for (int t = tid; t < SPD_NSRC * SPD_NSRC * 3; t += nthr) {
+    const int s = t / (SPD_NSRC * 3), tt = (t / 3) % SPD_NSRC, am = t % 3;
+    const int ls = spd_src_l(s), lt = spd_src_l(tt);
+    double val = 0.0;
+    const bool have = (tt < 3 || dj) && (tt == 0 || B.norb > 1) && (s >= 3 || tt >= 3);  // sp x sp sources: not needed here
+    if (am <= ls && am <= lt && have) {
+      const double add = (A.rho[s] + B.rho[tt]) * (A.rho[s] + B.rho[tt]);
+      val = spd_interaction(ls, lt, am, A.D[s], B.D[tt], add, r);
+    }
+    V[t] = val;
   }
-  for (int t = threadIdx.x; t < 90; t += blockDim.x) {
+  for (int t = tid; t < 81; t += nthr) S[t] = 0.0;
+  // auxiliary integrals of the nine (l_a, l_b) exponent combinations, one thread each
+  double* AB = sm + SPG_AB;
+  for (int c = tid; c < 9; c += nthr) {
+    const int la = c / 3, lb = c % 3;
+    const double za = A.zeta[la], zb = B.zeta[lb];
+    if (za > 0.0 && zb > 0.0) {
+      aux_A((0.5 * (za + zb)) * r, 8, AB + c * 18);
+      spd_aux_B((0.5 * (za - zb)) * r, (0.5 * (za - zb)) * r_regime, 8, AB + c * 18 + 9);
+    } else {
+      for (int k = 0; k < 18; ++k) AB[c * 18 + k] = 0.0;
+    }
+  }
+  SEQM_SYNC();
+  if (r <= SEQM_OVERLAP_CUTOFF) {
+    // 14 kinds x 9 rows of the (xi, eta) polynomial: one (kind, k) row per thread, then 14 threads add their 9 rows
+    double* part = sm + SPG_PART;
+    for (int t = tid; t < 126; t += nthr) {
+      const int kind = t / 9, k = t % 9;
+      int la, lb, m;
+      spd_kind(kind, &la, &lb, &m);
+      const int na = A.n[la], nb = B.n[lb];
+      double acc = 0.0;
+      if (na >= 1 && na <= 4 && nb >= 1 && nb <= 4) {
+        const double* poly = b.ovl_poly + ((long long)((na - 1) * 4 + (nb - 1)) * 14 + kind) * 81 + k * 9;
+        const double* Bk = AB + (la * 3 + lb) * 18 + 9;
+        for (int l = 0; l < 9; ++l) acc += poly[l] * Bk[l];
+        acc *= AB[(la * 3 + lb) * 18 + k];
+      }
+      part[t] = acc;
+    }
+    SEQM_SYNC();
+    for (int kind = tid; kind < 14; kind += nthr) {
+      int la, lb, m;
+      spd_kind(kind, &la, &lb, &m);
+      const int oa = (la == 0) ? 0 : (la == 1 ? 1 : 4), ob = (lb == 0) ? 0 : (lb == 1 ? 1 : 4);
+      if (oa >= A.norb || ob >= B.norb) continue;
+      double tot = 0.0;
+      for (int k = 0; k < 9; ++k) tot += part[kind * 9 + k];
+      const double sv = sm[SPG_PRE + kind] * ipow(0.5 * r, A.n[la] + B.n[lb] + 1) * tot;
+      const double sg = (((la + m) & 1) ? -1.0 : 1.0) * (((lb + m) & 1) ? -1.0 : 1.0);  // atom j sits at -z
+      const int ia = (m == 0) ? oa : (la == 1 ? 2 : (m == 1 ? 5 : 7));
+      const int ib = (m == 0) ? ob : (lb == 1 ? 2 : (m == 1 ? 5 : 7));
+      const double bb = 0.5 * (A.beta[la] + B.beta[lb]);
+      S[ia * 9 + ib] = sg * sv * bb;
+      if (m > 0) S[(ia + 1) * 9 + ib + 1] = sg * sv * bb;
+    }
+  }
+  // densities into the local frame: X_loc = R^t X R for the three blocks (tmp = X R, then R^t tmp)
+  for (int t = tid; t < 243; t += nthr) {
+    const int blk = t / 81, a = (t % 81) / 9, q = t % 9;
+    const double* X = sm + SPG_PI + 81 * blk;
+    double acc = 0.0;
+    for (int k = 0; k < 9; ++k) acc += X[a * 9 + k] * R[k * 9 + q];
+    tmp[t] = acc;
+  }
+  SEQM_SYNC();
+  for (int t = tid; t < 243; t += nthr) {
+    const int blk = t / 81, a = (t % 81) / 9, q = t % 9;
+    double acc = 0.0;
+    for (int k = 0; k < 9; ++k) acc += R[k * 9 + a] * tmp[blk * 81 + k * 9 + q];
+    sm[SPG_AI + t] = acc;
+  }
+  SEQM_SYNC();
+  const double* Ai = sm + SPG_AI;
+  const double* Aj = sm + SPG_AJ;
+  const double* Aij = sm + SPG_AIJ;
+  for (int t = tid; t < 90; t += nthr) {
     const int side = t / 45, kl = t % 45;
     int mu, nu;
     spd_unpack(kl, &mu, &nu);
-    const int o = side ? oj : oi, no = side ? noj : noi;
-    X[81 + t] = (mu < no) ? Pm[(o + mu) * n + o + nu] * (mu == nu ? 1.0 : 2.0) : 0.0;
+    pk[t] = (side ? Aj : Ai)[mu * 9 + nu] * (mu == nu ? 1.0 : 2.0);
+  }
+  SEQM_SYNC();
+  double en = 0.0;
+  // resonance term: 2 sum D_ij o (beta S)
+  for (int t = tid; t < 81; t += nthr) en += 2.0 * Aij[t] * S[t];
+  // two-electron and core-attraction terms with a d orbital; the multipole coefficients come from the sparse lists
+  // (<= 4 non-zero (source, m) entries per product) that the kernel staged in shared memory
+  const double* cv = sm + SPG_CV;
+  const int* cc = reinterpret_cast<const int*>(sm + SPG_CC);
+  const double ti = par(b, SEQM_P_TORE, i), tj = par(b, SEQM_P_TORE, j);
+  for (int t = tid; t < npi * npj; t += nthr) {
+    const int kl = t / npj, mn = t % npj;
+    if (kl < 10 && mn < 10) continue;
+    const double L = spd_local_integral(kl, mn, cv, cc, V);
+    double c = pk[kl] * pk[45 + mn];
+    if (mn == 0) c -= pk[kl] * tj;
+    if (kl == 0) c -= pk[45 + mn] * ti;
+    int mu, nu, la, sg;
+    spd_unpack(kl, &mu, &nu);
+    spd_unpack(mn, &la, &sg);
+    double x = Aij[mu * 9 + la] * Aij[nu * 9 + sg];
+    if (mu != nu) x += Aij[nu * 9 + la] * Aij[mu * 9 + sg];
+    if (la != sg) {
+      x += Aij[mu * 9 + sg] * Aij[nu * 9 + la];
+      if (mu != nu) x += Aij[nu * 9 + sg] * Aij[mu * 9 + la];
+    }
+    en += (c - 0.5 * x) * L;
+  }
+  if (dj && tid == 0 && r <= SEQM_OVERLAP_CUTOFF) {  // reference quirk of the (d_yz, d_xy) overlap element (molecular frame)
+    double ca, sb, cb, uu[3], vv[3];
+    spd_local_axes(e, uu, vv, &ca, &sb, &cb);
+    const double bdd = 0.5 * (A.beta[2] + B.beta[2]);
+    const double s333 = (bdd != 0.0) ? S[7 * 9 + 7] / bdd : 0.0;
+    const double fix = 2.0 * s333 * ca * sb * cb * (2.0 * ca * ca - 1.0);
+    en += 2.0 * bdd * fix * (sm[SPG_PIJ + 7 * 9 + 8] + sm[SPG_PIJ + 8 * 9 + 7]);
+  }
+  return block_sum(en, sm + SPG_RED);
+}
+
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_gradient_kernel(seqm_batch_t b, const double* __restrict__ xyz,
+                                                                          const double* __restrict__ P, double* __restrict__ gp) {
+  SEQM_DYN_SMEM(double, sm);
+  const int slot = blockIdx.x;
+  const int p = b.ypairs[slot];
+  const int i = b.pair_i[p], j = b.pair_j[p];
+  const MolView v = mol_view(b, b.atom_mol[i]);
+  const int li = i - v.a0, lj = j - v.a0;
+  const bool dj = lj < v.nsh;
+  const int noj = orb_cnt(v, lj);
+  const int oi = orb_off(v, li), oj = orb_off(v, lj), n = v.n;
+  const double* Pm = P + v.mat0;
+  for (int t = threadIdx.x; t < 243; t += blockDim.x) {  // molecular-frame density blocks, zero beyond the atoms' orbitals
+    const int blk = t / 81, a = (t % 81) / 9, q = t % 9;
+    const int ro = (blk == 1) ? oj : oi, co = (blk == 0) ? oi : oj;
+    const int nr = (blk == 1) ? noj : 9, nc = (blk == 0) ? 9 : noj;
+    sm[SPG_PI + t] = (a < nr && q < nc) ? Pm[(ro + a) * n + co + q] : 0.0;
+  }
+  __shared__ SpdAtom sAB[2];
+  if (threadIdx.x == 0) spd_load_atom(b, i, true, sAB[0]);
+  if (threadIdx.x == 1 || blockDim.x == 1) spd_load_atom(b, j, dj, sAB[1]);
+  SEQM_SYNC();
+  const SpdAtom& A = sAB[0];
+  const SpdAtom& B = sAB[1];
+  {  // geometry-independent staging: sparse multipole coefficients of both atoms, overlap prefactors
+    spd_stage_coefficients(b, !dj && noj == 4, sm + SPG_CV, reinterpret_cast<int*>(sm + SPG_CC));
+    for (int kind = threadIdx.x; kind < 14; kind += blockDim.x) {
+      int la, lb, m;
+      spd_kind(kind, &la, &lb, &m);
+      const int na = A.n[la], nb = B.n[lb];
+      double pre = 0.0;
+      if (na >= 1 && na <= 4 && nb >= 1 && nb <= 4 && A.zeta[la] > 0.0 && B.zeta[lb] > 0.0) {
+        double fa = 1.0, fb = 1.0;
+        for (int k = 2; k <= 2 * na; ++k) fa *= k;
+        for (int k = 2; k <= 2 * nb; ++k) fb *= k;
+        pre = pow(2.0 * A.zeta[la], na + 0.5) * pow(2.0 * B.zeta[lb], nb + 0.5) / sqrt(fa * fb);
+      }
+      sm[SPG_PRE + kind] = pre;
+    }
   }
   SEQM_SYNC();
   const double delta = 1.0e-4;
-  double Rj[3] = {xyz[3 * (long long)j], xyz[3 * (long long)j + 1], xyz[3 * (long long)j + 2]};
-  double r0;  // undisplaced distance (bohr): selects the B-integral regime of every stencil point
-  {
-    const double dx = Rj[0] - xyz[3 * (long long)i], dy = Rj[1] - xyz[3 * (long long)i + 1], dz = Rj[2] - xyz[3 * (long long)i + 2];
-    r0 = sqrt(dx * dx + dy * dy + dz * dz) * (1.0 / SEQM_A0);
-  }
+  const double Rj[3] = {xyz[3 * (long long)j], xyz[3 * (long long)j + 1], xyz[3 * (long long)j + 2]};
+  const double Ri0[3] = {xyz[3 * (long long)i], xyz[3 * (long long)i + 1], xyz[3 * (long long)i + 2]};
+  // undisplaced distance (bohr): selects the B-integral regime of every stencil point
+  const double r0 = sqrt((Rj[0] - Ri0[0]) * (Rj[0] - Ri0[0]) + (Rj[1] - Ri0[1]) * (Rj[1] - Ri0[1]) +
+                         (Rj[2] - Ri0[2]) * (Rj[2] - Ri0[2])) * (1.0 / SEQM_A0);
   double g[3];
 #pragma unroll 1
   for (int c = 0; c < 3; ++c) {
@@ -611,34 +785,16 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(SPD_THREADS) spd_pair_gradient_kernel(seqm_b
 #pragma unroll 1
     for (int k = 0; k < 4; ++k) {
       const double s = (k == 0) ? 1.0 : (k == 1 ? -1.0 : (k == 2 ? 2.0 : -2.0));
-      double Ri[3] = {xyz[3 * (long long)i], xyz[3 * (long long)i + 1], xyz[3 * (long long)i + 2]};
+      double Ri[3] = {Ri0[0], Ri0[1], Ri0[2]};
       Ri[c] += s * delta;
-      double* wsp = sm + SPD_OFF_SP;
-      if (threadIdx.x == 0) {  // sp x sp block of the sp path at this geometry
-        PairGeom<double> pg;
-        const double dx = Rj[0] - Ri[0], dy = Rj[1] - Ri[1], dz = Rj[2] - Ri[2];
-        const double d = sqrt(dx * dx + dy * dy + dz * dz);
-        pg.e[0] = dx / d; pg.e[1] = dy / d; pg.e[2] = dz / d;
-        pg.r = d * (1.0 / SEQM_A0);
-        double wl[10][10];
-        for (int a = 0; a < 10; ++a)
-          for (int q = 0; q < 10; ++q) wl[a][q] = 0.0;
-        pair_w(b, i, j, pg, wl, noj > 1 ? 22 : 4);
-        for (int a = 0; a < 10; ++a)
-          for (int q = 0; q < 10; ++q) wsp[a * 10 + q] = (noj > 1 || q == 0) ? wl[a][q] : 0.0;
-      }
-      SEQM_SYNC();
-      spd_pair_block(b, i, j, dj, Ri, Rj, wsp, sm, r0);
-      const double dx = Rj[0] - Ri[0], dy = Rj[1] - Ri[1], dz = Rj[2] - Ri[2];
-      const double rb = sqrt(dx * dx + dy * dy + dz * dz) * (1.0 / SEQM_A0);
-      E[k] = pair_cut(b, rb) ? 0.0 : spd_pair_energy(b, i, j, npi, npj, noi, noj, rb, sm, red);
+      E[k] = spd_pair_energy_local(b, i, j, dj, A, B, Ri, Rj, r0, sm);
       SEQM_SYNC();
     }
     g[c] = (8.0 * (E[0] - E[1]) - (E[2] - E[3])) / (12.0 * delta);
   }
-  if (threadIdx.x == 0) {
-    gp[3 * (long long)p] = g[0];
-    gp[3 * (long long)p + 1] = g[1];
-    gp[3 * (long long)p + 2] = g[2];
+  if (threadIdx.x == 0) {  // the sp gradient kernel has already written the sp x sp part of this pair
+    gp[3 * (long long)p] += g[0];
+    gp[3 * (long long)p + 1] += g[1];
+    gp[3 * (long long)p + 2] += g[2];
   }
 }

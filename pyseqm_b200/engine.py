@@ -238,6 +238,8 @@ class BatchPlan:
         self.struct = s
         self.ref = C.byref(s)
         self.large = self.nmax > lib.dll.seqm_max_orbitals()  # global-memory Fock + GEMM SP2/DIIS path
+        # the eigensolver route of the large path: one-sided Jacobi up to seqm_max_orbitals_eig() (256) orbitals
+        self.eig_ok = self.nmax <= lib.dll.seqm_max_orbitals_eig()
         if self.d_mode and self.large:
             raise NotImplementedError(f"method 'PM6' with d orbitals: a molecule with {self.nmax} orbitals exceeds the "
                                       f"shared-memory resident path ({lib.dll.seqm_max_orbitals()} orbitals)")
@@ -380,6 +382,9 @@ def op_eig_density(plan, F, want_P=True, want_C=False, Cguess=None, active=None,
     if Cguess is not None and (Cguess.numel() != plan.mat_total or Cguess.device != plan.device):
         raise SeqmError(f"op_eig_density: warm-start eigenvectors hold {Cguess.numel()} elements on {Cguess.device}, the "
                         f"plan has {plan.mat_total} on {plan.device} (a guess from another batch plan?)")
+    if plan.large:  # mid-size eigensolver (one-sided Jacobi): works in the eigenvector buffer, needs both; always cold
+        want_P = want_C = True
+        Cguess = None
     P = plan.new_mat() if (want_P or Cguess is not None) else None
     Cm = plan.new_mat() if (want_C or Cguess is not None) else None  # the warm start needs both scratch slots
     e = torch.zeros((plan.nmol, plan.nmax), dtype=torch.float64, device=plan.device) if want_e else None
@@ -505,7 +510,12 @@ def op_scf(plan, H, w, P, eps, converger, sp2=(False,), max_iter=1000, warm_star
     nbytes = plan.lib.dll.seqm_scf_workspace_bytes(plan.ref, C.byref(o))
     if nbytes < 0:
         raise SeqmError("seqm_scf_workspace_bytes failed")
-    ws = torch.zeros(nbytes, dtype=torch.uint8, device=plan.device)
+    # the workspace (DIIS history ~0.8 GB at configs[1]) belongs to the plan: allocated and zeroed once, reused by every
+    # later forward -- scf_init_kernel resets all the state the loop reads before writing
+    ws = plan.__dict__.get("_scf_ws")
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=plan.device)
+        plan.__dict__["_scf_ws"] = ws
     F = plan.new_mat()
     E = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
     nc = torch.ones(plan.nmol, dtype=torch.int32, device=plan.device)

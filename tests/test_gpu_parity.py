@@ -275,6 +275,28 @@ def test_pipelined_scf_is_bitwise_identical_to_single_stream(lib, dev, monkeypat
         assert torch.equal(a, b)
 
 
+def test_repeated_forward_reuses_the_workspace_bitwise(lib, dev):
+    """The SCF workspace is allocated once per plan and reused without re-zeroing: a second cold forward on the same
+    Molecule (its workspace now holds the first run's DIIS history) must reproduce the first one bit for bit, for the
+    pipelined DIIS loop and for adaptive mixing."""
+    import pyseqm_b200 as seqm
+    from pyseqm_b200.synthetic import qm9_like_batch
+
+    species, coords = qm9_like_batch(300, seed=29)
+    for conv in ([2], [1]):
+        sp = {"method": "PM3", "scf_eps": 1e-7, "scf_converger": conv, "sp2": [False]}
+        const = seqm.Constants().to(dev)
+        mol = seqm.Molecule(const, dict(sp), torch.as_tensor(coords, device=dev), torch.as_tensor(species, device=dev), _lib=lib)
+        mol.verbose = False
+        es = seqm.Electronic_Structure(dict(sp))
+        es(mol)
+        first = (mol.n_scf_iter, mol.Etot.clone(), mol.dm.clone(), mol.force.clone())
+        assert mol._plan.__dict__.get("_scf_ws") is not None
+        es(mol)
+        assert mol.n_scf_iter == first[0]
+        assert torch.equal(mol.Etot, first[1]) and torch.equal(mol.dm, first[2]) and torch.equal(mol.force, first[3])
+
+
 def test_device_batch_plan_against_numpy(lib, dev):
     from helpers import check_device_batch_plan
 

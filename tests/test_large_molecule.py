@@ -36,9 +36,65 @@ def check_dimer(lib, device):
     assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < 2e-6
     assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < 2e-3  # SP2-limited (weakly coupled stacked dimer)
     assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < 1e-2
-    # the eigensolver route is refused for this size instead of silently doing something else
+
+
+def stacked(dz, shift, second="coronene.xyz"):
+    """coronene with a second molecule stacked dz above it and shifted sideways (no exact degeneracies)."""
+    import os
+
+    import pyseqm_b200 as seqm
+    from conftest import GOLDEN
+
+    s, c = seqm.read_xyz([os.path.join(GOLDEN, "xyz", "coronene.xyz")])
+    t, d = seqm.read_xyz([os.path.join(GOLDEN, "xyz", second)])
+    Z = np.concatenate([s[0], t[0]])
+    X = np.concatenate([c[0], d[0] + np.array([shift, 0.3 * shift, dz])])
+    keep = Z > 0
+    Z, X = Z[keep], X[keep]
+    o = np.argsort(-Z, kind="stable")
+    return Z[o][None], X[o][None]
+
+
+def check_mid_eigensolver(lib, device):
+    """Eigensolver route between 119 and 256 orbitals (north_star: one-sided Jacobi up to about 256 orbitals;
+    sym_eig_trunc, diag.py:110-241) against the oracle at north-star tolerances with equal iteration counts:
+    coronene + benzene (138 orbitals, matrix in shared memory) and a shifted coronene dimer (216 orbitals, matrix in L2)."""
+    import seqm_oracle as so
+    from helpers import run_molecule
+
+    sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2]}
+    for S, C, norb in ((*stacked(3.4, 0.7, "benzene.xyz"), 138), (*stacked(3.5, 1.2), 216)):
+        ref = so.single_point(S, C, sp)
+        mol, es = run_molecule(lib, device, S, C, sp)
+        assert int(mol._plan.nmax) == norb and mol._plan.large
+        assert not bool(es.notconverged.any())
+        assert mol.n_scf_iter == ref["n_scf_iter"]
+        assert np.abs(mol.Etot.cpu().numpy() - ref["Etot"]).max() < 1e-6
+        assert np.abs(mol.dm.cpu().numpy() - ref["dm"]).max() < 1e-8
+        assert np.abs(mol.force.cpu().numpy() - ref["force"]).max() < 1e-5
+        assert np.abs(mol.e_gap.cpu().numpy() - ref["e_gap"]).max() < 1e-6
+        n = norb
+        assert np.abs(mol.e_mo.cpu().numpy()[:, :n] - ref["e_mo"][:, :n]).max() < 1e-6
+    # beyond 256 orbitals the eigensolver route is refused instead of silently doing something else
+    s3, c3 = stacked(3.5, 1.2)
+    s3 = np.concatenate([s3[0][s3[0] > 1], s3[0][s3[0] > 1], s3[0][s3[0] == 1]])[None]
+    c3 = np.concatenate([c3[0][: (s3[0] > 1).sum() // 2], c3[0][: (s3[0] > 1).sum() // 2] + np.array([0.0, 0.0, 7.0]),
+                         c3[0][(s3[0] > 1).sum() // 2:]])[None]
     with pytest.raises(NotImplementedError, match="SP2"):
-        run_molecule(lib, device, s2, c2, {"method": "AM1", "scf_eps": 1e-6, "scf_converger": [2]})
+        run_molecule(lib, device, s3, c3, sp)
+
+
+def test_hostemu_mid_size_eigensolver():
+    from helpers import hostemu_lib
+
+    check_mid_eigensolver(hostemu_lib(), torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_gpu_mid_size_eigensolver():
+    from helpers import cuda_lib
+
+    check_mid_eigensolver(cuda_lib(), torch.device("cuda:0"))
 
 
 def test_hostemu_large_path_dimer():
