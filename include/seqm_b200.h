@@ -225,6 +225,13 @@ int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double
 /* packed eigenvector matrices -> dense (nmol, nmax, nmax), identity on the padding: the `v` of diag.py:110-241 */
 int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void* stream);
 
+/* Post-SCF by-products in one launch on the packed density: Mulliken charges q = tore - population
+ * (ElectronicStructure.py:104-127; (nmol, molsize), 0 on padding), ground-state dipole (calc_ground_dipole, dipole.py:85-107;
+ * (nmol, 3) or NULL; scale = to_debye * debye_to_AU, a0 = bohr in Angstrom) and force = -grad scattered into the padded
+ * (nmol, molsize, 3) layout (force NULL: skipped; grad [nat*3] from seqm_gradient). */
+int seqm_post_scf(const seqm_batch_t* b, const double* P, const double* xyz, const double* grad, double* q, double* dipole,
+                  double* force, double a0, double scale, void* stream);
+
 /* MO crossing matcher -- Energy._crossing_match_molecular_orbitals / _grouped, seqm/basics.py:596-719 (called on every
  * forward after the first one on the same Molecule, basics.py:846-857): the new orbitals are permuted inside the
  * occupied and inside the virtual block so that orbital k continues old orbital k (largest |overlap|, greedy repair
@@ -273,6 +280,11 @@ long long seqm_launch_count(void);
 int seqm_jacobi_stats(unsigned long long* out, int reset);
 /* measured FP64 FMA peak (TFLOP/s) of the current device: roofline denominator of the FP64-bound kernels */
 double seqm_fp64_peak_tflops(void);
+/* C = A B for row-major n x n device matrices through the library's FP64 tensor-core GEMM (the product inside the
+ * large-molecule SP2 loop, SP2.py:55, and the DIIS commutator); B == NULL: C = A A for a SYMMETRIC A through the
+ * upper-triangle kernel (only tiles on and above the diagonal are computed, the rest is mirrored).  For tests and the
+ * bench's DGEMM line. */
+int seqm_square_product(int n, const double* A, const double* B, double* C, void* stream);
 int seqm_profile_enable(int on);
 int seqm_profile_kinds(void);
 const char* seqm_profile_name(int kind);

@@ -77,9 +77,13 @@ class Electronic_Structure(torch.nn.Module):
                 molecule, P0, learned_parameters=learned_parameters, xl_bomd_params=xl_bomd_params)  # fmt: skip
         else:
             raise NotImplementedError(f"dm_prop={dm_prop!r} is not implemented by the B200 path")
-        with torch.no_grad():
-            molecule.q = molecule.const.tore[molecule.species] - self.atomic_charges(
-                molecule.dm, n_orbital=getattr(molecule, "orbital_stride", 4))
+        q = molecule.__dict__.pop("_q_post", None)  # written by the post-SCF kernel of the forward that just ran
+        if q is not None:
+            molecule.q = q
+        else:
+            with torch.no_grad():
+                molecule.q = molecule.const.tore[molecule.species] - self.atomic_charges(
+                    molecule.dm, n_orbital=getattr(molecule, "orbital_stride", 4))
 
     def get_force(self):
         return self.force

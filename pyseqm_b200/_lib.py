@@ -64,11 +64,13 @@ class SeqmError(RuntimeError):
     pass
 
 
-SOURCES = ("seqm_b200.cu", "seqm_spd.cu", "seqm_eigh.cu")  # translation units, compiled in parallel
+SOURCES = ("seqm_b200.cu", "seqm_pair.cu", "seqm_spd.cu", "seqm_eigh.cu", "seqm_post.cu")  # translation units, compiled in parallel
 # files that only one translation unit includes (everything else is shared): an edit there recompiles that unit alone
 _ONLY = {"seqm_spd.cu": {"seqm_spd.cu", "spd_kernels.cuh"},
          "seqm_eigh.cu": {"seqm_eigh.cu", "hestenes_kernels.cuh"},
-         "seqm_b200.cu": {"seqm_b200.cu", "pair_kernels.cuh", "scf_driver.cuh", "plan_kernels.cuh", "eig_kernels.cuh",
+         "seqm_post.cu": {"seqm_post.cu"},
+         "seqm_pair.cu": {"seqm_pair.cu", "pair_kernels.cuh"},  # ~25 min of nvcc: keep edits out of it
+         "seqm_b200.cu": {"seqm_b200.cu", "atom_kernels.cuh", "scf_driver.cuh", "plan_kernels.cuh", "eig_kernels.cuh",
                           "fock_kernels.cuh", "large_kernels.cuh"}}  # fmt: skip
 
 
@@ -78,8 +80,12 @@ def build_library(verbose=False):
     newest = max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC))
     hdr = os.path.join(_HERE, "..", "include", "seqm_b200.h")
     newest = max(newest, os.path.getmtime(hdr))
-    if os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
-        return LIB_PATH
+    stamp = LIB_PATH + ".sources"  # the translation units the existing library was linked from
+    linked = open(stamp).read().split() if os.path.exists(stamp) else []
+    objs_all = [os.path.join(os.path.dirname(LIB_PATH), src.replace(".cu", ".o")) for src in SOURCES]
+    have_objs = all(os.path.exists(o) for o in objs_all)
+    if os.path.exists(LIB_PATH) and linked == list(SOURCES) and not have_objs and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH  # a shipped library without its objects (nothing to compare against but the sources)
     flags = [f for f in NVCC_FLAGS if f != "--shared"]
     procs, objs = [], []
     for src in SOURCES:
@@ -96,10 +102,15 @@ def build_library(verbose=False):
     for cmd, p in procs:
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, cmd)
+    if (not procs and os.path.exists(LIB_PATH) and linked == list(SOURCES)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(o) for o in objs)):
+        return LIB_PATH  # every object is newer than its sources and the library is newer than every object
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB_PATH] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
+    with open(stamp, "w") as f:
+        f.write(" ".join(SOURCES) + "\n")
     return LIB_PATH
 
 
@@ -145,9 +156,11 @@ class SeqmLib:
             "seqm_elec_energy_xl": ([B, P, P, P, P, P, P], C.c_int),
             "seqm_xl_propagate": ([C.c_int64, C.c_double, C.c_double, P, P, P, P, C.c_int32, C.c_int32, P, P], C.c_int),
             "seqm_orbitals_dense": ([B, P, P, P], C.c_int),
+            "seqm_post_scf": ([B, P, P, P, P, P, P, C.c_double, C.c_double, P], C.c_int),
             "seqm_mo_match": ([B, P, P, P, P, P, P, P, P, P, P], C.c_int),
             "seqm_launch_count": ([], C.c_longlong),
             "seqm_fp64_peak_tflops": ([], C.c_double),
+            "seqm_square_product": ([C.c_int, P, P, P, P], C.c_int),
             "seqm_jacobi_stats": ([C.POINTER(C.c_ulonglong), C.c_int], C.c_int),
             "seqm_profile_enable": ([C.c_int], C.c_int),
             "seqm_profile_kinds": ([], C.c_int),

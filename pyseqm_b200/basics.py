@@ -129,17 +129,19 @@ class Energy(torch.nn.Module):
         else:
             e_mo, e_gap = None, None
         EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)
+        # Mulliken charges, ground-state dipole (basics.py:966-969: none for PM6 with d orbitals) and the padded force
+        # tensor in one launch on the packed density
+        g = engine.op_gradient(plan, xyz, P) if do_force else None
+        q, dip, force = engine.op_post_scf(plan, P, xyz, g, want_dipole=not plan.d_mode)
+        molecule.__dict__["_q_post"] = q
+        if dip is not None:
+            molecule.dipole = dip
         grad = None
         if do_force:
-            g = engine.op_gradient(plan, xyz, P)
-            grad = torch.zeros((plan.nmol * plan.molsize, 3), dtype=torch.float64, device=plan.device)
-            grad[plan.real_atoms] = g
-            grad = grad.reshape(plan.nmol, plan.molsize, 3)
+            grad = -force
             molecule.analytical_gradient = grad
             t0 = _timing(molecule, "Force", t0)
         Pd = engine.op_unpack(plan, P, out=P0 if (P0 is not None and P0.is_contiguous() and not wide) else None)
-        if not plan.d_mode:  # basics.py:966-969: no ground-state dipole for PM6 with d orbitals
-            _ground_dipole(molecule, Pd)
         if wide:
             Pd = widen_orbitals(Pd, plan.molsize, molecule.orbital_stride)
         if P0 is not None and Pd is not P0:
@@ -150,34 +152,10 @@ class Energy(torch.nn.Module):
         Hf = Etot - Eiso
         if self.Hf_flag:
             Hf = Hf + eheat
-        self._grad = grad
+        self._grad, self._force = grad, force
         if all_terms:
             return Hf, Etot, Eelec, Enuc, Eiso, EnucAB, e_gap, e_mo, Pd, None, notconv
         return Eelec, EnucAB, Pd, notconv
-
-
-def _ground_dipole(molecule, Pd):
-    """calc_ground_dipole (seqm/seqm_functions/dipole.py:85-107) on the dense density."""
-    from .seqm_functions.constants import a0, debye_to_AU, to_debye
-
-    const = molecule.const
-    b, n = molecule.coordinates.shape[:2]
-    sp = molecule.species
-    coord = molecule.coordinates.detach()
-    blocks = Pd.view(b, n, 4, n, 4).diagonal(0, 1, 3).permute(0, 3, 1, 2)  # (b, n, 4, 4)
-    trace = blocks.diagonal(0, 2, 3).sum(-1)
-    heavy = (sp > 1).to(Pd.dtype)
-    hyd = (sp == 1).to(Pd.dtype)
-    # -R * (population of the atom) ; hydrogens only count their s orbital
-    pop = trace * heavy + blocks[:, :, 0, 0] * hyd
-    elec = -(pop.unsqueeze(-1) * coord).sum(dim=1)
-    # sp hybridisation term: -2 * dd * a0 * P[s, p_k]
-    dd = torch.zeros((b * n,), dtype=Pd.dtype, device=Pd.device)
-    dd[molecule._plan.real_atoms] = molecule._plan.parameter("dd") * a0
-    dd = dd.view(b, n) * heavy
-    elec = elec - 2.0 * (dd.unsqueeze(-1) * blocks[:, :, 0, 1:4]).sum(dim=1)
-    nuc = (const.tore[sp].unsqueeze(-1) * coord).sum(dim=1)
-    molecule.dipole = (elec + nuc) * to_debye * debye_to_AU
 
 
 class ForceXL(torch.nn.Module):
@@ -225,15 +203,13 @@ class ForceXL(torch.nn.Module):
         Eelec = engine.op_elec_energy_xl(plan, D, Pp, F, H)
         EnucAB, Enuc = engine.op_nuclear_energy(plan, xyz, w)
         g = engine.op_gradient_xl(plan, xyz, D, Pp)
-        force = torch.zeros((plan.nmol * plan.molsize, 3), dtype=torch.float64, device=plan.device)
-        force[plan.real_atoms] = -g
-        force = force.reshape(plan.nmol, plan.molsize, 3)
+        q, dip, force = engine.op_post_scf(plan, D, xyz, g)
         t0 = _timing(molecule, "Force", t0)
         Etot = Eelec + Enuc
         Eiso, eheat = _atom_sums(plan, const)
         Hf = Etot - Eiso + (eheat if self.Hf_flag else 0.0)
         molecule.w = w
-        return dict(force=force, D=D, Hf=Hf, Etot=Etot, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo_n=e_mo_n)
+        return dict(force=force, D=D, Hf=Hf, Etot=Etot, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo_n=e_mo_n, q=q, dipole=dip)
 
     def forward(self, molecule, P, cis_amp=None, learned_parameters=dict(), xl_bomd_params=dict(), *args, **kwargs):
         if xl_bomd_params and "max_rank" in xl_bomd_params:
@@ -243,7 +219,8 @@ class ForceXL(torch.nn.Module):
         plan = molecule._plan
         r = self.forward_packed(molecule, engine.op_pack(plan, P), learned_parameters=learned_parameters)
         Dd = engine.op_unpack(plan, r["D"])
-        _ground_dipole(molecule, Dd)
+        molecule.dipole = r["dipole"]
+        molecule.__dict__["_q_post"] = r["q"]
         N = 4 * plan.molsize
         if r["e_mo_n"] is not None:
             e = torch.zeros((plan.nmol, N), dtype=torch.float64, device=plan.device)
@@ -287,5 +264,5 @@ class Force(torch.nn.Module):
         Hf, Etot, Eelec, Enuc, Eiso, _, e_gap, e, D, charge, notconverged = self.energy(
             molecule, learned_parameters=learned_parameters, all_terms=True, P0=P0, do_force=do_force
         )
-        force = -self.energy._grad if do_force else torch.tensor([])
+        force = self.energy._force if do_force else torch.tensor([])
         return force, D, Hf, Etot, Eelec, Enuc, Eiso, e, e_gap, charge, notconverged

@@ -7,8 +7,9 @@
 
 #define SEQM_MAX_ORB 118  // two n x n fp64 matrices must fit the 227 KB shared memory of one SM
 
-// The library is built from two translation units (seqm_b200.cu and seqm_spd.cu, compiled in parallel): the second one
-// defines SEQM_SECONDARY_TU and only sees declarations of the process-wide state.
+// The library is built from several translation units compiled in parallel (seqm_b200.cu is the primary one; seqm_pair.cu,
+// seqm_spd.cu, seqm_eigh.cu, seqm_post.cu define SEQM_SECONDARY_TU and only see declarations of the process-wide state).
+// seqm_pair.cu additionally defines SEQM_PAIR_TU: it owns the Slater-overlap polynomial tables.
 #ifndef SEQM_SECONDARY_TU
 static char g_seqm_err[512] = "";
 long long g_seqm_launches = 0;
@@ -75,7 +76,7 @@ SEQM_HD int prod_cnt(const MolView& v, int a) { return a < v.nsh ? 45 : (a < v.n
 SEQM_HD int pair_local(const MolView& v, int a, int b) { return a * (2 * v.na - a - 1) / 2 + (b - a - 1); }
 SEQM_HD double par(const seqm_batch_t& b, int row, int atom) { return b.atom_par[(long long)row * b.nat + atom]; }
 
-#ifndef SEQM_SECONDARY_TU
+#ifdef SEQM_PAIR_TU
 // ---- overlap polynomial tables (host-built, device constant) --------------------------------------
 SEQM_CONSTANT OverlapTables c_ovl;
 
@@ -121,7 +122,7 @@ static void build_overlap_tables(OverlapTables* T) {
     }
 }
 static int g_tables_ready = 0;
-static int ensure_tables() {
+int pairtu_ensure_tables() {
   if (g_tables_ready) return SEQM_OK;
   OverlapTables h;
   build_overlap_tables(&h);
@@ -137,8 +138,9 @@ static int ensure_tables() {
   g_tables_ready = 1;
   return SEQM_OK;
 }
-
-#endif  // SEQM_SECONDARY_TU
+#else
+int pairtu_ensure_tables();
+#endif  // SEQM_PAIR_TU
 
 // ---- bulk asynchronous copies (TMA engine, 1-D) and their mbarriers ------------------------------------------------------
 // cp.async.bulk.shared::cluster.global (SASS UBLKCP) moves a contiguous, 16-byte aligned block whose size is a multiple

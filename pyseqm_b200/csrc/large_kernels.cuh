@@ -191,6 +191,120 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) dgemm_dmma_kernel(int M, int N, int K, 
 }
 #endif
 
+// C = X X for a SYMMETRIC X (n x n, leading dimension n), the product SP2 spends its time in (SP2.py:55): only the tiles
+// on and above the diagonal are computed and every off-diagonal tile is also stored transposed, i.e. 0.53 of the FLOPs
+// of the general product for n = 1520.  96x96x16 CTA tiles (16 x 17 / 2 = 136 tiles for n = 1520: one wave of the 148
+// SMs), 8 warps as 2 (m) x 4 (n), each 48x24 = 6x3 DMMA tiles; fragment layout and shared-memory padding as in
+// dgemm_dmma_kernel (row strides 20 and 100 doubles), global loads with unit lane stride in both tiles.
+// skip: optional device flag; a non-zero value turns the launch into a no-op (SP2 already converged, see sp2_large_one).
+#define SEQM_SYM_TB 96
+#define SEQM_SYM_SMEM (2 * (SEQM_SYM_TB * (SEQM_DMMA_BK + 4) + SEQM_DMMA_BK * (SEQM_SYM_TB + 4)) * sizeof(double))
+SEQM_HD void sym_tile_of(int q, int nb, int* bi, int* bj) {  // q-th tile of the upper triangle, row by row
+  int i = 0;
+  while (q >= nb - i) {
+    q -= nb - i;
+    ++i;
+  }
+  *bi = i;
+  *bj = i + q;
+}
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) dgemm_sym_kernel(int n, const double* __restrict__ X, double* __restrict__ C,
+                                                           const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  constexpr int TB = SEQM_SYM_TB, BK = SEQM_DMMA_BK;
+  const int nb = (n + TB - 1) / TB;
+  int bi, bj;
+  sym_tile_of(blockIdx.x, nb, &bi, &bj);
+  const int bm = bi * TB, bn = bj * TB;
+#ifndef SEQM_HOSTEMU
+  constexpr int LDA = BK + 4, LDB = TB + 4, NQ = TB * BK / 256;  // 6 doubles per thread, matrix and stage
+  SEQM_DYN_SMEM(double, dsm);
+  double* const sA0 = dsm;                 // [2][m][k]
+  double* const sB0 = dsm + 2 * TB * LDA;  // [2][k][n]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 2) * 48, wn = (warp & 3) * 24;
+  double acc[6][3][2];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double ra[NQ], rb[NQ];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int e = tid + 256 * q;
+      const int r = bm + (e >> 4), c = k0 + (e & 15);
+      ra[q] = (r < n && c < n) ? X[(long long)r * n + c] : 0.0;
+      const int rr = k0 + e / TB, cc = bn + e % TB;
+      rb[q] = (rr < n && cc < n) ? X[(long long)rr * n + cc] : 0.0;
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int e = tid + 256 * q;
+      sA0[buf * TB * LDA + (e >> 4) * LDA + (e & 15)] = ra[q];
+      sB0[buf * BK * LDB + (e / TB) * LDB + e % TB] = rb[q];
+    }
+  };
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < n; k0 += BK) {
+    const bool more = (k0 + BK) < n;
+    if (more) load_tiles(k0 + BK);
+    const double* pa = sA0 + buf * TB * LDA + (wm + g) * LDA + t;
+    const double* pb = sB0 + buf * BK * LDB + t * LDB + wn + g;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[6], bf[3];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) af[i] = pa[i * 8 * LDA + kk];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) bf[j] = pb[kk * LDB + j * 8];
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+    if (more) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  const bool mirror = bi != bj;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int r = bm + wm + i * 8 + g;
+    if (r >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = bn + wn + j * 8 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (c + h >= n) continue;
+        C[(long long)r * n + c + h] = acc[i][j][h];
+        if (mirror) C[(long long)(c + h) * n + r] = acc[i][j][h];  // 8 lanes (g) write 8 consecutive doubles
+      }
+    }
+  }
+#else
+  for (int r = bm; r < bm + TB && r < n; ++r)
+    for (int c = bn; c < bn + TB && c < n; ++c) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s += X[(long long)r * n + k] * X[(long long)k * n + c];
+      C[(long long)r * n + c] = s;
+      if (bi != bj) C[(long long)c * n + r] = s;
+    }
+#endif
+}
+
 // ---- Fock build with everything in global memory -------------------------------------------------------
 // off-diagonal blocks: one work item per (pair, mu, lambda)
 SEQM_GLOBAL void fock_large_offdiag_kernel(seqm_batch_t b, const double* __restrict__ P, const double* __restrict__ H,
@@ -277,9 +391,12 @@ SEQM_GLOBAL void fock_large_diag_kernel(seqm_batch_t b, const double* __restrict
 }
 
 // ---- SP2 pieces (one molecule at a time; state in a small device struct) ---------------------------------
+// done: set by the decision step of the iteration that converged (its update still runs); finished: set by the decision
+// step after that -- from then on every SP2 kernel of the stream is a no-op, so the host can queue iterations ahead
+// without reading the state back
 struct Sp2State {
   double h1, hN, tr, tr2, errm0, errm1, nocc;
-  int take_sq, done, iters, pad;
+  int take_sq, done, iters, finished;
 };
 // Gershgorin bounds: one CTA, rows strided over threads
 SEQM_GLOBAL void sp2_bounds_kernel(int n, const double* __restrict__ Fm, double nocc, Sp2State* st) {
@@ -301,6 +418,7 @@ SEQM_GLOBAL void sp2_bounds_kernel(int n, const double* __restrict__ Fm, double 
     st->nocc = nocc;
     st->done = 0;
     st->iters = 0;
+    st->finished = 0;
   }
 }
 SEQM_GLOBAL void sp2_init_kernel(int n, const double* __restrict__ Fm, double* __restrict__ X, const Sp2State* st) {
@@ -339,7 +457,42 @@ SEQM_GLOBAL void sp2_trace_kernel(int n, const double* __restrict__ X, const dou
     }
   }
 }
+// One decision step per SP2 iteration (one CTA): traces of X and X^2 from their diagonals, the branch (SP2.py:55-83), the
+// re-summed trace of the matrix the update kernel is about to write (same element expressions, same summation order as
+// sp2_trace_kernel on the updated matrix), error history and stop test.
+SEQM_GLOBAL void sp2_decide_kernel(int n, const double* __restrict__ X, const double* __restrict__ X2, Sp2State* st, double eps) {
+  __shared__ double red[33];
+  __shared__ int s_sq;
+  if (st->done) {
+    if (threadIdx.x == 0) st->finished = 1;
+    return;
+  }
+  double c = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += X2[(long long)i * n + i];
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    st->tr2 = c;
+    s_sq = (fabs(c - st->nocc) < fabs(2.0 * st->tr - c - st->nocc)) ? 1 : 0;
+    st->take_sq = s_sq;
+  }
+  SEQM_SYNC();
+  const int sq = s_sq;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x2 = X2[(long long)i * n + i];
+    a += sq ? x2 : 2.0 * X[(long long)i * n + i] - x2;
+  }
+  a = block_sum(a, red);
+  if (threadIdx.x == 0) {
+    st->tr = a;
+    st->errm1 = st->errm0;
+    st->errm0 = fabs(a - st->nocc);
+    st->iters += 1;
+    if ((st->errm0 < eps && st->errm1 < eps) || st->iters >= 10000) st->done = 1;
+  }
+}
 SEQM_GLOBAL void sp2_update_kernel(int n, double* __restrict__ X, const double* __restrict__ X2, const Sp2State* st) {
+  if (st->finished) return;
   const int sq = st->take_sq;
   const long long nn = (long long)n * n;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nn; t += (long long)gridDim.x * blockDim.x)
@@ -371,18 +524,24 @@ SEQM_GLOBAL void commutator_kernel(int n, const double* __restrict__ G, double* 
 #endif
   }
 }
-// dots[q] = sum_{i<j} R[i][j] * Rq[i][j] for the cF stored residuals (one CTA per q)
+// dots[q] = sum_{i<j} R[i][j] * Rq[i][j] for the cF stored residuals: SEQM_DOT_PARTS CTAs per q write partial sums
+// (rows strided over the parts), residual_dots_finish_kernel adds them in a fixed order (deterministic, no atomics)
+#define SEQM_DOT_PARTS 64
 SEQM_GLOBAL void residual_dots_kernel(int n, const double* __restrict__ R, const double* __restrict__ hist, long long stride,
-                                      double* __restrict__ emat_row) {
+                                      double* __restrict__ part) {
   __shared__ double red[33];
-  const int q = blockIdx.x;
+  const int q = blockIdx.x / SEQM_DOT_PARTS, slice = blockIdx.x % SEQM_DOT_PARTS;
   const double* Rq = hist + (long long)q * stride;
   double s = 0.0;
-  const long long nn = (long long)n * n;
-  for (long long t = threadIdx.x; t < nn; t += blockDim.x) {
-    const int i = (int)(t / n), j = (int)(t % n);
-    if (j > i) s += R[t] * Rq[t];
-  }
+  for (int i = slice; i < n; i += SEQM_DOT_PARTS)
+    for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) s += R[(long long)i * n + j] * Rq[(long long)i * n + j];
   s = block_sum(s, red);
-  if (threadIdx.x == 0) emat_row[q] = s;
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+SEQM_GLOBAL void residual_dots_finish_kernel(const double* __restrict__ part, int cF, double* __restrict__ emat_row) {
+  for (int q = threadIdx.x; q < cF; q += blockDim.x) {
+    double s = 0.0;
+    for (int k = 0; k < SEQM_DOT_PARTS; ++k) s += part[q * SEQM_DOT_PARTS + k];
+    emat_row[q] = s;
+  }
 }

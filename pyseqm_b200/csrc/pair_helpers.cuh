@@ -86,7 +86,7 @@ SEQM_HD void pair_w(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T
   rotate_to_molecular(ri, nint, Tm, w);
 }
 
-#ifndef SEQM_SECONDARY_TU  // needs the overlap tables, which live in the primary translation unit
+#ifdef SEQM_PAIR_TU  // needs the overlap tables, which live in seqm_pair.cu
 template <class T>
 SEQM_HD void pair_overlap(const seqm_batch_t& b, int i, int j, const PairGeom<T>& g, T S[4][4]) {
   const bool hi = b.atom_Z[i] > 1, hj = b.atom_Z[j] > 1;

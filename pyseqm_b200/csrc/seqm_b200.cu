@@ -3,11 +3,20 @@
 #include <mutex>
 #include <vector>
 
-#include "pair_kernels.cuh"
+#include "atom_kernels.cuh"
 #include "scf_driver.cuh"
 #include "plan_kernels.cuh"
 
 // PM6 d-orbital kernels: second translation unit (seqm_spd.cu)
+// seqm_pair.cu (the pair-code kernels; pairtu_ensure_tables is declared in common.cuh)
+int pairtu_launch_integrals(const seqm_batch_t* b, int cls, int grid, int block, const double* xyz, double* w, double* hab,
+                            cudaStream_t st);
+int pairtu_launch_gradient(const seqm_batch_t* b, int cls, int grid, int block, const double* xyz, const double* D,
+                           const double* P, double* gp, cudaStream_t st);
+int pairtu_launch_gradient_forward(const seqm_batch_t* b, int grid, int block, const double* xyz, const double* P, double* gp,
+                                   cudaStream_t st);
+int pairtu_launch_nuclear(const seqm_batch_t* b, int grid, int block, const double* xyz, const double* w, double* EnucAB,
+                          cudaStream_t st);
 int spd_set_attributes(int smem_optin);
 int spd_launch_pair(const seqm_batch_t* b, const double* xyz, const double* w, double* wd, double* hab_d, cudaStream_t st);
 int spd_launch_hcore(const seqm_batch_t* b, const double* w, const double* hab, double* H, cudaStream_t st);
@@ -102,6 +111,7 @@ static int ensure_device() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQM_DMMA_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(sp2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(dgemm_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEQM_SYM_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fock_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(diis_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   if (e == cudaSuccess && spd_set_attributes(g_smem_optin) != SEQM_OK) return SEQM_ERR_CUDA;
@@ -113,7 +123,7 @@ static int ensure_device() {
   }
 #endif
   g_dev_ready = 1;
-  return ensure_tables();
+  return pairtu_ensure_tables();
 }
 static int check_batch(const seqm_batch_t* b) {
   if (!b || b->nmol <= 0 || b->nat <= 0) {
@@ -185,7 +195,17 @@ static int launch_gemm(int n, const double* A, const double* B, double* C, cudaS
   PROF(PK_GEMM, st, SEQM_LAUNCH(dgemm_kernel, nb * nb, 256, 0, st, n, n, n, A, n, B, n, C, n));
   return seqm_check_launch("dgemm_kernel");
 }
+// C = X X for a symmetric X: upper-triangle tiles only (dgemm_sym_kernel); skip: device flag that voids the launch
+static int launch_gemm_sym(int n, const double* X, double* C, const int* skip, cudaStream_t st) {
+  const int nb = (n + SEQM_SYM_TB - 1) / SEQM_SYM_TB;
+  PROF(PK_GEMM, st, SEQM_LAUNCH(dgemm_sym_kernel, nb * (nb + 1) / 2, 256, SEQM_SYM_SMEM, st, n, X, C, skip));
+  return seqm_check_launch("dgemm_sym_kernel");
+}
 // SP2 purification of one large molecule: X, X2 scratch of n*n doubles, state on the device; P = 2 X.
+// The iterations are queued in chunks without reading the state back: once the decision step has seen convergence the
+// remaining kernels of the chunk return at once (Sp2State.done / finished).  The first chunk is as long as the previous
+// solve needed (consecutive SCF iterations need the same number of purification steps to within one or two).
+static int g_sp2_guess = 0;
 static int sp2_large_one(int n, int nocc, const double* Fm, double* Pm, double eps, double* X, double* X2, Sp2State* stt,
                          int* iters_out, cudaStream_t st) {
   if (eps > 1.0e-3) eps = 1.0e-3;
@@ -197,12 +217,16 @@ static int sp2_large_one(int n, int nocc, const double* Fm, double* Pm, double e
   SEQM_LAUNCH(sp2_trace_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)nullptr, stt, eps, 1);
   int rc = seqm_check_launch("sp2 setup");
   if (rc) return rc;
-  for (int it = 0; it < 10000; ++it) {
-    rc = launch_gemm(n, X, X, X2, st);
-    if (rc) return rc;
-    PROF(PK_SP2, st, SEQM_LAUNCH(sp2_trace_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)X2, stt, eps, 0));
-    PROF(PK_SP2, st, SEQM_LAUNCH(sp2_update_kernel, ge, 256, 0, st, n, X, (const double*)X2, (const Sp2State*)stt));
-    PROF(PK_SP2, st, SEQM_LAUNCH(sp2_trace_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)nullptr, stt, eps, 0));
+  int queued = 0;
+  for (;;) {
+    const int chunk = (queued == 0 && g_sp2_guess > 0) ? g_sp2_guess : 4;
+    for (int it = 0; it < chunk; ++it) {
+      rc = launch_gemm_sym(n, X, X2, &stt->done, st);
+      if (rc) return rc;
+      PROF(PK_SP2, st, SEQM_LAUNCH(sp2_decide_kernel, 1, 1024, 0, st, n, (const double*)X, (const double*)X2, stt, eps));
+      PROF(PK_SP2, st, SEQM_LAUNCH(sp2_update_kernel, ge, 256, 0, st, n, X, (const double*)X2, (const Sp2State*)stt));
+    }
+    queued += chunk;
     rc = seqm_check_launch("sp2 iteration");
     if (rc) return rc;
     Sp2State h;
@@ -215,6 +239,7 @@ static int sp2_large_one(int n, int nocc, const double* Fm, double* Pm, double e
 #endif
     if (h.done) {
       if (iters_out) *iters_out = h.iters;
+      g_sp2_guess = h.iters;
       break;
     }
   }
@@ -263,10 +288,11 @@ static int launch_pair_gradient(const seqm_batch_t* b, const double* xyz, const 
                                 cudaStream_t st) {
   const int n0 = b->pair_cls_off[1] - b->pair_cls_off[0], n1 = b->pair_cls_off[2] - b->pair_cls_off[1],
             n2 = b->pair_cls_off[3] - b->pair_cls_off[2];
-  if (n0 > 0) PROF(PK_GRAD, st, SEQM_LAUNCH(pair_gradient_kernel<0>, grid1d(n0, 128), 128, 0, st, *b, xyz, D, P, gp));
-  if (n1 > 0) PROF(PK_GRAD, st, SEQM_LAUNCH(pair_gradient_kernel<1>, grid1d(n1, 64), 64, 0, st, *b, xyz, D, P, gp));
-  if (n2 > 0) PROF(PK_GRAD, st, SEQM_LAUNCH(pair_gradient_kernel<2>, grid1d(n2, 64), 64, 0, st, *b, xyz, D, P, gp));
-  return seqm_check_launch("pair_gradient_kernel");
+  int rc = SEQM_OK;
+  if (n0 > 0) PROF(PK_GRAD, st, rc = pairtu_launch_gradient(b, 0, grid1d(n0, 128), 128, xyz, D, P, gp, st));
+  if (n1 > 0 && !rc) PROF(PK_GRAD, st, rc = pairtu_launch_gradient(b, 1, grid1d(n1, 64), 64, xyz, D, P, gp, st));
+  if (n2 > 0 && !rc) PROF(PK_GRAD, st, rc = pairtu_launch_gradient(b, 2, grid1d(n2, 64), 64, xyz, D, P, gp, st));
+  return rc;
 }
 static int diis_grid(int nmol) {
 #ifdef SEQM_HOSTEMU
@@ -564,6 +590,15 @@ int seqm_jacobi_stats(unsigned long long* out, int reset) {
 }
 
 /* measured FP64 FMA peak of the device in TFLOP/s (all SMs, 8 chains/thread); blocks the host */
+int seqm_square_product(int n, const double* A, const double* B, double* C, void* stream) {
+  if (n <= 0 || !A || !C) {
+    seqm_set_error("seqm_square_product: bad argument");
+    return SEQM_ERR_ARG;
+  }
+  int rc = ensure_device();
+  if (rc) return rc;
+  return B ? launch_gemm(n, A, B, C, SEQM_STREAM(stream)) : launch_gemm_sym(n, A, C, (const int*)nullptr, SEQM_STREAM(stream));
+}
 double seqm_fp64_peak_tflops(void) {
 #ifndef SEQM_HOSTEMU
   if (ensure_device()) return -1.0;
@@ -682,10 +717,10 @@ int seqm_pair_integrals(const seqm_batch_t* b, const double* xyz, double* w, dou
   cudaStream_t st = SEQM_STREAM(stream);
   const int n0 = b->pair_cls_off[1] - b->pair_cls_off[0], n1 = b->pair_cls_off[2] - b->pair_cls_off[1],
             n2 = b->pair_cls_off[3] - b->pair_cls_off[2];
-  if (n0 > 0) PROF(PK_PAIR, st, SEQM_LAUNCH(pair_integrals_kernel<0>, grid1d(n0, 128), 128, 0, st, *b, xyz, w, hab));
-  if (n1 > 0) PROF(PK_PAIR, st, SEQM_LAUNCH(pair_integrals_kernel<1>, grid1d(n1, 64), 64, 0, st, *b, xyz, w, hab));
-  if (n2 > 0) PROF(PK_PAIR, st, SEQM_LAUNCH(pair_integrals_kernel<2>, grid1d(n2, 64), 64, 0, st, *b, xyz, w, hab));
-  return seqm_check_launch("pair_integrals_kernel");
+  if (n0 > 0) PROF(PK_PAIR, st, rc = pairtu_launch_integrals(b, 0, grid1d(n0, 128), 128, xyz, w, hab, st));
+  if (n1 > 0 && !rc) PROF(PK_PAIR, st, rc = pairtu_launch_integrals(b, 1, grid1d(n1, 64), 64, xyz, w, hab, st));
+  if (n2 > 0 && !rc) PROF(PK_PAIR, st, rc = pairtu_launch_integrals(b, 2, grid1d(n2, 64), 64, xyz, w, hab, st));
+  return rc;
 }
 
 int seqm_pair_integrals_d(const seqm_batch_t* b, const double* xyz, const double* w, double* wd, double* hab_d,
@@ -713,7 +748,8 @@ int seqm_hcore(const seqm_batch_t* b, const double* w, const double* hab, double
     PROF(PK_HCORE, SEQM_STREAM(stream), rc = spd_launch_hcore(b, w, hab, H, SEQM_STREAM(stream)));
     return rc;
   }
-  PROF(PK_HCORE, SEQM_STREAM(stream), SEQM_LAUNCH(hcore_kernel, b->nmol, 128, 0, SEQM_STREAM(stream), *b, w, hab, H));
+  const int slices = (b->nmax > SEQM_MAX_ORB) ? 32 : 1;
+  PROF(PK_HCORE, SEQM_STREAM(stream), SEQM_LAUNCH(hcore_kernel, b->nmol * slices, 128, 0, SEQM_STREAM(stream), *b, w, hab, H, slices));
   return seqm_check_launch("hcore_kernel");
 }
 
@@ -787,8 +823,7 @@ int seqm_nuclear_energy(const seqm_batch_t* b, const double* xyz, const double* 
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    PROF(PK_NUC, SEQM_STREAM(stream), SEQM_LAUNCH(nuclear_energy_kernel, grid1d(b->npairs, 128), 128, 0, SEQM_STREAM(stream), *b, xyz, w, EnucAB));
-    rc = seqm_check_launch("nuclear_energy_kernel");
+    PROF(PK_NUC, SEQM_STREAM(stream), rc = pairtu_launch_nuclear(b, grid1d(b->npairs, 128), 128, xyz, w, EnucAB, SEQM_STREAM(stream)));
     if (rc) return rc;
   }
   SEQM_LAUNCH(pair_sum_kernel, b->nmol, 64, 0, SEQM_STREAM(stream), *b, EnucAB, Enuc);
@@ -884,8 +919,7 @@ int seqm_gradient_forward(const seqm_batch_t* b, const double* xyz, const double
   int rc = check_batch(b);
   if (rc) return rc;
   if (b->npairs > 0) {
-    SEQM_LAUNCH(pair_gradient_forward_kernel, grid1d(b->npairs, 64), 64, 0, SEQM_STREAM(stream), *b, xyz, P, pair_scratch);
-    rc = seqm_check_launch("pair_gradient_forward_kernel");
+    rc = pairtu_launch_gradient_forward(b, grid1d(b->npairs, 64), 64, xyz, P, pair_scratch, SEQM_STREAM(stream));
     if (rc) return rc;
   }
   SEQM_LAUNCH(atom_gradient_kernel, grid1d(b->nat, 128), 128, 0, SEQM_STREAM(stream), *b, pair_scratch, grad);
@@ -1250,7 +1284,9 @@ int seqm_scf(const seqm_batch_t* b, const seqm_scf_opts_t* o, const double* H, c
           rc = launch_gemm(n, F + hm[m].mat0, P + hm[m].mat0, W.Xl, st);  // G = F P ; R = G - G^t
           if (rc) return rc;
           PROF(PK_DIIS_STORE, st, SEQM_LAUNCH(commutator_kernel, grid1d(nn, 256), 256, 0, st, n, (const double*)W.Xl, Rh, W.rmax));
-          PROF(PK_DIIS_STORE, st, SEQM_LAUNCH(residual_dots_kernel, cF, 1024, 0, st, n, (const double*)Rh, (const double*)(W.RES + h0), nn,
+          PROF(PK_DIIS_STORE, st, SEQM_LAUNCH(residual_dots_kernel, cF * SEQM_DOT_PARTS, 256, 0, st, n, (const double*)Rh,
+                                              (const double*)(W.RES + h0), nn, W.part));
+          PROF(PK_DIIS_STORE, st, SEQM_LAUNCH(residual_dots_finish_kernel, 1, 32, 0, st, (const double*)W.part, cF,
                                               W.EMAT + (long long)m * SEQM_EM * SEQM_EM + counter * SEQM_EM));
 #ifndef SEQM_HOSTEMU
           cudaMemcpyAsync(W.diis_err + m, W.rmax, sizeof(double), cudaMemcpyDeviceToDevice, st);

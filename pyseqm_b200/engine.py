@@ -462,6 +462,21 @@ def op_orbitals_dense(plan, Cm):
     return V
 
 
+def op_post_scf(plan, P, xyz, g=None, want_dipole=True):
+    """Mulliken charges (nmol, molsize), ground-state dipole (nmol, 3) and force = -g in the padded (nmol, molsize, 3)
+    layout, one launch on the packed density (seqm_post_scf).  g: (nat, 3) from op_gradient, or None."""
+    from .seqm_functions.constants import a0, debye_to_AU, to_debye
+
+    q = torch.empty((plan.nmol, plan.molsize), dtype=torch.float64, device=plan.device)
+    dip = torch.empty((plan.nmol, 3), dtype=torch.float64, device=plan.device) if want_dipole else None
+    force = torch.empty((plan.nmol, plan.molsize, 3), dtype=torch.float64, device=plan.device) if g is not None else None
+    if g is not None:
+        g = g.contiguous()
+    plan.lib.check(plan.lib.dll.seqm_post_scf(plan.ref, ptr(P), ptr(xyz), ptr(g), ptr(q), ptr(dip), ptr(force), float(a0),
+                                              float(to_debye * debye_to_AU), stream_of(q)), "seqm_post_scf")  # fmt: skip
+    return q, dip, force
+
+
 def op_mo_match(plan, V_new, V_old, e):
     """Energy._crossing_match_molecular_orbitals[_grouped] (basics.py:596-719): V (nmol, nmax, nmax), e (nmol, nmax)."""
     V_new, V_old, e = V_new.contiguous(), V_old.contiguous(), e.contiguous()
