@@ -8,6 +8,8 @@
 // Per rotation step all n/2 disjoint pairs are annihilated at once: thread (k,l) owns the 2x2 tile
 // rows {p_k,q_k} x cols {p_l,q_l} and applies R_k^t . tile . R_l in place, so one barrier per step.
 #pragma once
+#include <utility>
+
 #include "common.cuh"
 
 #define SEQM_JACOBI_MAX_SWEEPS 60
@@ -169,6 +171,30 @@ SEQM_D seqm_d2 jacobi_pair_rotation(const double* A, int k, int ph, double tol, 
 // Optional fused DIIS mixing (scf_loop.py:1045-1056) at the end of the density solve: Pold <- P ;
 // P <- a P + (1 - a) Pnew with a = 0.5 until two Fock matrices are stored (*cF < 2), else 0.
 struct JacobiMix { double* P; double* Pold; const int* cF; };
+
+#ifndef SEQM_HOSTEMU
+// shared-memory accesses through 32-bit shared-window addresses (no generic-pointer arithmetic in the sweep loop);
+// volatile: never merged or moved across the block barriers
+SEQM_D double seqm_lds(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+SEQM_D void seqm_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+template <int OFF>
+SEQM_D seqm_d2 seqm_lds2(unsigned a) {
+  seqm_d2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int PH>
+struct JacobiPhase { static constexpr int value = PH; };
+// f(JacobiPhase<0>{}), f(JacobiPhase<1>{}), ... : a loop whose index is a compile-time constant inside the body
+template <int... Js, class F>
+SEQM_D void seqm_static_for(std::integer_sequence<int, Js...>, F&& f) {
+  (f(JacobiPhase<Js>{}), ...);
+}
+#endif
 
 #ifndef SEQM_HOSTEMU
 // one FP64 tensor-core step: the 8x8 accumulator tile (c0, c1 = row lane/4, columns 2 (lane%4) + {0,1}) gains
@@ -388,7 +414,11 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   constexpr int TPO = (NR + NO - 1) / NO;             // remaining tiles per non-part-A thread
   constexpr int TPX = (TPO > 1) ? TPO : 1;
 #ifndef SEQM_HOSTEMU
-  int tk[TPX], tl[TPX], oe[TPX][4], oo[TPX][4];
+  // per owned tile: does it exist / is it diagonal, the shared-window byte addresses of its four elements in even
+  // (ae) and odd (ao) steps and of its two rotation pairs in the cs buffer of even steps (odd: + NP * 16 bytes)
+  bool thas[TPX], tdiag[TPX];
+  unsigned ae[TPX][4], ao[TPX][4], ck_a[TPX], cl_a[TPX];
+  const unsigned A_u32 = seqm_smem_u32(A), cs_u32 = seqm_smem_u32(cs);
 #pragma unroll
   for (int qt = 0; qt < TPX; ++qt) {
     int k = -1, l = 0;
@@ -398,10 +428,20 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
       const int r = (tid - NA) + qt * NO;
       if (r < NR) jacobi_rest_tile<NP>(r, k, l);
     }
-    tk[qt] = k;
-    tl[qt] = l;
-    jacobi_tile_offsets<NP>(k < 0 ? 0 : k, l, oe[qt], oo[qt]);
+    thas[qt] = k >= 0;
+    tdiag[qt] = k == l;
+    int oe[4], oo[4];
+    jacobi_tile_offsets<NP>(k < 0 ? 0 : k, l, oe, oo);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ae[qt][e] = A_u32 + 8u * (unsigned)oe[e];
+      ao[qt][e] = A_u32 + 8u * (unsigned)oo[e];
+    }
+    ck_a[qt] = cs_u32 + 16u * (unsigned)(k < 0 ? 0 : k);
+    cl_a[qt] = cs_u32 + 16u * (unsigned)l;
   }
+  const unsigned vcs_a = cs_u32 + 16u * (unsigned)(vseg * (SEG / 2));  // first rotation pair of this thread's V segment
+  const unsigned vcp_a = cs_u32 + 16u * (unsigned)((vseg * (SEG / 2) + NP - 1) % NP);  // (previous segment's last, my first)
 #endif
   __shared__ int s_flag[2][2];  // [sweep parity][0: some rotation, 1: some rotation above tol_big]
   if (tid == 0) { s_flag[0][0] = s_flag[0][1] = s_flag[1][0] = s_flag[1][1] = 0; }
@@ -440,39 +480,77 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     // rotations of step 0 (the later ones are computed inside the previous step)
     for (int k = tid; k < NP; k += nthr) cs[k] = jacobi_pair_rotation<NP>(A, k, 0, tol, tol_big, flag);
     SEQM_SYNC();
-    for (int step = 0; step < M; ++step) {
-      const int ph = step & 1;
-      const seqm_d2* csc = cs + (step & 1) * NP;       // this step's rotations
-      seqm_d2* csn = cs + ((step + 1) & 1) * NP;       // next step's
-      if (step == 1 && tid == 0) { s_flag[(sweep + 1) & 1][0] = 0; s_flag[(sweep + 1) & 1][1] = 0; }
+#ifndef SEQM_HOSTEMU
+    // One rotation step with the phase (even / odd pairing) as a compile-time constant: the tile addresses of the
+    // phase are plain registers and the rotation pairs are read at immediate offsets from per-tile base addresses.
+    auto step_body = [&](auto phc, int step) {
+      constexpr int PH = decltype(phc)::value;
+      constexpr int CUR = PH * NP * 16;              // byte offset of this step's rotations in the cs double buffer
+      seqm_d2* csn = cs + (PH ^ 1) * NP;             // next step's
+      if (PH == 1 && step == 1 && tid == 0) { s_flag[(sweep + 1) & 1][0] = 0; s_flag[(sweep + 1) & 1][1] = 0; }
       // ---- A <- M_k^t A M_l on the upper-triangular tiles k <= l only (A is symmetric; elements (r,c) with
       //      r <= c are authoritative, the wrap pair (m-1,0) of odd steps uses the mirrored location (0,r))
-#ifndef SEQM_HOSTEMU
 #pragma unroll
       for (int qt = 0; qt < TPX; ++qt) {
-        const int k = tk[qt], l = tl[qt];
-        if (k >= 0) {
-          const int a00 = ph ? oo[qt][0] : oe[qt][0], a01 = ph ? oo[qt][1] : oe[qt][1];
-          const int a10 = ph ? oo[qt][2] : oe[qt][2], a11 = ph ? oo[qt][3] : oe[qt][3];
-          const seqm_d2 ck = csc[k], cl = csc[l];
-          const bool diag = (k == l);
-          const double x0 = A[a00], y0 = A[a01], y1 = A[a11];
-          const double x1 = diag ? y0 : A[a10];
+        if (thas[qt]) {
+          const unsigned a00 = PH ? ao[qt][0] : ae[qt][0], a01 = PH ? ao[qt][1] : ae[qt][1];
+          const unsigned a10 = PH ? ao[qt][2] : ae[qt][2], a11 = PH ? ao[qt][3] : ae[qt][3];
+          const seqm_d2 ck = seqm_lds2<CUR>(ck_a[qt]), cl = seqm_lds2<CUR>(cl_a[qt]);
+          const bool diag = tdiag[qt];
+          const double x0 = seqm_lds(a00), y0 = seqm_lds(a01), y1 = seqm_lds(a11);
+          const double x1 = diag ? y0 : seqm_lds(a10);
           const double bx0 = cl.x * x0 + cl.y * y0, by0 = cl.y * x0 - cl.x * y0;
           const double bx1 = cl.x * x1 + cl.y * y1, by1 = cl.y * x1 - cl.x * y1;
-          A[a00] = ck.x * bx0 + ck.y * bx1;
-          A[a01] = ck.x * by0 + ck.y * by1;
-          A[a11] = ck.y * by0 - ck.x * by1;
-          if (!diag) A[a10] = ck.y * bx0 - ck.x * bx1;
+          seqm_sts(a00, ck.x * bx0 + ck.y * bx1);
+          seqm_sts(a01, ck.x * by0 + ck.y * by1);
+          seqm_sts(a11, ck.y * by0 - ck.x * by1);
+          if (!diag) seqm_sts(a10, ck.y * bx0 - ck.x * bx1);
         }
         if (qt == 0 && tid < GA) {
           // the part-A tiles are done: their warps (only) meet on named barrier 1 and compute the next rotations
           if (GA == K::THREADS) __syncthreads();
           else asm volatile("bar.sync 1, %0;" ::"r"(GA) : "memory");
-          if (step + 1 < M && tid < NP) csn[tid] = jacobi_pair_rotation<NP>(A, tid, ph ^ 1, tol, tol_big, flag);
+          if (step + 1 < M && tid < NP) csn[tid] = jacobi_pair_rotation<NP>(A, tid, PH ^ 1, tol, tol_big, flag);
         }
       }
+      // ---- V <- V M
+      if (PH == 0) {
+        seqm_static_for(std::make_integer_sequence<int, SEG / 2>{}, [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          const seqm_d2 c = seqm_lds2<CUR + 16 * j>(vcs_a);
+          const double x = vr[2 * j], y = vr[2 * j + 1];
+          vr[2 * j] = c.x * x + c.y * y;
+          vr[2 * j + 1] = c.y * x - c.x * y;
+        });
+      } else {
+        const int lane = tid & 31;
+        const double first_old = vr[0], last_old = vr[SEG - 1];
+        const double y_next = __shfl_sync(0xffffffffu, first_old, (lane & ~(SR - 1)) | ((lane + 1) & (SR - 1)));
+        const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~(SR - 1)) | ((lane + SR - 1) & (SR - 1)));
+        seqm_static_for(std::make_integer_sequence<int, SEG / 2 - 1>{}, [&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          const seqm_d2 c = seqm_lds2<CUR + 16 * j>(vcs_a);
+          const double x = vr[2 * j + 1], y = vr[2 * j + 2];
+          vr[2 * j + 1] = c.x * x + c.y * y;
+          vr[2 * j + 2] = c.y * x - c.x * y;
+        });
+        const seqm_d2 cn = seqm_lds2<CUR + 16 * (SEG / 2 - 1)>(vcs_a);  // pair (my last, next quarter's first)
+        const seqm_d2 cp = seqm_lds2<CUR>(vcp_a);                       // pair (previous quarter's last, my first)
+        vr[SEG - 1] = cn.x * last_old + cn.y * y_next;
+        vr[0] = cp.y * x_prev - cp.x * first_old;
+      }
+      SEQM_SYNC();
+    };
+    for (int step = 0; step < M; step += 2) {
+      step_body(JacobiPhase<0>{}, step);
+      step_body(JacobiPhase<1>{}, step + 1);
+    }
 #else
+    for (int step = 0; step < M; ++step) {
+      const int ph = step & 1;
+      const seqm_d2* csc = cs + (step & 1) * NP;       // this step's rotations
+      seqm_d2* csn = cs + ((step + 1) & 1) * NP;       // next step's
+      if (step == 1 && tid == 0) { s_flag[(sweep + 1) & 1][0] = 0; s_flag[(sweep + 1) & 1][1] = 0; }
       for (int t = 0; t < NT; ++t) {  // the single emulation thread plays every tile owner, part A first
         int k, l;
         if (t < NA) jacobi_part_a_tile<NP>(t, k, l);
@@ -494,35 +572,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         if (t == NA - 1 && step + 1 < M)
           for (int kk = 0; kk < NP; ++kk) csn[kk] = jacobi_pair_rotation<NP>(A, kk, ph ^ 1, tol, tol_big, flag);
       }
-#endif
       // ---- V <- V M
-#ifndef SEQM_HOSTEMU
-      if (!ph) {
-#pragma unroll
-        for (int j = 0; j < SEG / 2; ++j) {
-          const seqm_d2 c = csc[vseg * (SEG / 2) + j];
-          const double x = vr[2 * j], y = vr[2 * j + 1];
-          vr[2 * j] = c.x * x + c.y * y;
-          vr[2 * j + 1] = c.y * x - c.x * y;
-        }
-      } else {
-        const int lane = tid & 31;
-        const double first_old = vr[0], last_old = vr[SEG - 1];
-        const double y_next = __shfl_sync(0xffffffffu, first_old, (lane & ~(SR - 1)) | ((lane + 1) & (SR - 1)));
-        const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~(SR - 1)) | ((lane + SR - 1) & (SR - 1)));
-#pragma unroll
-        for (int j = 0; j < SEG / 2 - 1; ++j) {
-          const seqm_d2 c = csc[vseg * (SEG / 2) + j];
-          const double x = vr[2 * j + 1], y = vr[2 * j + 2];
-          vr[2 * j + 1] = c.x * x + c.y * y;
-          vr[2 * j + 2] = c.y * x - c.x * y;
-        }
-        const seqm_d2 cn = csc[vseg * (SEG / 2) + SEG / 2 - 1];    // pair (my last, next quarter's first)
-        const seqm_d2 cp = csc[(vseg * (SEG / 2) + NP - 1) % NP];  // pair (previous quarter's last, my first)
-        vr[SEG - 1] = cn.x * last_old + cn.y * y_next;
-        vr[0] = cp.y * x_prev - cp.x * first_old;
-      }
-#else
       for (int i = 0; i < M; ++i)
         for (int l = 0; l < NP; ++l) {
           const int p = 2 * l + ph, q = (p + 1) % M;
@@ -530,9 +580,9 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
           Vh[i * M + p] = csc[l].x * x + csc[l].y * y;
           Vh[i * M + q] = csc[l].y * x - csc[l].x * y;
         }
-#endif
       SEQM_SYNC();
     }
+#endif
     // quadratic convergence: once every rotation of a sweep was below tol_big (1e-6 |A| inside the SCF, 1e-8 |A|
     // when eigenpairs are returned) the off-diagonal left behind is O(tol_big^2 / gap): an occupied-virtual
     // coupling below 1e-9 eV, i.e. a density error below 1e-10, so no check sweep is needed
