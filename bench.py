@@ -247,8 +247,9 @@ def parity_at_size(seqm, dev, const, species_h, coords_h, want_ref_gpu):
     return par, cpu, ref_gpu, ok_num
 
 
-def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist, sp2):
-    """replica-steps/s of XL-BOMD NVE on `nrep` coronene replicas per GPU (configs[2]; t = 0 SCF excluded)."""
+def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist, sp2, ksa=None):
+    """replica-steps/s of XL-BOMD NVE on `nrep` coronene replicas per GPU (configs[2]; t = 0 SCF excluded).
+    ksa: xl_bomd_params of a KSA_XL_BOMD run (rank-m Krylov kernel at electronic temperature T_el) instead."""
     import torch
 
     xyz = os.path.join(ROOT, "tests", "golden", "xyz", "coronene.xyz")
@@ -256,7 +257,10 @@ def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist, sp2):
     sp = {"method": "AM1", "scf_eps": 1.0e-7, "scf_converger": [2], "sp2": sp2}
     torch.manual_seed(1234 + int(os.environ.get("RANK", "0")))
     mol = seqm.Molecule(const, sp, torch.as_tensor(c, device=dev), torch.as_tensor(s, device=dev))
-    md = seqm.XL_BOMD(xl_bomd_params={"k": 6}, seqm_parameters=sp, timestep=0.4, Temp=300.0)
+    if ksa:
+        md = seqm.KSA_XL_BOMD(xl_bomd_params=dict(ksa), seqm_parameters=sp, timestep=0.4, Temp=300.0)
+    else:
+        md = seqm.XL_BOMD(xl_bomd_params={"k": 6}, seqm_parameters=sp, timestep=0.4, Temp=300.0)
     md.initialize(mol)
     for i in range(3):
         md._do_integrator_step(i, mol, dict())
@@ -269,7 +273,7 @@ def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist, sp2):
     for i in range(3, 3 + nsteps):
         md._do_integrator_step(i, mol, dict())
         if i % 50 == 0:
-            Es.append(mol.Etot + md._kinetic_energy(mol))
+            Es.append(md._thermo_potential(mol) + md._kinetic_energy(mol))
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
@@ -279,8 +283,10 @@ def xl_bomd_rate(seqm, dev, const, nrep, nsteps, world, dist, sp2):
     drift = float((torch.stack(Es) - Es[0]).abs().max()) if len(Es) > 1 else None
     return {"metric": "XL-BOMD MD steps/s (replica-steps/s)", "value": nrep * world * nsteps / float(t), "unit": "replica-steps/s",
             "ms_per_md_step": float(t) / nsteps * 1e3, "replicas_per_gpu": nrep, "steps": nsteps, "molecule": "coronene C24H12 (108 orbitals)",
-            "method": "AM1, k=6, dt=0.4 fs, 300 K, density by " + ("in-SM SP2 purification on the FP64 tensor cores, eps 1e-5"
-                                                               if sp2[0] else "the Jacobi eigensolver (reference branch xlbomd.py:361)"),
+            "method": "AM1, k=6, dt=0.4 fs, 300 K, density by " + (
+                f"Fermi occupations at T_el = {ksa['T_el']} K, rank-{ksa['max_rank']} Krylov kernel (KSA_XL_BOMD, xlbomd.py:201-341)" if ksa
+                else "in-SM SP2 purification on the FP64 tensor cores, eps 1e-5" if sp2[0]
+                else "the Jacobi eigensolver (reference branch xlbomd.py:361)"),
             "max_abs_total_energy_change_eV": drift,
             "finite": bool(torch.isfinite(mol.Etot).all() and torch.isfinite(Ek).all())}  # fmt: skip
 
@@ -655,6 +661,13 @@ def main():
         eig = xl_bomd_rate(seqm, dev, const, args.xl_replicas, min(nsteps, 100), world, d, [False])
         xl["eigensolver_branch"] = {k: eig[k] for k in ("value", "unit", "ms_per_md_step", "steps", "method", "finite")}
         xl["reference_cpu"] = "21.5 replica-steps/s (16 replicas x 10 steps, 8 host threads; BASELINE.md section 2)"
+        try:  # KSA-XL-BOMD on the same replicas (a quarter of them: every step is 3 response solves)
+            kp = {"k": 6, "max_rank": 3, "err_threshold": 0.0, "T_el": 1500}
+            ks = xl_bomd_rate(seqm, dev, const, max(args.xl_replicas // 4, 1), min(nsteps, 50), world, d, [False], ksa=kp)
+            xl["ksa_branch"] = {k: ks[k] for k in ("value", "unit", "ms_per_md_step", "replicas_per_gpu", "steps", "method",
+                                                   "max_abs_total_energy_change_eV", "finite")}  # fmt: skip
+        except Exception as e:
+            xl["ksa_branch"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
     parity = cpu_baseline = ref_gpu = c380 = pm6 = None
     parity_ok = True

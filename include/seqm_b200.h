@@ -232,6 +232,21 @@ int seqm_orbitals_dense(const seqm_batch_t* b, const double* C, double* V, void*
 int seqm_post_scf(const seqm_batch_t* b, const double* P, const double* xyz, const double* grad, double* q, double* dipole,
                   double* force, double a0, double scale, void* stream);
 
+/* ---- KSA-XL-BOMD building blocks on the packed layout (seqm_ksa.cu; reference: xlbomd.py:201-341, fermi_q.py:8-72,
+ * canon_dm_prt.py:6-39).  One CTA per molecule; every matrix argument is a packed [mat_total] buffer.
+ *   seqm_packed_gemm     C_m = op(A_m) op(B_m), op = transpose when the flag is non-zero; C must not alias A or B
+ *   seqm_scale_columns   out_m[i][k] = s * f[m*nmax + k] * C_m[i][k]   (D0 = (2 Q f) Q^t with seqm_packed_gemm)
+ *   seqm_canon_prt       in place: X_m (first-order Fock perturbation in the eigenbasis) -> first-order density response in
+ *                        the eigenbasis incl. the chemical-potential correction; e [nmol*nmax] eigenvalues, mu [nmol],
+ *                        beta = 1 / (kB T_el), m_iter recursion steps (the reference uses 10)
+ *   seqm_packed_dot      out[m] = sum_ij X_m[i][j] Y_m[i][j]
+ *   seqm_packed_axpby    Y_m = a[m] X_m + c[m] Y_m  (a NULL: 1, c NULL: 1, X NULL: Y_m = c[m] Y_m) */
+int seqm_packed_gemm(const seqm_batch_t* b, const double* A, const double* B, double* C, int transA, int transB, void* stream);
+int seqm_scale_columns(const seqm_batch_t* b, const double* C, const double* f, double s, double* out, void* stream);
+int seqm_canon_prt(const seqm_batch_t* b, const double* e, const double* mu, double* X, double beta, int m_iter, void* stream);
+int seqm_packed_dot(const seqm_batch_t* b, const double* X, const double* Y, double* out, void* stream);
+int seqm_packed_axpby(const seqm_batch_t* b, const double* a, const double* X, const double* c, double* Y, void* stream);
+
 /* MO crossing matcher -- Energy._crossing_match_molecular_orbitals / _grouped, seqm/basics.py:596-719 (called on every
  * forward after the first one on the same Molecule, basics.py:846-857): the new orbitals are permuted inside the
  * occupied and inside the virtual block so that orbital k continues old orbital k (largest |overlap|, greedy repair

@@ -124,8 +124,8 @@ class XL_BOMD(Molecular_Dynamics_Basic):
     def __init__(self, damp=None, xl_bomd_params=dict(), *args, **kwargs):
         if damp is not None:
             raise NotImplementedError("Langevin damping is not provided by the B200 MD driver (damp=None only)")
-        if "max_rank" in xl_bomd_params:
-            raise NotImplementedError("KSA-XL-BOMD (max_rank) is not part of the B200 path")
+        if "max_rank" in xl_bomd_params and not self._KSA:
+            raise NotImplementedError("xl_bomd_params['max_rank'] selects the Krylov kernel: use KSA_XL_BOMD")
         super().__init__(*args, **kwargs)
         self.k = xl_bomd_params["k"]
         self.xl_bomd_params = xl_bomd_params
@@ -139,8 +139,15 @@ class XL_BOMD(Molecular_Dynamics_Basic):
         self.coeff = tmp.repeat(2)
         self._ctx = None
 
+    _KSA = False
+
     def _thermo_potential(self, molecule):
         return molecule.Etot + molecule.Electronic_entropy
+
+    def _propagation_source(self, ctx):
+        """(X, c) of P(n+1) = kappa [c X + (1 - c) P(n)] + sum_j coeff_j Pt[j]: the density D(n) with c = 0.95
+        (MolecularDynamics.py:1418-1427)."""
+        return ctx["D"], 0.95
 
     def initialize(self, molecule, remove_com=None, learned_parameters=dict(), steps=None, *args, **kwargs):
         molecule.Electronic_entropy = torch.zeros(molecule.species.shape[0], dtype=torch.float64,
@@ -174,15 +181,19 @@ class XL_BOMD(Molecular_Dynamics_Basic):
             molecule.coordinates.add_(molecule.velocities * dt)
             # P(n+1) = kappa [c D(n) + (1-c) P(n)] + sum_j coeff_j Pt[j]    (c = 0.95; eq. 22 of the paper)
             cindx = step % self.m
-            c = 0.95
-            P = engine.op_xl_propagate(plan, self.coeff_D, c, ctx["D"], ctx["P"], ctx["Pt"],
+            src, c = self._propagation_source(ctx)
+            P = engine.op_xl_propagate(plan, self.coeff_D, c, src, ctx["P"], ctx["Pt"],
                                        self.coeff[cindx : cindx + self.m].contiguous(), self.m - 1 - cindx)
             ctx["P"] = P
         # MD needs D, E, forces only.  molecule.dm / molecule.q are refreshed at the end of run() (or on demand by
         # refresh_density()); inside the loop the density lives in the packed layout (molecule._dm_packed)
         r = self.esdriver.conservative_force_xl.forward_packed(molecule, P, want_e=False,
-                                                               learned_parameters=learned_parameters)
+                                                               learned_parameters=learned_parameters,
+                                                               xl_bomd_params=self.xl_bomd_params if self._KSA else None)
         ctx["D"] = r["D"]
+        if self._KSA:
+            ctx["d2"] = r["dP2dt2"]
+            molecule.Electronic_entropy, molecule.Krylov_Error, molecule.Fermi_occ = r["EEnt"], r["Krylov_Error"], r["Fermi_occ"]
         molecule.force, molecule.Hf, molecule.Etot = r["force"], r["Hf"], r["Etot"]
         molecule.Eelec, molecule.Enuc, molecule.Eiso = r["Eelec"], r["Enuc"], r["Eiso"]
         molecule._dm_packed = r["D"]
@@ -214,3 +225,30 @@ class XL_BOMD(Molecular_Dynamics_Basic):
         out = super().run(molecule, steps, *args, **kwargs)
         self.refresh_density(molecule)
         return out
+
+
+class KSA_XL_BOMD(XL_BOMD):
+    """Krylov-subspace-approximation XL-BOMD (MolecularDynamics.py:1608-1619): the field density is driven by the rank-m
+    approximation of the kernel acting on D - P at electronic temperature T_el,
+    P(n+1) = kappa (dP2dt2(n) + P(n)) + sum_j coeff_j Pt[j]; xl_bomd_params = {"k", "max_rank", "err_threshold", "T_el"}."""
+
+    _KSA = True
+
+    def __init__(self, damp=None, xl_bomd_params=dict(), *args, **kwargs):
+        for key in ("max_rank", "err_threshold", "T_el"):
+            if key not in xl_bomd_params:
+                raise KeyError(f"KSA_XL_BOMD needs xl_bomd_params[{key!r}]")
+        super().__init__(damp, xl_bomd_params, *args, **kwargs)
+
+    def _propagation_source(self, ctx):
+        return ctx["d2"] + ctx["P"], 1.0
+
+    def initialize(self, molecule, *args, **kwargs):
+        super().initialize(molecule, *args, **kwargs)
+        if "d2" not in self._ctx:
+            self._ctx["d2"] = torch.zeros_like(self._ctx["P"])  # dP2dt2 = 0 at t = 0 (MolecularDynamics.py:1580-1581)
+
+    def refresh_density(self, molecule):
+        super().refresh_density(molecule)
+        if self._ctx is not None:
+            molecule.dP2dt2 = engine.op_unpack(molecule._plan, self._ctx["d2"])

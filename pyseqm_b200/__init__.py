@@ -2,7 +2,7 @@
 `Molecule` / `Electronic_Structure(seqm_parameters).forward` API.  `import pyseqm_b200 as seqm`."""
 from .ElectronicStructure import Electronic_Structure  # noqa: F401
 from .Molecule import Molecule  # noqa: F401
-from .MolecularDynamics import XL_BOMD, Molecular_Dynamics_Basic  # noqa: F401
+from .MolecularDynamics import KSA_XL_BOMD, XL_BOMD, Molecular_Dynamics_Basic  # noqa: F401
 from .seqm_functions.constants import Constants  # noqa: F401
 from .seqm_functions.read_xyz import read_xyz  # noqa: F401
 

@@ -64,11 +64,12 @@ class SeqmError(RuntimeError):
     pass
 
 
-SOURCES = ("seqm_b200.cu", "seqm_pair.cu", "seqm_spd.cu", "seqm_eigh.cu", "seqm_post.cu")  # translation units, compiled in parallel
+SOURCES = ("seqm_b200.cu", "seqm_pair.cu", "seqm_spd.cu", "seqm_eigh.cu", "seqm_post.cu", "seqm_ksa.cu")  # translation units, compiled in parallel
 # files that only one translation unit includes (everything else is shared): an edit there recompiles that unit alone
 _ONLY = {"seqm_spd.cu": {"seqm_spd.cu", "spd_kernels.cuh"},
          "seqm_eigh.cu": {"seqm_eigh.cu", "hestenes_kernels.cuh"},
          "seqm_post.cu": {"seqm_post.cu"},
+         "seqm_ksa.cu": {"seqm_ksa.cu"},
          "seqm_pair.cu": {"seqm_pair.cu", "pair_kernels.cuh"},  # ~25 min of nvcc: keep edits out of it
          "seqm_b200.cu": {"seqm_b200.cu", "atom_kernels.cuh", "scf_driver.cuh", "plan_kernels.cuh", "eig_kernels.cuh",
                           "fock_kernels.cuh", "large_kernels.cuh"}}  # fmt: skip
@@ -161,6 +162,11 @@ class SeqmLib:
             "seqm_launch_count": ([], C.c_longlong),
             "seqm_fp64_peak_tflops": ([], C.c_double),
             "seqm_square_product": ([C.c_int, P, P, P, P], C.c_int),
+            "seqm_packed_gemm": ([B, P, P, P, C.c_int, C.c_int, P], C.c_int),
+            "seqm_scale_columns": ([B, P, P, C.c_double, P, P], C.c_int),
+            "seqm_canon_prt": ([B, P, P, P, C.c_double, C.c_int, P], C.c_int),
+            "seqm_packed_dot": ([B, P, P, P, P], C.c_int),
+            "seqm_packed_axpby": ([B, P, P, P, P, P], C.c_int),
             "seqm_jacobi_stats": ([C.POINTER(C.c_ulonglong), C.c_int], C.c_int),
             "seqm_profile_enable": ([C.c_int], C.c_int),
             "seqm_profile_kinds": ([], C.c_int),

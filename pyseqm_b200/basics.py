@@ -175,11 +175,14 @@ class ForceXL(torch.nn.Module):
         # the warm-start eigenvectors of the previous step live on the MOLECULE, tagged with its plan (`_C_xl`): a
         # driver reused for another batch must never feed the eigensolver a guess that belongs to a different plan
 
-    def forward_packed(self, molecule, Pp, want_e=True, learned_parameters=None):
+    def forward_packed(self, molecule, Pp, want_e=True, learned_parameters=None, xl_bomd_params=None):
         plan = molecule._plan
         const = molecule.const
+        ksa = bool(xl_bomd_params) and "max_rank" in xl_bomd_params
         if plan.d_mode:
             raise NotImplementedError("XL-BOMD with PM6 d-shell elements is not on the B200 path")
+        if ksa and (self.sp2[0] or plan.large and not plan.eig_ok):
+            raise NotImplementedError("KSA-XL-BOMD needs the eigenpairs of the Fock matrix: eigensolver route, <= 256 orbitals")
         if learned_parameters:  # xlbomd.py:90-116 re-packs the parameters on every step
             if callable(learned_parameters):
                 raise NotImplementedError("callable learned_parameters need autograd through the SCF; not on the B200 path")
@@ -190,7 +193,10 @@ class ForceXL(torch.nn.Module):
         H = engine.op_hcore(plan, w, hab)
         t0 = _timing(molecule, "Hcore + STO Integrals", t0)
         F = engine.op_fock(plan, Pp, H, w)
-        if self.sp2[0]:
+        extra = {}
+        if ksa:
+            e_mo_n, D, extra = self._ksa_density(molecule, plan, F, Pp, w, xl_bomd_params)
+        elif self.sp2[0]:
             D, _ = engine.op_sp2_density(plan, F, self.sp2[1])
             e_mo_n = None
         else:
@@ -209,15 +215,92 @@ class ForceXL(torch.nn.Module):
         Eiso, eheat = _atom_sums(plan, const)
         Hf = Etot - Eiso + (eheat if self.Hf_flag else 0.0)
         molecule.w = w
-        return dict(force=force, D=D, Hf=Hf, Etot=Etot, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo_n=e_mo_n, q=q, dipole=dip)
+        return dict(force=force, D=D, Hf=Hf, Etot=Etot, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo_n=e_mo_n, q=q, dipole=dip,
+                    **extra)  # fmt: skip
+
+    KB = 8.61739e-5  # eV/K (xlbomd.py:207)
+    CANON_DM_PRT_ITER = 10  # xlbomd.py:55
+
+    def fermi_density(self, plan, F, T_el, C0=None):
+        """Fermi_Q (fermi_q.py:8-72) on packed matrices -> e (nmol, nmax), Q (packed eigenvectors), occupations f (nmol, nmax),
+        mu (nmol,), D0 = 2 Q f Q^t (packed), entropy S (nmol,)."""
+        beta = 1.0 / (self.KB * T_el)
+        e, _, Q = engine.op_eig_density(plan, F, want_P=False, want_C=True, Cguess=C0, want_e=True)
+        nocc = plan.nocc
+        mask = (torch.arange(plan.nmax, device=plan.device).unsqueeze(0) < plan.norb.unsqueeze(1)).to(torch.float64)
+        mu = 0.5 * (e.gather(1, nocc.unsqueeze(1) - 1) + e.gather(1, nocc.unsqueeze(1)))
+        nocc_f = nocc.to(torch.float64)
+        f = None
+        for _ in range(64):  # Newton iteration for the chemical potential, stop test over the whole batch (fermi_q.py:47-58)
+            f = torch.sigmoid(-beta * (e - mu)) * mask
+            occ = f.sum(dim=1)
+            docc = (beta * f * (1.0 - f)).sum(dim=1).clamp_min(1e-30)
+            if bool(((nocc_f - occ).abs() <= 1e-9).all()):
+                break
+            mu = mu + ((nocc_f - occ) / docc).unsqueeze(1)
+        D = engine.op_packed_gemm(plan, engine.op_scale_columns(plan, Q, f, 2.0), Q, tb=True)  # 2 (Q f) Q^t
+        ok = (f > 1e-14) & ((1.0 - f) > 1e-14)
+        p = f.masked_fill(~ok, 0.5)
+        S = ((-self.KB * (p * torch.log(p) + (1.0 - p) * torch.log(1.0 - p))) * ok.to(torch.float64)).sum(dim=1)
+        return e, Q, f, mu.reshape(-1).contiguous(), D, S
+
+    def density_response(self, plan, FO1, Q, e, mu, beta):
+        """Canon_DM_PRT (canon_dm_prt.py:6-39) on packed matrices: first-order response of the finite-temperature density to
+        the Fock perturbation FO1."""
+        X = engine.op_packed_gemm(plan, Q, engine.op_packed_gemm(plan, FO1, Q), ta=True)  # Q^t FO1 Q
+        engine.op_canon_prt(plan, e, mu, X, beta, self.CANON_DM_PRT_ITER)
+        return engine.op_packed_gemm(plan, engine.op_packed_gemm(plan, Q, X), Q, tb=True)  # Q X Q^t
+
+    def _ksa_density(self, molecule, plan, F, Pp, w, xl):
+        """Krylov branch of EnergyXL.forward (xlbomd.py:201-341): finite-temperature density D from the eigenpairs of F(P)
+        (Fermi_Q, fermi_q.py:8-72), then the rank-m Krylov approximation of the kernel acting on D - P
+        (JCTC 16, 3628 (2020), Alg. 3) with the response of every Krylov vector from canonical density-matrix perturbation
+        theory (Canon_DM_PRT, canon_dm_prt.py:6-39).  Everything stays in the packed layout; the matrix work runs in
+        seqm_ksa.cu / the Fock and eigensolver kernels, the (nmol, nmax) chemical-potential Newton iteration and the
+        rank x rank solves are a few tiny torch calls."""
+        T_el, rank, thr = float(xl["T_el"]), int(xl["max_rank"]), float(xl["err_threshold"])
+        beta = 1.0 / (self.KB * T_el)
+        tag, C0 = molecule.__dict__.get("_C_xl", (None, None))
+        if tag is not plan or C0 is None or C0.numel() != plan.mat_total:
+            C0 = None
+        e, Q, f, mu1, D, S = self.fermi_density(plan, F, T_el, C0)
+        molecule.__dict__["_C_xl"] = (plan, Q)
+        # ---- rank-m kernel approximation
+        dDS = D - Pp
+        nrm = engine.op_packed_dot(plan, dDS, dDS).sqrt()
+        H0 = plan.new_mat()
+        V, W = [], []
+        dW = dDS
+        err = torch.full((plan.nmol,), 10.0, dtype=torch.float64, device=plan.device)
+        alpha = None
+        while len(V) < rank and float(err.max()) > thr:
+            v = dW.clone()
+            for vj in V:  # Arnoldi orthogonalisation
+                engine.op_packed_axpby(plan, -engine.op_packed_dot(plan, v, vj), vj, None, v)
+            engine.op_packed_axpby(plan, None, None, engine.op_packed_dot(plan, v, v).rsqrt(), v)
+            V.append(v)
+            FO1 = engine.op_fock(plan, v, H0, w)  # G(dD): the Fock build without the one-electron part (G_XL_LR.py:7)
+            W.append(self.density_response(plan, FO1, Q, e, mu1, beta) - v)
+            dW = W[-1]
+            r = len(W)
+            O = torch.stack([torch.stack([engine.op_packed_dot(plan, W[a], W[b]) for b in range(r)], dim=1) for a in range(r)], dim=1)
+            rhs = torch.stack([engine.op_packed_dot(plan, W[a], dDS) for a in range(r)], dim=1)
+            alpha = torch.linalg.solve(O, rhs.unsqueeze(-1)).squeeze(-1)
+            ident = -dDS
+            for a in range(r):
+                engine.op_packed_axpby(plan, alpha[:, a], W[a], None, ident)
+            err = engine.op_packed_dot(plan, ident, ident).sqrt() / nrm
+        d2 = plan.new_mat()
+        for a in range(len(V)):
+            engine.op_packed_axpby(plan, -alpha[:, a], V[a], None, d2)
+        return e, D, dict(EEnt=-2.0 * T_el * S, dP2dt2=d2, Krylov_Error=err, Fermi_occ=f)
 
     def forward(self, molecule, P, cis_amp=None, learned_parameters=dict(), xl_bomd_params=dict(), *args, **kwargs):
-        if xl_bomd_params and "max_rank" in xl_bomd_params:
-            raise NotImplementedError("KSA-XL-BOMD (max_rank) is not part of the B200 path")
         if molecule.orbital_stride != 4:
             raise NotImplementedError("XL-BOMD with method='PM6' is not on the B200 path; use 'PM6_SP' for sp-only elements")
         plan = molecule._plan
-        r = self.forward_packed(molecule, engine.op_pack(plan, P), learned_parameters=learned_parameters)
+        r = self.forward_packed(molecule, engine.op_pack(plan, P), learned_parameters=learned_parameters,
+                                xl_bomd_params=xl_bomd_params)
         Dd = engine.op_unpack(plan, r["D"])
         molecule.dipole = r["dipole"]
         molecule.__dict__["_q_post"] = r["q"]
@@ -229,6 +312,9 @@ class ForceXL(torch.nn.Module):
             e_gap = (e.gather(1, lumo) - e.gather(1, lumo - 1)).reshape(-1)
         else:
             e, e_gap = None, torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
+        if "dP2dt2" in r:  # KSA: entropy term, kernel-propagated second derivative, Krylov residual, occupations
+            return (r["force"], Dd, r["Hf"], r["Etot"], r["Eelec"], r["Enuc"], r["Eiso"], e, e_gap, r["EEnt"],
+                    engine.op_unpack(plan, r["dP2dt2"]), r["Krylov_Error"], r["Fermi_occ"])  # fmt: skip
         EEnt = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
         return (r["force"], Dd, r["Hf"], r["Etot"], r["Eelec"], r["Enuc"], r["Eiso"], e, e_gap, EEnt, None, None, None)
 

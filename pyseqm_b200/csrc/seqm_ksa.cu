@@ -1,0 +1,190 @@
+// seqm_ksa.cu -- translation unit of libseqm_b200.so for KSA-XL-BOMD: dense per-molecule algebra on
+// the packed layout around the Fock-contraction and eigensolver kernels of the SCF path.
+//   packed_gemm_kernel        C_m = op(A_m) op(B_m) for every molecule (congruence transforms Q^t F1 Q, Q X Q^t; D = Q f Q^t)
+//   scale_columns_kernel      out_m[i][k] = s * f[m][k] * C_m[i][k]          (Fermi_Q: D0 = 2 (Q f) Q^t, fermi_q.py:59-61)
+//   canon_prt_kernel          recursive Fermi-operator expansion of the first-order density response in the eigenbasis and the
+//                             chemical-potential correction (Canon_DM_PRT, canon_dm_prt.py:17-34; Alg. 2 of JCTC 16, 3628)
+//   packed_dot / axpy / scale per-molecule Frobenius products and updates of the Krylov vectors (xlbomd.py:253-333)
+#define SEQM_SECONDARY_TU
+#include "common.cuh"
+
+#define KSA_TM 64
+#define KSA_TK 16
+// one CTA per molecule; 64x64 output tiles, 4x4 outputs per work item, operands staged through shared memory
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) packed_gemm_kernel(seqm_batch_t b, const double* __restrict__ A,
+                                                            const double* __restrict__ B, double* __restrict__ C, int ta, int tb) {
+  __shared__ double sA[KSA_TK][KSA_TM + 1];  // [k][i]
+  __shared__ double sB[KSA_TK][KSA_TM + 1];  // [k][j]
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n, tid = threadIdx.x, nthr = blockDim.x;
+  const double* Am = A + v.mat0;
+  const double* Bm = B + v.mat0;
+  double* Cm = C + v.mat0;
+  for (int i0 = 0; i0 < n; i0 += KSA_TM)
+    for (int j0 = 0; j0 < n; j0 += KSA_TM) {
+#ifndef SEQM_HOSTEMU
+      double acc[4][4];
+      const int oi = (tid >> 4) * 4, oj = (tid & 15) * 4;
+      for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
+      for (int k0 = 0; k0 < n; k0 += KSA_TK) {
+        for (int t = tid; t < KSA_TK * KSA_TM; t += nthr) {
+          const int kk = t / KSA_TM, ii = t % KSA_TM;
+          const int gi = i0 + ii, gk = k0 + kk, gj = j0 + ii;
+          sA[kk][ii] = (gi < n && gk < n) ? (ta ? Am[gk * n + gi] : Am[gi * n + gk]) : 0.0;
+          sB[kk][ii] = (gj < n && gk < n) ? (tb ? Bm[gj * n + gk] : Bm[gk * n + gj]) : 0.0;
+        }
+        SEQM_SYNC();
+        for (int kk = 0; kk < KSA_TK; ++kk) {
+          double a[4], c[4];
+          for (int x = 0; x < 4; ++x) a[x] = sA[kk][oi + x];
+          for (int y = 0; y < 4; ++y) c[y] = sB[kk][oj + y];
+          for (int x = 0; x < 4; ++x)
+            for (int y = 0; y < 4; ++y) acc[x][y] += a[x] * c[y];
+        }
+        SEQM_SYNC();
+      }
+      for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y)
+          if (i0 + oi + x < n && j0 + oj + y < n) Cm[(i0 + oi + x) * n + j0 + oj + y] = acc[x][y];
+#else  // host emulation (one thread per CTA): plain loops over the tile
+      (void)sA;
+      (void)sB;
+      (void)tid;
+      (void)nthr;
+      for (int gi = i0; gi < i0 + KSA_TM && gi < n; ++gi)
+        for (int gj = j0; gj < j0 + KSA_TM && gj < n; ++gj) {
+          double s = 0.0;
+          for (int k = 0; k < n; ++k) s += (ta ? Am[k * n + gi] : Am[gi * n + k]) * (tb ? Bm[gj * n + k] : Bm[k * n + gj]);
+          Cm[gi * n + gj] = s;
+        }
+#endif
+    }
+}
+
+SEQM_GLOBAL void scale_columns_kernel(seqm_batch_t b, const double* __restrict__ C, const double* __restrict__ f, double s,
+                                      double* __restrict__ out) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n;
+  const double* fm = f + (long long)v.m * b.nmax;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) out[v.mat0 + t] = s * fm[t % n] * C[v.mat0 + t];
+}
+
+// X: first-order perturbation in the eigenbasis of the unperturbed Fock matrix (packed, in place); e (nmol, nmax), mu (nmol)
+SEQM_GLOBAL void canon_prt_kernel(seqm_batch_t b, const double* __restrict__ e, const double* __restrict__ mu,
+                                  double* __restrict__ X, double beta, int m_iter) {
+  __shared__ double red[33];
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n;
+  const double* em = e + (long long)v.m * b.nmax;
+  const double mu0 = mu[v.m];
+  double* Xm = X + v.mat0;
+  const double cnst = exp2((double)(-2 - m_iter)) * beta;
+  double tr = 0.0;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+    const int i = t / n, j = t - i * n;
+    double pi = 0.5 - cnst * (em[i] - mu0), pj = 0.5 - cnst * (em[j] - mu0);
+    double x = -cnst * Xm[t];
+    for (int it = 0; it < m_iter; ++it) {
+      const double pi2 = pi * pi, pj2 = pj * pj;
+      const double dx = pi * x + x * pj;
+      const double idi = 1.0 / (2.0 * (pi2 - pi) + 1.0), idj = 1.0 / (2.0 * (pj2 - pj) + 1.0);
+      pi = idi * pi2;
+      pj = idj * pj2;
+      x = idi * (dx + 2.0 * (x - dx) * pj);
+    }
+    Xm[t] = x;
+    if (i == j) tr += x;
+  }
+  double dsum = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double p = 0.5 - cnst * (em[i] - mu0);
+    for (int it = 0; it < m_iter; ++it) {
+      const double p2 = p * p;
+      p = p2 / (2.0 * (p2 - p) + 1.0);
+    }
+    dsum += beta * p * (1.0 - p);
+  }
+  tr = block_sum(tr, red);
+  dsum = block_sum(dsum, red);
+  const double dmu1 = -tr / dsum;
+  SEQM_SYNC();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double p = 0.5 - cnst * (em[i] - mu0);
+    for (int it = 0; it < m_iter; ++it) {
+      const double p2 = p * p;
+      p = p2 / (2.0 * (p2 - p) + 1.0);
+    }
+    Xm[i * n + i] += beta * p * (1.0 - p) * dmu1;
+  }
+}
+
+SEQM_GLOBAL void packed_dot_kernel(seqm_batch_t b, const double* __restrict__ X, const double* __restrict__ Y,
+                                   double* __restrict__ out) {
+  __shared__ double red[33];
+  const MolView v = mol_view(b, blockIdx.x);
+  double s = 0.0;
+  for (int t = threadIdx.x; t < v.n * v.n; t += blockDim.x) s += X[v.mat0 + t] * Y[v.mat0 + t];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[v.m] = s;
+}
+// Y_m = a_m X_m + c_m Y_m   (a == NULL: a_m = 1; c == NULL: c_m = 1; X == NULL: Y_m = c_m Y_m)
+SEQM_GLOBAL void packed_axpby_kernel(seqm_batch_t b, const double* __restrict__ a, const double* __restrict__ X,
+                                     const double* __restrict__ c, double* __restrict__ Y) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const double am = a ? a[v.m] : 1.0, cm = c ? c[v.m] : 1.0;
+  for (int t = threadIdx.x; t < v.n * v.n; t += blockDim.x)
+    Y[v.mat0 + t] = (X ? am * X[v.mat0 + t] : 0.0) + cm * Y[v.mat0 + t];
+}
+
+static int ksa_check(const seqm_batch_t* b, const void* p, const void* q, const char* what) {
+  if (!b || !p || !q) {
+    seqm_set_error("%s: null pointer", what);
+    return SEQM_ERR_ARG;
+  }
+  return SEQM_OK;
+}
+#ifndef SEQM_HOSTEMU
+#define KSA_STREAM(s) ((cudaStream_t)(s))
+#else
+#define KSA_STREAM(s) (s)
+#endif
+
+extern "C" {
+int seqm_packed_gemm(const seqm_batch_t* b, const double* A, const double* B, double* C, int transA, int transB, void* stream) {
+  int rc = ksa_check(b, A, B, "seqm_packed_gemm");
+  if (rc) return rc;
+  if (!C || C == A || C == B) {
+    seqm_set_error("seqm_packed_gemm: the result must be a distinct buffer");
+    return SEQM_ERR_ARG;
+  }
+  SEQM_LAUNCH(packed_gemm_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, A, B, C, transA, transB);
+  return seqm_check_launch("packed_gemm_kernel");
+}
+int seqm_scale_columns(const seqm_batch_t* b, const double* C, const double* f, double s, double* out, void* stream) {
+  int rc = ksa_check(b, C, f, "seqm_scale_columns");
+  if (rc) return rc;
+  SEQM_LAUNCH(scale_columns_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, C, f, s, out);
+  return seqm_check_launch("scale_columns_kernel");
+}
+int seqm_canon_prt(const seqm_batch_t* b, const double* e, const double* mu, double* X, double beta, int m_iter, void* stream) {
+  int rc = ksa_check(b, e, mu, "seqm_canon_prt");
+  if (rc) return rc;
+  SEQM_LAUNCH(canon_prt_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, e, mu, X, beta, m_iter);
+  return seqm_check_launch("canon_prt_kernel");
+}
+int seqm_packed_dot(const seqm_batch_t* b, const double* X, const double* Y, double* out, void* stream) {
+  int rc = ksa_check(b, X, Y, "seqm_packed_dot");
+  if (rc) return rc;
+  SEQM_LAUNCH(packed_dot_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, X, Y, out);
+  return seqm_check_launch("packed_dot_kernel");
+}
+int seqm_packed_axpby(const seqm_batch_t* b, const double* a, const double* X, const double* c, double* Y, void* stream) {
+  if (!b || !Y) {
+    seqm_set_error("seqm_packed_axpby: null pointer");
+    return SEQM_ERR_ARG;
+  }
+  SEQM_LAUNCH(packed_axpby_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, a, X, c, Y);
+  return seqm_check_launch("packed_axpby_kernel");
+}
+}

@@ -477,6 +477,42 @@ def op_post_scf(plan, P, xyz, g=None, want_dipole=True):
     return q, dip, force
 
 
+# ---- KSA-XL-BOMD building blocks (seqm_ksa.cu) --------------------------------------------------------------------------
+def op_packed_gemm(plan, A, B, ta=False, tb=False):
+    out = plan.new_mat()
+    plan.lib.check(plan.lib.dll.seqm_packed_gemm(plan.ref, ptr(A), ptr(B), ptr(out), int(ta), int(tb), stream_of(out)),
+                   "seqm_packed_gemm")  # fmt: skip
+    return out
+
+
+def op_scale_columns(plan, Cm, f, s):
+    out = plan.new_mat()
+    f = f.contiguous()
+    plan.lib.check(plan.lib.dll.seqm_scale_columns(plan.ref, ptr(Cm), ptr(f), float(s), ptr(out), stream_of(out)), "seqm_scale_columns")
+    return out
+
+
+def op_canon_prt(plan, e, mu, X, beta, m_iter):
+    """in place on X (packed, eigenbasis)"""
+    e, mu = e.contiguous(), mu.contiguous()
+    plan.lib.check(plan.lib.dll.seqm_canon_prt(plan.ref, ptr(e), ptr(mu), ptr(X), float(beta), int(m_iter), stream_of(X)), "seqm_canon_prt")
+    return X
+
+
+def op_packed_dot(plan, X, Y):
+    out = torch.empty((plan.nmol,), dtype=torch.float64, device=plan.device)
+    plan.lib.check(plan.lib.dll.seqm_packed_dot(plan.ref, ptr(X), ptr(Y), ptr(out), stream_of(out)), "seqm_packed_dot")
+    return out
+
+
+def op_packed_axpby(plan, a, X, c, Y):
+    """Y_m = a[m] X_m + c[m] Y_m in place (a / c None: 1; X None: pure scaling)"""
+    a = None if a is None else a.contiguous()
+    c = None if c is None else c.contiguous()
+    plan.lib.check(plan.lib.dll.seqm_packed_axpby(plan.ref, ptr(a), ptr(X), ptr(c), ptr(Y), stream_of(Y)), "seqm_packed_axpby")
+    return Y
+
+
 def op_mo_match(plan, V_new, V_old, e):
     """Energy._crossing_match_molecular_orbitals[_grouped] (basics.py:596-719): V (nmol, nmax, nmax), e (nmol, nmax)."""
     V_new, V_old, e = V_new.contiguous(), V_old.contiguous(), e.contiguous()
