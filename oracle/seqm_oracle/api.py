@@ -73,7 +73,12 @@ def single_point(species, coordinates, seqm_parameters, P0=None, do_force=True, 
     hc = build_hcore(P, par, mp)
     H, w = hc["H"], hc["w"]
     D0 = initial_density(P) if P0 is None else np.asarray(P0, dtype=np.float64)
-    D, notconv, n_iter = run_scf(P, par, H, w, D0, eps, conv, sp2)
+    if conv[0] == 3:  # scf_forward3 (scf_loop.py:1135-1381): SCF by Krylov-subspace-approximated Newton steps
+        from .ksa import scf_ksa
+
+        D, notconv, n_iter = scf_ksa(P, par, H, w, D0, eps, conv[1])
+    else:
+        D, notconv, n_iter = run_scf(P, par, H, w, D0, eps, conv, sp2)
     F = build_fock(P, par, H, w, D)
     _, e_mo, V = density_from_fock(F, P.nHeavy, P.nHydro, P.nocc, want_eig=True)
     Eelec = elec_energy(D, F, H)

@@ -79,7 +79,35 @@ def canon_dm_prt(FO1, T_el, eig, mu, m_iter=CANON_DM_PRT_ITER):
     return P1
 
 
-def krylov_kernel(P, par, w, D, field, eig, mu, T_el, max_rank, err_threshold):
+def scf_ksa(P, par, H, w, D0, eps, xl, max_iter=1000):
+    """scf_forward3 (scf_loop.py:1135-1381): field <- field - sum_k alpha_k V_k per iteration, stop on |dEelec| <= eps per
+    molecule; CANON_DM_PRT_ITER = 8 in this file of the reference (scf_loop.py:47).  Converged molecules keep their field (and
+    therefore their Fock matrix and Fermi data), which is what the reference's refresh of the unconverged subset amounts to.
+    -> field density, notconverged, iterations"""
+    from .energy import elec_energy
+
+    T_el = xl["T_el"]
+    field = np.array(D0, dtype=np.float64)
+    nmol = field.shape[0]
+    F = build_fock(P, par, H, w, field)
+    Eelec = np.zeros(nmol)
+    err = np.ones(nmol)
+    notconv = np.ones(nmol, dtype=bool)
+    n_iter = 0
+    while notconv.any() and n_iter < max_iter:
+        n_iter += 1
+        D, S, eig, f, mu = fermi_q(F, T_el, P.nocc, P.nHeavy, P.nHydro)
+        d2, _ = krylov_kernel(P, par, w, D, field, eig, mu, T_el, xl["max_rank"], xl["err_threshold"], m_iter=8)
+        field[notconv] += d2[notconv]  # d2 = -sum_k alpha_k V_k
+        F = build_fock(P, par, H, w, field)
+        Enew = elec_energy(field, F, H)
+        err[notconv] = np.abs(Enew - Eelec)[notconv]
+        Eelec[notconv] = Enew[notconv]
+        notconv = err > eps
+    return field, notconv, n_iter
+
+
+def krylov_kernel(P, par, w, D, field, eig, mu, T_el, max_rank, err_threshold, m_iter=CANON_DM_PRT_ITER):
     """Rank-m approximation of the kernel acting on the residual D - field (xlbomd.py:238-341) -> dP2dt2, Error."""
     fro = lambda A: np.sqrt(np.sum(A * A, axis=(1, 2)))  # noqa: E731
     dDS = D - field
@@ -96,7 +124,7 @@ def krylov_kernel(P, par, w, D, field, eig, mu, T_el, max_rank, err_threshold):
         v = v / fro(v)[:, None, None]
         V.append(v)
         FO1 = build_fock(P, par, H0, w, v)  # G(dD): the Fock build without Hcore (G_XL_LR.py:7)
-        PO1 = canon_dm_prt(FO1, T_el, eig, mu)
+        PO1 = canon_dm_prt(FO1, T_el, eig, mu, m_iter)
         W.append(PO1 - v)
         dW = W[-1]
         r = len(W)

@@ -59,8 +59,10 @@ def reject_unsupported(seqm_parameters):
     if sp.get("normal modes", False):
         bad.append("normal modes")
     conv = sp.get("scf_converger", [2])
-    if conv[0] not in (0, 1, 2):
+    if conv[0] not in (0, 1, 2, 3):
         bad.append(f"scf_converger={conv}")
+    if conv[0] == 3 and not (len(conv) > 1 and isinstance(conv[1], dict) and {"max_rank", "err_threshold", "T_el"} <= set(conv[1])):
+        bad.append("scf_converger=[3] without its {'max_rank', 'err_threshold', 'T_el'} dictionary")
     if bad:
         raise NotImplementedError("not implemented by the B200 SCF path: " + ", ".join(bad))
 

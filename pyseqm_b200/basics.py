@@ -77,13 +77,20 @@ class Energy(torch.nn.Module):
         C0 = molecule.__dict__.get("_C_last") if (P0 is not None and self.warm_start) else None
         if C0 is not None and C0.numel() != plan.mat_total:
             C0 = None
-        F, Eelec, notconv, n_iter, Clast = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
-                                                         warm_start=self.warm_start, want_C=True, C0=C0,
-                                                         max_iter=self.max_iter)  # fmt: skip
+        if self.scf_converger[0] == 3:  # KSA (scf_forward3): scf_converger = [3, {"max_rank", "err_threshold", "T_el"}]
+            if plan.d_mode or self.sp2[0] or (plan.large and not plan.eig_ok):
+                raise NotImplementedError("scf_converger=[3] (KSA) runs on the eigensolver route of the sp methods (<= 256 orbitals)")
+            F, Eelec, notconv, n_iter = KsaOps().scf_ksa(plan, H, w, P, self.eps, self.scf_converger[1], self.max_iter)
+            Clast = None
+        else:
+            F, Eelec, notconv, n_iter, Clast = engine.op_scf(plan, H, w, P, self.eps, self.scf_converger, self.sp2,
+                                                             warm_start=self.warm_start, want_C=True, C0=C0,
+                                                             max_iter=self.max_iter)  # fmt: skip
         molecule.__dict__["_C_last"] = Clast
         molecule.n_scf_iter = n_iter
         if molecule.verbose:
-            tag = {0: "scf direct step  ", 1: "scf adaptive step    ", 2: "scf pulay diis   "}[self.scf_converger[0]]
+            tag = {0: "scf direct step  ", 1: "scf adaptive step    ", 2: "scf pulay diis   ",
+                   3: "scf KSA step     "}[self.scf_converger[0]]  # fmt: skip
             print(f"{tag}: {n_iter:>3d} | N not converged: {int(notconv.sum())}")
         if bool(notconv.any()):
             nnot = int(notconv.sum())
@@ -158,7 +165,102 @@ class Energy(torch.nn.Module):
         return Eelec, EnucAB, Pd, notconv
 
 
-class ForceXL(torch.nn.Module):
+class KsaOps:
+    """Building blocks of the Krylov-subspace-approximation paths (KSA-XL-BOMD, xlbomd.py:201-341; SCF by KSA,
+    scf_loop.py:1135-1381) on packed device buffers."""
+
+    KB = 8.61739e-5  # eV/K (xlbomd.py:207)
+    CANON_DM_PRT_ITER = 10  # xlbomd.py:55
+
+    def fermi_density(self, plan, F, T_el, C0=None):
+        """Fermi_Q (fermi_q.py:8-72) on packed matrices -> e (nmol, nmax), Q (packed eigenvectors), occupations f (nmol, nmax),
+        mu (nmol,), D0 = 2 Q f Q^t (packed), entropy S (nmol,)."""
+        beta = 1.0 / (self.KB * T_el)
+        e, _, Q = engine.op_eig_density(plan, F, want_P=False, want_C=True, Cguess=C0, want_e=True)
+        nocc = plan.nocc
+        mask = (torch.arange(plan.nmax, device=plan.device).unsqueeze(0) < plan.norb.unsqueeze(1)).to(torch.float64)
+        mu = 0.5 * (e.gather(1, nocc.unsqueeze(1) - 1) + e.gather(1, nocc.unsqueeze(1)))
+        nocc_f = nocc.to(torch.float64)
+        f = None
+        for _ in range(64):  # Newton iteration for the chemical potential, stop test over the whole batch (fermi_q.py:47-58)
+            f = torch.sigmoid(-beta * (e - mu)) * mask
+            occ = f.sum(dim=1)
+            docc = (beta * f * (1.0 - f)).sum(dim=1).clamp_min(1e-30)
+            if bool(((nocc_f - occ).abs() <= 1e-9).all()):
+                break
+            mu = mu + ((nocc_f - occ) / docc).unsqueeze(1)
+        D = engine.op_packed_gemm(plan, engine.op_scale_columns(plan, Q, f, 2.0), Q, tb=True)  # 2 (Q f) Q^t
+        ok = (f > 1e-14) & ((1.0 - f) > 1e-14)
+        p = f.masked_fill(~ok, 0.5)
+        S = ((-self.KB * (p * torch.log(p) + (1.0 - p) * torch.log(1.0 - p))) * ok.to(torch.float64)).sum(dim=1)
+        return e, Q, f, mu.reshape(-1).contiguous(), D, S
+
+    def density_response(self, plan, FO1, Q, e, mu, beta, m_iter=None):
+        """Canon_DM_PRT (canon_dm_prt.py:6-39) on packed matrices: first-order response of the finite-temperature density to
+        the Fock perturbation FO1."""
+        X = engine.op_packed_gemm(plan, Q, engine.op_packed_gemm(plan, FO1, Q), ta=True)  # Q^t FO1 Q
+        engine.op_canon_prt(plan, e, mu, X, beta, m_iter or self.CANON_DM_PRT_ITER)
+        return engine.op_packed_gemm(plan, engine.op_packed_gemm(plan, Q, X), Q, tb=True)  # Q X Q^t
+
+    def krylov_kernel(self, plan, w, dDS, Q, e, mu, beta, rank, thr, m_iter=None):
+        """Rank-m Krylov approximation of the kernel acting on the residual dDS = D - P (xlbomd.py:238-341, Alg. 3 of JCTC 16,
+        3628): Arnoldi vectors V_k, their responses W_k = PO1(V_k) - V_k, least-squares coefficients alpha (nmol, r) with
+        sum_k alpha_k W_k ~ dDS, relative residual err (nmol,).  The kernel applied to dDS is -sum_k alpha_k V_k."""
+        nrm = engine.op_packed_dot(plan, dDS, dDS).sqrt()
+        H0 = plan.new_mat()
+        V, W = [], []
+        dW = dDS
+        err = torch.full((plan.nmol,), 10.0, dtype=torch.float64, device=plan.device)
+        alpha = None
+        while len(V) < rank and float(err.max()) > thr:
+            v = dW.clone()
+            for vj in V:  # Arnoldi orthogonalisation
+                engine.op_packed_axpby(plan, -engine.op_packed_dot(plan, v, vj), vj, None, v)
+            engine.op_packed_axpby(plan, None, None, engine.op_packed_dot(plan, v, v).rsqrt(), v)
+            V.append(v)
+            FO1 = engine.op_fock(plan, v, H0, w)  # G(dD): the Fock build without the one-electron part (G_XL_LR.py:7)
+            W.append(self.density_response(plan, FO1, Q, e, mu, beta, m_iter) - v)
+            dW = W[-1]
+            r = len(W)
+            O = torch.stack([torch.stack([engine.op_packed_dot(plan, W[a], W[b]) for b in range(r)], dim=1) for a in range(r)], dim=1)
+            rhs = torch.stack([engine.op_packed_dot(plan, W[a], dDS) for a in range(r)], dim=1)
+            alpha = torch.linalg.solve(O, rhs.unsqueeze(-1)).squeeze(-1)
+            ident = -dDS
+            for a in range(r):
+                engine.op_packed_axpby(plan, alpha[:, a], W[a], None, ident)
+            err = engine.op_packed_dot(plan, ident, ident).sqrt() / nrm
+        return alpha, V, err
+
+    def scf_ksa(self, plan, H, w, P, eps, xl, max_iter=1000):
+        """scf_forward3 (scf_loop.py:1135-1381): SCF by Krylov-subspace-approximated Newton steps on the field density at
+        electronic temperature T_el, P <- P - sum_k alpha_k V_k, until |dEelec| <= eps per molecule (the only criterion).
+        Every molecule is carried through every iteration (the update is masked): for a converged molecule P, hence F and its
+        Fermi data, no longer change, which is what the reference's subset refresh amounts to.  CANON_DM_PRT_ITER = 8 here
+        (scf_loop.py:47).  -> F, Eelec, notconverged, n_iter"""
+        T_el, rank, thr = float(xl["T_el"]), int(xl["max_rank"]), float(xl["err_threshold"])
+        beta = 1.0 / (self.KB * T_el)
+        F = engine.op_fock(plan, P, H, w)
+        Eelec = torch.zeros(plan.nmol, dtype=torch.float64, device=plan.device)
+        err = torch.ones_like(Eelec)
+        notconv = torch.ones(plan.nmol, dtype=torch.bool, device=plan.device)
+        Q = None
+        n_iter = 0
+        while bool(notconv.any()) and n_iter < max_iter:
+            n_iter += 1
+            e, Q, f, mu, D, S = self.fermi_density(plan, F, T_el, Q)
+            alpha, V, _ = self.krylov_kernel(plan, w, D - P, Q, e, mu, beta, rank, thr, m_iter=8)
+            live = notconv.to(torch.float64)
+            for a in range(len(V)):
+                engine.op_packed_axpby(plan, -alpha[:, a] * live, V[a], None, P)
+            F = engine.op_fock(plan, P, H, w)
+            Enew = engine.op_elec_energy(plan, P, H, F)
+            err = torch.where(notconv, (Enew - Eelec).abs(), err)
+            Eelec = torch.where(notconv, Enew, Eelec)
+            notconv = err > eps
+        return F, Eelec, notconv, n_iter
+
+
+class ForceXL(torch.nn.Module, KsaOps):
     """XL-BOMD energy and force for a given field density P (seqm/dynamics/xlbomd.py:73-570, non-KSA branch):
     hcore -> F(P) -> D from F (Jacobi eigensolver, or SP2 when sp2=[True, eps]) -> shadow energy
     sum D o F - 1/2 (F - h) o P -> force at fixed D and P.  No SCF.
@@ -218,39 +320,6 @@ class ForceXL(torch.nn.Module):
         return dict(force=force, D=D, Hf=Hf, Etot=Etot, Eelec=Eelec, Enuc=Enuc, Eiso=Eiso, e_mo_n=e_mo_n, q=q, dipole=dip,
                     **extra)  # fmt: skip
 
-    KB = 8.61739e-5  # eV/K (xlbomd.py:207)
-    CANON_DM_PRT_ITER = 10  # xlbomd.py:55
-
-    def fermi_density(self, plan, F, T_el, C0=None):
-        """Fermi_Q (fermi_q.py:8-72) on packed matrices -> e (nmol, nmax), Q (packed eigenvectors), occupations f (nmol, nmax),
-        mu (nmol,), D0 = 2 Q f Q^t (packed), entropy S (nmol,)."""
-        beta = 1.0 / (self.KB * T_el)
-        e, _, Q = engine.op_eig_density(plan, F, want_P=False, want_C=True, Cguess=C0, want_e=True)
-        nocc = plan.nocc
-        mask = (torch.arange(plan.nmax, device=plan.device).unsqueeze(0) < plan.norb.unsqueeze(1)).to(torch.float64)
-        mu = 0.5 * (e.gather(1, nocc.unsqueeze(1) - 1) + e.gather(1, nocc.unsqueeze(1)))
-        nocc_f = nocc.to(torch.float64)
-        f = None
-        for _ in range(64):  # Newton iteration for the chemical potential, stop test over the whole batch (fermi_q.py:47-58)
-            f = torch.sigmoid(-beta * (e - mu)) * mask
-            occ = f.sum(dim=1)
-            docc = (beta * f * (1.0 - f)).sum(dim=1).clamp_min(1e-30)
-            if bool(((nocc_f - occ).abs() <= 1e-9).all()):
-                break
-            mu = mu + ((nocc_f - occ) / docc).unsqueeze(1)
-        D = engine.op_packed_gemm(plan, engine.op_scale_columns(plan, Q, f, 2.0), Q, tb=True)  # 2 (Q f) Q^t
-        ok = (f > 1e-14) & ((1.0 - f) > 1e-14)
-        p = f.masked_fill(~ok, 0.5)
-        S = ((-self.KB * (p * torch.log(p) + (1.0 - p) * torch.log(1.0 - p))) * ok.to(torch.float64)).sum(dim=1)
-        return e, Q, f, mu.reshape(-1).contiguous(), D, S
-
-    def density_response(self, plan, FO1, Q, e, mu, beta):
-        """Canon_DM_PRT (canon_dm_prt.py:6-39) on packed matrices: first-order response of the finite-temperature density to
-        the Fock perturbation FO1."""
-        X = engine.op_packed_gemm(plan, Q, engine.op_packed_gemm(plan, FO1, Q), ta=True)  # Q^t FO1 Q
-        engine.op_canon_prt(plan, e, mu, X, beta, self.CANON_DM_PRT_ITER)
-        return engine.op_packed_gemm(plan, engine.op_packed_gemm(plan, Q, X), Q, tb=True)  # Q X Q^t
-
     def _ksa_density(self, molecule, plan, F, Pp, w, xl):
         """Krylov branch of EnergyXL.forward (xlbomd.py:201-341): finite-temperature density D from the eigenpairs of F(P)
         (Fermi_Q, fermi_q.py:8-72), then the rank-m Krylov approximation of the kernel acting on D - P
@@ -265,31 +334,7 @@ class ForceXL(torch.nn.Module):
             C0 = None
         e, Q, f, mu1, D, S = self.fermi_density(plan, F, T_el, C0)
         molecule.__dict__["_C_xl"] = (plan, Q)
-        # ---- rank-m kernel approximation
-        dDS = D - Pp
-        nrm = engine.op_packed_dot(plan, dDS, dDS).sqrt()
-        H0 = plan.new_mat()
-        V, W = [], []
-        dW = dDS
-        err = torch.full((plan.nmol,), 10.0, dtype=torch.float64, device=plan.device)
-        alpha = None
-        while len(V) < rank and float(err.max()) > thr:
-            v = dW.clone()
-            for vj in V:  # Arnoldi orthogonalisation
-                engine.op_packed_axpby(plan, -engine.op_packed_dot(plan, v, vj), vj, None, v)
-            engine.op_packed_axpby(plan, None, None, engine.op_packed_dot(plan, v, v).rsqrt(), v)
-            V.append(v)
-            FO1 = engine.op_fock(plan, v, H0, w)  # G(dD): the Fock build without the one-electron part (G_XL_LR.py:7)
-            W.append(self.density_response(plan, FO1, Q, e, mu1, beta) - v)
-            dW = W[-1]
-            r = len(W)
-            O = torch.stack([torch.stack([engine.op_packed_dot(plan, W[a], W[b]) for b in range(r)], dim=1) for a in range(r)], dim=1)
-            rhs = torch.stack([engine.op_packed_dot(plan, W[a], dDS) for a in range(r)], dim=1)
-            alpha = torch.linalg.solve(O, rhs.unsqueeze(-1)).squeeze(-1)
-            ident = -dDS
-            for a in range(r):
-                engine.op_packed_axpby(plan, alpha[:, a], W[a], None, ident)
-            err = engine.op_packed_dot(plan, ident, ident).sqrt() / nrm
+        alpha, V, err = self.krylov_kernel(plan, w, D - Pp, Q, e, mu1, beta, rank, thr)
         d2 = plan.new_mat()
         for a in range(len(V)):
             engine.op_packed_axpby(plan, -alpha[:, a], V[a], None, d2)

@@ -292,3 +292,51 @@ def test_gpu_ksa_md(name):
     from helpers import cuda_lib
 
     run_ksa_product(cuda_lib(), torch.device("cuda:0"), load_ksa(name))
+
+
+KSA_SCF_CASES = ["ksa_scf_mixed", "ksa_scf_methanal"]
+
+
+def load_ksa_scf(name):
+    g = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    g["seqm_parameters"] = json.loads(str(g["seqm_parameters"]))
+    g["n_scf_iter"] = int(g["n_scf_iter"])
+    return g
+
+
+@pytest.mark.parametrize("name", KSA_SCF_CASES)
+def test_oracle_ksa_scf_matches_reference(name):
+    """scf_converger = [3, {...}] (scf_forward3, scf_loop.py:1135-1381): oracle against the reference single points."""
+    import seqm_oracle as so
+
+    g = load_ksa_scf(name)
+    r = so.single_point(g["species"], g["coordinates"], g["seqm_parameters"])
+    assert r["n_scf_iter"] == g["n_scf_iter"]
+    for k, tol in (("Etot", 1e-6), ("Eelec", 1e-6), ("Hf", 1e-6), ("dm", 1e-8), ("force", 1e-5), ("e_gap", 1e-6), ("q", 1e-8)):
+        assert np.abs(r[k] - g[k]).max() < tol, k
+
+
+def check_ksa_scf(lib, device, name):
+    from helpers import run_molecule
+
+    g = load_ksa_scf(name)
+    mol, es = run_molecule(lib, device, g["species"], g["coordinates"], g["seqm_parameters"])
+    assert mol.n_scf_iter == g["n_scf_iter"]
+    assert not bool(es.notconverged.any())
+    for k, tol in (("Etot", 1e-6), ("Eelec", 1e-6), ("Hf", 1e-6), ("dm", 1e-8), ("force", 1e-5), ("e_gap", 1e-6), ("q", 1e-8)):
+        assert np.abs(getattr(mol, k).cpu().numpy() - g[k]).max() < tol, k
+
+
+@pytest.mark.parametrize("name", KSA_SCF_CASES)
+def test_hostemu_ksa_scf(name):
+    from helpers import hostemu_lib
+
+    check_ksa_scf(hostemu_lib(), torch.device("cpu"), name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", KSA_SCF_CASES)
+def test_gpu_ksa_scf(name):
+    from helpers import cuda_lib
+
+    check_ksa_scf(cuda_lib(), torch.device("cuda:0"), name)

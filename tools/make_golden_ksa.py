@@ -102,7 +102,36 @@ def operators():
     print("ksa_operators: S", t(S), "S_hot", t(Sh), "mu", t(mu).ravel(), "|PO1|", float(PO1.abs().max()))
 
 
+def scf_ksa_cases():
+    """scf_converger = [3, {...}] (scf_forward3, scf_loop.py:1135-1381) single points; the iteration count is the number in the
+    reference's own verbose line "scf KSA step : N"."""
+    import re
+
+    from seqm.ElectronicStructure import Electronic_Structure
+
+    xl = {"max_rank": 3, "err_threshold": 0.0, "T_el": 1500}
+    for name, files in (("ksa_scf_mixed", ["methane.xyz", "benzene.xyz"]), ("ksa_scf_methanal", ["methanal.1.xyz", "methanal.2.xyz"])):
+        species, coords = read_xyz([os.path.join(XYZ, f) for f in files])
+        sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [3, dict(xl)]}
+        sp_in = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [3, dict(xl)]}  # the reference adds 'elements' to it
+        mol = Molecule(Constants(), sp_in, torch.as_tensor(coords), torch.as_tensor(species, dtype=torch.int64))
+        mol.verbose = True
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            Electronic_Structure(sp_in)(mol)
+        n_iter = int(re.findall(r"scf KSA step\s*:\s+(\d+) \|", buf.getvalue())[-1])
+        t = lambda x: x.detach().numpy()  # noqa: E731
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), species=np.asarray(species), coordinates=np.asarray(coords),
+                            seqm_parameters=json.dumps(sp), n_scf_iter=n_iter, Etot=t(mol.Etot), Eelec=t(mol.Eelec), Hf=t(mol.Hf),
+                            dm=t(mol.dm), force=t(mol.force), e_gap=t(mol.e_gap), q=t(mol.q))  # fmt: skip
+        print(name, "iterations", n_iter, "Etot", t(mol.Etot))
+
+
 if __name__ == "__main__":
+    if os.environ.get("GOLDEN_ONLY") == "scf":
+        scf_ksa_cases()
+        sys.exit(0)
+    scf_ksa_cases()
     operators()
     if os.environ.get("GOLDEN_ONLY") == "operators":
         sys.exit(0)
