@@ -246,6 +246,12 @@ int seqm_scale_columns(const seqm_batch_t* b, const double* C, const double* f, 
 int seqm_canon_prt(const seqm_batch_t* b, const double* e, const double* mu, double* X, double beta, int m_iter, void* stream);
 int seqm_packed_dot(const seqm_batch_t* b, const double* X, const double* Y, double* out, void* stream);
 int seqm_packed_axpby(const seqm_batch_t* b, const double* a, const double* X, const double* c, double* Y, void* stream);
+/* CIS sigma-vector, antisymmetric half (makeA_pi_batched, rcis_batch.py:336-381): Fa = response of the two-electron part of
+ * the Fock operator to the ANTISYMMETRIC density Pa (exchange only; Fa is antisymmetric).  The symmetric half is seqm_fock on
+ * the symmetric part of the transition density with Hcore = 0.  sp methods only. */
+int seqm_fock_antisym(const seqm_batch_t* b, const double* Pa, const double* w, double* Fa, void* stream);
+/* XT_m = X_m^t for every molecule of a packed buffer (out of place) */
+int seqm_packed_transpose(const seqm_batch_t* b, const double* X, double* XT, void* stream);
 
 /* MO crossing matcher -- Energy._crossing_match_molecular_orbitals / _grouped, seqm/basics.py:596-719 (called on every
  * forward after the first one on the same Molecule, basics.py:846-857): the new orbitals are permuted inside the

@@ -167,6 +167,8 @@ class SeqmLib:
             "seqm_canon_prt": ([B, P, P, P, C.c_double, C.c_int, P], C.c_int),
             "seqm_packed_dot": ([B, P, P, P, P], C.c_int),
             "seqm_packed_axpby": ([B, P, P, P, P, P], C.c_int),
+            "seqm_fock_antisym": ([B, P, P, P, P], C.c_int),
+            "seqm_packed_transpose": ([B, P, P, P], C.c_int),
             "seqm_jacobi_stats": ([C.POINTER(C.c_ulonglong), C.c_int], C.c_int),
             "seqm_profile_enable": ([C.c_int], C.c_int),
             "seqm_profile_kinds": ([], C.c_int),

@@ -137,6 +137,51 @@ SEQM_GLOBAL void packed_axpby_kernel(seqm_batch_t b, const double* __restrict__ 
     Y[v.mat0 + t] = (X ? am * X[v.mat0 + t] : 0.0) + cm * Y[v.mat0 + t];
 }
 
+// Response of the two-electron part of the Fock operator to an ANTISYMMETRIC density Pa (the part of a CIS transition density
+// the symmetric Fock build does not see; makeA_pi_batched, rcis_batch.py:336-381): only exchange survives,
+//   Fa_AB[mu][la] = -1/2 sum_{nu in A, sg in B} Pa[nu][sg] (mu nu | la sg),  Fa_BA = -Fa_AB^t,
+// plus the one-centre exchange terms (s,p): Pa (hsp - gsp)/2, (p,p'): Pa (gpp/4 - 3 gp2/4).  One CTA per molecule.
+SEQM_GLOBAL void fock_antisym_kernel(seqm_batch_t b, const double* __restrict__ Pa, const double* __restrict__ w,
+                                     double* __restrict__ Fa) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n;
+  const double* Pm = Pa + v.mat0;
+  double* Fm = Fa + v.mat0;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) Fm[t] = 0.0;
+  SEQM_SYNC();
+  for (int t = threadIdx.x; t < v.npair * 16; t += blockDim.x) {
+    const int pl = t >> 4, mu = (t >> 2) & 3, la = t & 3;
+    const int p = v.p0 + pl;
+    const int i = b.pair_i[p] - v.a0, j = b.pair_j[p] - v.a0;
+    const int ni = orb_cnt(v, i), nj = orb_cnt(v, j);
+    if (mu >= ni || la >= nj) continue;
+    const int oi = orb_off(v, i), oj = orb_off(v, j);
+    const double* wp = w + (long long)p * 100;
+    double k = 0.0;
+    for (int nu = 0; nu < ni; ++nu)
+      for (int sg = 0; sg < nj; ++sg) k += Pm[(oi + nu) * n + oj + sg] * wp[pack2(mu, nu) * 10 + pack2(la, sg)];
+    Fm[(oi + mu) * n + oj + la] = -0.5 * k;
+    Fm[(oj + la) * n + oi + mu] = 0.5 * k;
+  }
+  for (int t = threadIdx.x; t < v.nheavy * 6; t += blockDim.x) {
+    const int a = t / 6, e = t % 6;  // upper-triangle element of the 4 x 4 block: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    const int mu = (e < 3) ? 0 : ((e < 5) ? 1 : 2);
+    const int nu = (e < 3) ? e + 1 : ((e < 5) ? e - 1 : 3);
+    const int oa = orb_off(v, a), ga = v.a0 + a;
+    const double c = (mu == 0) ? 0.5 * (par(b, SEQM_P_HSP, ga) - par(b, SEQM_P_GSP, ga))
+                               : 0.25 * par(b, SEQM_P_GPP, ga) - 0.75 * par(b, SEQM_P_GP2, ga);
+    const double f = Pm[(oa + mu) * n + oa + nu] * c;
+    Fm[(oa + mu) * n + oa + nu] = f;
+    Fm[(oa + nu) * n + oa + mu] = -f;
+  }
+}
+
+SEQM_GLOBAL void packed_transpose_kernel(seqm_batch_t b, const double* __restrict__ X, double* __restrict__ XT) {
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n;
+  for (int t = threadIdx.x; t < n * n; t += blockDim.x) XT[v.mat0 + t] = X[v.mat0 + (t % n) * n + t / n];
+}
+
 static int ksa_check(const seqm_batch_t* b, const void* p, const void* q, const char* what) {
   if (!b || !p || !q) {
     seqm_set_error("%s: null pointer", what);
@@ -178,6 +223,30 @@ int seqm_packed_dot(const seqm_batch_t* b, const double* X, const double* Y, dou
   if (rc) return rc;
   SEQM_LAUNCH(packed_dot_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, X, Y, out);
   return seqm_check_launch("packed_dot_kernel");
+}
+int seqm_packed_transpose(const seqm_batch_t* b, const double* X, double* XT, void* stream) {
+  int rc = ksa_check(b, X, XT, "seqm_packed_transpose");
+  if (rc) return rc;
+  if (X == XT) {
+    seqm_set_error("seqm_packed_transpose: out of place only");
+    return SEQM_ERR_ARG;
+  }
+  SEQM_LAUNCH(packed_transpose_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, X, XT);
+  return seqm_check_launch("packed_transpose_kernel");
+}
+int seqm_fock_antisym(const seqm_batch_t* b, const double* Pa, const double* w, double* Fa, void* stream) {
+  int rc = ksa_check(b, Pa, Fa, "seqm_fock_antisym");
+  if (rc) return rc;
+  if (b->method == SEQM_PM6_D) {
+    seqm_set_error("seqm_fock_antisym: sp methods only");
+    return SEQM_ERR_UNSUPPORTED;
+  }
+  if (b->npairs > 0 && !w) {
+    seqm_set_error("seqm_fock_antisym: w is NULL");
+    return SEQM_ERR_ARG;
+  }
+  SEQM_LAUNCH(fock_antisym_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, Pa, w, Fa);
+  return seqm_check_launch("fock_antisym_kernel");
 }
 int seqm_packed_axpby(const seqm_batch_t* b, const double* a, const double* X, const double* c, double* Y, void* stream) {
   if (!b || !Y) {

@@ -513,6 +513,21 @@ def op_packed_axpby(plan, a, X, c, Y):
     return Y
 
 
+def op_sigma_ao(plan, X, w, all_symmetric=False):
+    """Two-electron response F[X] of a (generally non-symmetric) packed AO matrix X, e.g. a CIS transition density
+    (makeA_pi_batched, rcis_batch.py:296-403): the Fock build of its symmetric part without Hcore plus the exchange-only
+    response of its antisymmetric part."""
+    XT = torch.empty_like(X)
+    plan.lib.check(plan.lib.dll.seqm_packed_transpose(plan.ref, ptr(X), ptr(XT), stream_of(X)), "seqm_packed_transpose")
+    F = op_fock(plan, 0.5 * (X + XT), plan.new_mat(), w)
+    if not all_symmetric:
+        Fa = torch.empty_like(X)
+        Xa = 0.5 * (X - XT)
+        plan.lib.check(plan.lib.dll.seqm_fock_antisym(plan.ref, ptr(Xa), ptr(w), ptr(Fa), stream_of(Fa)), "seqm_fock_antisym")
+        F += Fa
+    return F
+
+
 def op_mo_match(plan, V_new, V_old, e):
     """Energy._crossing_match_molecular_orbitals[_grouped] (basics.py:596-719): V (nmol, nmax, nmax), e (nmol, nmax)."""
     V_new, V_old, e = V_new.contiguous(), V_old.contiguous(), e.contiguous()

@@ -340,3 +340,64 @@ def test_gpu_ksa_scf(name):
     from helpers import cuda_lib
 
     check_ksa_scf(cuda_lib(), torch.device("cuda:0"), name)
+
+
+# ---- CIS sigma-vector building block (makeA_pi_batched, rcis_batch.py:296-403) ------------------------
+def _dense_from_packed(Xp, nheavy, nhyd, molsize):
+    """(nmol, nroots, norb, norb) in packed orbital order -> dense padded (nmol * nroots, 4 molsize, 4 molsize)"""
+    idx = np.concatenate([np.arange(4 * nheavy), 4 * nheavy + 4 * np.arange(nhyd)])
+    nmol, nr = Xp.shape[:2]
+    D = np.zeros((nmol, nr, 4 * molsize, 4 * molsize))
+    D[:, :, idx[:, None], idx[None, :]] = Xp
+    return D, idx
+
+
+def test_oracle_cis_sigma_matches_reference():
+    from seqm_oracle import cis
+    from seqm_oracle.hamiltonian import build_hcore
+    from seqm_oracle.integrals import atom_multipoles
+    from seqm_oracle.parser import parse
+    from seqm_oracle.tables import method_parameters
+
+    g = dict(np.load(os.path.join(GOLDEN, "cis_sigma_methanal.npz")))
+    P = parse(g["species"], g["coordinates"])
+    par = method_parameters("AM1", P.Z)
+    w = build_hcore(P, par, atom_multipoles(P.Z, par))["w"]
+    nh, ny = int(P.nHeavy[0]), int(P.nHydro[0])
+    for key_x, key_f, sym in (("X", "F", False), ("Xs", "Fs", True)):
+        Xd, idx = _dense_from_packed(g[key_x], nh, ny, P.molsize)
+        for r in range(Xd.shape[1]):
+            F = cis.sigma_ao(P, par, w, Xd[:, r], all_symmetric=sym)
+            assert np.abs(F[:, idx[:, None], idx[None, :]] - g[key_f][:, r]).max() < 1e-12
+
+
+def check_cis_sigma(lib, device):
+    import pyseqm_b200 as seqm
+    from pyseqm_b200.seqm_functions.hcore import hcore
+    from pyseqm_b200.seqm_functions.rcis_batch import makeA_pi_batched
+
+    torch.set_default_dtype(torch.float64)
+    g = dict(np.load(os.path.join(GOLDEN, "cis_sigma_methanal.npz")))
+    sp = json.loads(str(g["seqm_parameters"]))
+    mol = seqm.Molecule(seqm.Constants().to(device), dict(sp), torch.as_tensor(g["coordinates"], device=device),
+                        torch.as_tensor(g["species"], device=device), _lib=lib)  # fmt: skip
+    w = hcore(mol)[1]
+    F = makeA_pi_batched(mol, torch.as_tensor(g["X"], device=device), w, allSymmetric=False)
+    assert np.abs(F.cpu().numpy() - g["F"]).max() < 1e-11
+    Fs = makeA_pi_batched(mol, torch.as_tensor(g["Xs"], device=device), w, allSymmetric=True)
+    assert np.abs(Fs.cpu().numpy() - g["Fs"]).max() < 1e-11
+    with pytest.raises(ValueError):
+        makeA_pi_batched(mol, torch.zeros((2, 1, 7, 7), dtype=torch.float64, device=device), w)
+
+
+def test_hostemu_cis_sigma():
+    from helpers import hostemu_lib
+
+    check_cis_sigma(hostemu_lib(), torch.device("cpu"))
+
+
+@pytest.mark.gpu
+def test_gpu_cis_sigma():
+    from helpers import cuda_lib
+
+    check_cis_sigma(cuda_lib(), torch.device("cuda:0"))

@@ -102,6 +102,29 @@ def operators():
     print("ksa_operators: S", t(S), "S_hot", t(Sh), "mu", t(mu).ravel(), "|PO1|", float(PO1.abs().max()))
 
 
+def cis_sigma():
+    """makeA_pi_batched (rcis_batch.py:296-403) of the reference on two methanal geometries, three random non-symmetric AO
+    matrices per molecule, both symmetry modes."""
+    from seqm.seqm_functions.hcore import hcore
+    from seqm.seqm_functions.rcis_batch import makeA_pi_batched
+
+    species, coords = read_xyz([os.path.join(XYZ, f) for f in ("methanal.1.xyz", "methanal.2.xyz")])
+    sp = {"method": "AM1", "scf_eps": 1e-7, "scf_converger": [2]}
+    mol = Molecule(Constants(), sp, torch.as_tensor(coords), torch.as_tensor(species, dtype=torch.int64))
+    M, w, *_ = hcore(mol)
+    norb = int(mol.norb[0])
+    g = torch.Generator().manual_seed(5)
+    X = torch.randn(mol.nmol, 3, norb, norb, generator=g, dtype=torch.float64)
+    F = makeA_pi_batched(mol, X.clone(), w, allSymmetric=False)
+    Xs = 0.5 * (X + X.transpose(2, 3))
+    Fs = makeA_pi_batched(mol, Xs.clone(), w, allSymmetric=True)
+    t = lambda x: x.detach().numpy()  # noqa: E731
+    np.savez_compressed(os.path.join(GOLD, "cis_sigma_methanal.npz"), species=np.asarray(species), coordinates=np.asarray(coords),
+                        seqm_parameters=json.dumps({k_: v_ for k_, v_ in sp.items() if k_ != 'elements'}), X=t(X), F=t(F),
+                        Xs=t(Xs), Fs=t(Fs))  # fmt: skip
+    print("cis_sigma_methanal |F|", float(F.abs().max()), "antisymmetric part", float((F - F.transpose(2, 3)).abs().max()))
+
+
 def scf_ksa_cases():
     """scf_converger = [3, {...}] (scf_forward3, scf_loop.py:1135-1381) single points; the iteration count is the number in the
     reference's own verbose line "scf KSA step : N"."""
@@ -131,7 +154,11 @@ if __name__ == "__main__":
     if os.environ.get("GOLDEN_ONLY") == "scf":
         scf_ksa_cases()
         sys.exit(0)
+    if os.environ.get("GOLDEN_ONLY") == "cis":
+        cis_sigma()
+        sys.exit(0)
     scf_ksa_cases()
+    cis_sigma()
     operators()
     if os.environ.get("GOLDEN_ONLY") == "operators":
         sys.exit(0)
