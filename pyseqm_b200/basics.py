@@ -211,6 +211,8 @@ class KsaOps:
         V, W = [], []
         dW = dDS
         err = torch.full((plan.nmol,), 10.0, dtype=torch.float64, device=plan.device)
+        Ofull = torch.zeros((plan.nmol, rank, rank), dtype=torch.float64, device=plan.device)
+        rhs_full = torch.zeros((plan.nmol, rank), dtype=torch.float64, device=plan.device)
         alpha = None
         while len(V) < rank and float(err.max()) > thr:
             v = dW.clone()
@@ -222,9 +224,10 @@ class KsaOps:
             W.append(self.density_response(plan, FO1, Q, e, mu, beta, m_iter) - v)
             dW = W[-1]
             r = len(W)
-            O = torch.stack([torch.stack([engine.op_packed_dot(plan, W[a], W[b]) for b in range(r)], dim=1) for a in range(r)], dim=1)
-            rhs = torch.stack([engine.op_packed_dot(plan, W[a], dDS) for a in range(r)], dim=1)
-            alpha = torch.linalg.solve(O, rhs.unsqueeze(-1)).squeeze(-1)
+            for a in range(r):  # only the new row / column of the Gram matrix and the new right-hand side entry
+                Ofull[:, a, r - 1] = Ofull[:, r - 1, a] = engine.op_packed_dot(plan, W[a], W[r - 1])
+            rhs_full[:, r - 1] = engine.op_packed_dot(plan, W[r - 1], dDS)
+            alpha = torch.linalg.solve(Ofull[:, :r, :r], rhs_full[:, :r].unsqueeze(-1)).squeeze(-1)
             ident = -dDS
             for a in range(r):
                 engine.op_packed_axpby(plan, alpha[:, a], W[a], None, ident)

@@ -62,6 +62,52 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) packed_gemm_kernel(seqm_batch_t b, cons
     }
 }
 
+#ifndef SEQM_HOSTEMU
+// FP64 tensor-core version for molecules whose op(B) fits the SM's shared memory (n <= ~160): op(B) zero-padded to a multiple
+// of 8 with a row stride of 4 mod 16 (conflict-free fragment loads), op(A) fragments straight from global memory / L1, one
+// warp per 8x8 output tile, mma.sync.m8n8k4.f64 (DMMA) -- the scheme of the eigensolver's warm-start transform.
+SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS(256) packed_gemm_dmma_kernel(seqm_batch_t b, const double* __restrict__ A,
+                                                                 const double* __restrict__ B, double* __restrict__ C, int ta, int tb) {
+  SEQM_DYN_SMEM(double, S);
+  const MolView v = mol_view(b, blockIdx.x);
+  const int n = v.n, tid = threadIdx.x, nthr = blockDim.x;
+  const double* Am = A + v.mat0;
+  const double* Bm = B + v.mat0;
+  double* Cm = C + v.mat0;
+  const int np8 = (n + 7) & ~7, nt8 = np8 >> 3, LDT = np8 + 4;
+  for (int t = tid; t < np8 * LDT; t += nthr) {
+    const int k = t / LDT, j = t - k * LDT;
+    S[t] = (k < n && j < n) ? (tb ? Bm[j * n + k] : Bm[k * n + j]) : 0.0;
+  }
+  __syncthreads();
+  const int warp = tid >> 5, nwarps = nthr >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  for (int tile = warp; tile < nt8 * nt8; tile += nwarps) {
+    const int m0 = (tile / nt8) * 8, n0 = (tile % nt8) * 8;
+    const int r = m0 + g;
+    double c0 = 0.0, c1 = 0.0;
+    for (int k0 = 0; k0 < np8; k0 += 16) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kc = k0 + 4 * u + t4;
+        af[u] = (r < n && kc < n) ? (ta ? Am[kc * n + r] : Am[r * n + kc]) : 0.0;
+        bf[u] = (kc < np8) ? S[kc * LDT + n0 + g] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0), "+d"(c1)
+                     : "d"(af[u]), "d"(bf[u]));
+    }
+    const int c = n0 + 2 * t4;
+    if (r < n) {
+      if (c < n) Cm[r * n + c] = c0;
+      if (c + 1 < n) Cm[r * n + c + 1] = c1;
+    }
+  }
+}
+#endif
+
 SEQM_GLOBAL void scale_columns_kernel(seqm_batch_t b, const double* __restrict__ C, const double* __restrict__ f, double s,
                                       double* __restrict__ out) {
   const MolView v = mol_view(b, blockIdx.x);
@@ -203,6 +249,27 @@ int seqm_packed_gemm(const seqm_batch_t* b, const double* A, const double* B, do
     seqm_set_error("seqm_packed_gemm: the result must be a distinct buffer");
     return SEQM_ERR_ARG;
   }
+#ifndef SEQM_HOSTEMU
+  {
+    static int smem_max = -1;  // one device per process (seqm_b200.cu: ensure_device)
+    if (smem_max < 0) {
+      int dev = 0, optin = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      smem_max = optin - 1024;
+      if (cudaFuncSetAttribute(packed_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess) {
+        cudaGetLastError();
+        smem_max = 0;
+      }
+    }
+    const int np8 = (b->nmax + 7) & ~7;
+    const size_t need = sizeof(double) * (size_t)np8 * (np8 + 4);
+    if (need <= (size_t)smem_max) {
+      SEQM_LAUNCH(packed_gemm_dmma_kernel, b->nmol, 256, need, KSA_STREAM(stream), *b, A, B, C, transA, transB);
+      return seqm_check_launch("packed_gemm_dmma_kernel");
+    }
+  }
+#endif
   SEQM_LAUNCH(packed_gemm_kernel, b->nmol, 256, 0, KSA_STREAM(stream), *b, A, B, C, transA, transB);
   return seqm_check_launch("packed_gemm_kernel");
 }
