@@ -613,12 +613,15 @@ def main():
             "bound_enum": "tensor",
             "bound_note": "compute side of the roofline, FP64: tcgen05 has no FP64 kind, so the peak is the FP64 pipe (DFMA = DMMA "
             "rate on B200, 36.5 / 37.2 TFLOP/s measured).  ncu (profiles/) shows the kernel limited by dependent-chain latency and "
-            "shared-memory wavefronts, not by the tensor pipe (DMMA sub-pipe < 3 %)",
+            "shared-memory wavefronts, not by the tensor pipe (DMMA sub-pipe < 3 %); instruction budget of a step: 4.9 G warp "
+            "instructions, 0.9 G of them FP64 = 45 % of the issue slots and 17 % of the FP64 pipe in the time the solver takes "
+            "(profiles/jacobi_inst_r02.txt)",
             "achieved": (jac_flops / (j_ms * 1e-3) / 1e12) if j_ms else None,
             "peak": fp64_peak, "unit": "TFLOP/s", "peak_source": "measured in this run: seqm_fp64_peak_tflops() "
             "DFMA probe (MEASURED_PEAKS.json has no fp64 entry)",
             "traffic": 77.4e6, "traffic_note": "DRAM bytes read + written per full-batch eigensolver call from the ncu --set full "
-            "capture in profiles/jacobi_r01_final.txt (writes stay in the 126 MB L2); the HBM floor 16 n^2 B per molecule is 74.9 MB",
+            "captures in profiles/jacobi_r01_final.txt and profiles/hot_r02_final.txt (writes stay in the 126 MB L2); the HBM floor "
+            "16 n^2 B per molecule is 74.9 MB",
             "algorithmic": "10 n^3 + 2 n^2 nocc flop (batch mean) x molecules solved in the step (library counter)",
             "molecules_solved": solved, "sweeps_per_solve": round(jstats["sweeps"] / max(solved, 1), 3),
             "share_of_step": round(j_ms / tot, 4), "dominant_kernel_by_time": top,
@@ -630,8 +633,9 @@ def main():
             "unit": "GB/s", "peak_source": hbm_src,
             "algorithmic": "(1184 B/pair + 384 B/atom, batch mean per molecule) x active molecules summed over the launches",
             "active_molecule_launches": int(fock_active_molecules), "launches": int(f_n),
-            "traffic": 213.1e6, "traffic_note": "ncu dram__bytes_read+write per half-batch launch (profiles/others_r01_final.txt): "
-            "below the algorithmic bytes because H-H / X-H pairs touch 8 / 80 B of their 800 B w block",
+            "traffic": 212.9e6, "traffic_note": "ncu dram__bytes_read+write per half-batch launch (profiles/hot_r02_final.txt: 198.3 MB "
+            "read + 14.5 MB written in 84 us, cold): below the algorithmic bytes because H-H / X-H pairs touch 8 / 80 B of "
+            "their 800 B w block",
             "share_of_step": round(f_ms / tot, 4),
         }  # fmt: skip
         if roofline["fock_kernel_hbm"]["achieved"]:

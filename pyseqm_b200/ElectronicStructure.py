@@ -58,8 +58,8 @@ class Electronic_Structure(torch.nn.Module):
 
     def forward(self, molecule, learned_parameters=dict(), xl_bomd_params=dict(), P0=None, err_threshold=None,
                 max_rank=None, T_el=None, dm_prop="SCF", *args, **kwargs):  # fmt: skip
-        if max_rank is not None or T_el is not None:
-            raise NotImplementedError("KSA / finite-temperature options are not part of the B200 SCF path")
+        # max_rank / T_el: accepted and unused, as in the reference (ElectronicStructure.py:47-48); the KSA parameters travel
+        # in xl_bomd_params (XL-BOMD) or in scf_converger = [3, {...}] (SCF)
         kwargs.pop("cis_amp", None)
         if dm_prop == "SCF":
             (molecule.force, P, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso, molecule.e_mo,
