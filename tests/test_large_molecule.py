@@ -174,7 +174,7 @@ def test_gpu_c380_against_reference():
     g = load_golden("cfg4_C380_AM1_sp2")
     mol, es = run_molecule(cuda_lib(), torch.device("cuda:0"), g["species"], g["coordinates"], g["seqm_parameters"])
     assert not bool(es.notconverged.any())
-    # north-star tolerances; measured margins on a B200 (tools/c380_margins.py): 41 = 41 iterations, dEtot 9e-10 eV,
+    # north-star tolerances; measured margins on a B200 (tools/sp2_margins.py): 41 = 41 iterations, dEtot 9e-10 eV,
     # dEnuc 3e-9 eV, dForce 2.6e-9 eV/A, dq 7e-11, dgap 3e-11 eV
     assert mol.n_scf_iter == g["n_scf_iter"] == 41
     assert abs(float(mol.Etot[0]) - float(g["Etot"][0])) < 1e-6

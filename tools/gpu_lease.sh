@@ -1,5 +1,5 @@
 # round-2 final lease: parity suite, smoke, default bench (both arms), PM6 extra, forward launch count, ncu launch list and
-# --set full captures of the eigensolver and the Fock kernel.  Usage: gpurun --timeout 3300 -- 'bash tools/gpu_round3.sh TAG'
+# --set full captures of the eigensolver and the Fock kernel.  Usage: gpurun --timeout 3300 -- 'bash tools/gpu_lease.sh TAG'
 TAG=${1:-r02c}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_$TAG.log
