@@ -514,6 +514,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         }
       }
       // ---- V <- V M
+#ifndef SEQM_EXP_NOV  // SEQM_EXP_NOV: timing experiment only (tools/bench_eig.py), sweeps without the eigenvector update
       if (PH == 0) {
         seqm_static_for(std::make_integer_sequence<int, SEG / 2>{}, [&](auto jc) {
           constexpr int j = decltype(jc)::value;
@@ -539,6 +540,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         vr[SEG - 1] = cn.x * last_old + cn.y * y_next;
         vr[0] = cp.y * x_prev - cp.x * first_old;
       }
+#endif
       SEQM_SYNC();
     };
     for (int step = 0; step < M; step += 2) {
@@ -582,6 +584,10 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         }
       SEQM_SYNC();
     }
+#endif
+#ifdef SEQM_EXP_NOV
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) vr[e] = (vrow == vseg * SEG + e) ? 1.0 : 0.0;
 #endif
     // quadratic convergence: once every rotation of a sweep was below tol_big (1e-6 |A| inside the SCF, 1e-8 |A|
     // when eigenpairs are returned) the off-diagonal left behind is O(tol_big^2 / gap): an occupied-virtual
