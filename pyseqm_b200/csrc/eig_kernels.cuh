@@ -38,9 +38,9 @@ struct alignas(16) seqm_d2 { double x, y; };
 // odd steps pair (1,2)(3,4)...(m-1,0); every rotation is followed by a swap of the two slots, so after m
 // steps every pair has met exactly once.  Static positions mean no index tables, no integer division by
 // runtime values and compile-time register indices:
-//   * A lives in shared memory in two column planes (even columns | odd columns, row stride LD padded so
-//     that the row segments touched by one warp fall in disjoint banks): every access of both the even and
-//     the odd step is a conflict-free 64-bit access with unit lane stride.
+//   * the upper triangle of A lives in shared memory tile-major (jacobi_aidx): one plane per element of the 2x2 tiles,
+//     indexed by the owner slot of the tile, so the even step is a unit-stride 64-bit access and the odd step is unit
+//     stride along every tile row (the kernel is bound by shared-memory wavefronts: ncu).
 //   * V never touches shared memory during the sweeps: thread (row i, segment s) keeps m/SR consecutive
 //     entries of row i in registers (SR = 4 threads per row, 8 for the classes with NP >= 40); the one pair that
 //     straddles two segments in odd steps is exchanged with two 64-bit shuffles inside the SR-lane group.
@@ -49,7 +49,7 @@ struct alignas(16) seqm_d2 { double x, y; };
 //     to the sign of slot 0, which is irrelevant for an eigenbasis).
 // Slots n..m-1 are decoupled dummies whose diagonal lies above the Gershgorin bound; they rank last.
 // blockDim.x must be SR*m (V ownership); tiles are strided over all threads.
-// shared: A[m*LD] | cs[NP] (double2) | scr[40] | dg[m] | perm[m] (int) | occm[m] (int)
+// shared: A[AREG] | cs[2][NP] (double2) | scr[40] | dg[m] | perm[m] (int) | occm[m] (int)
 //
 // Inside the SCF only the density is consumed, and it depends on the occupied SUBSPACE alone.  Before every sweep
 // the occupied-virtual block of the current A is inspected (slots ranked by their diagonal); once its largest
@@ -65,10 +65,6 @@ struct alignas(16) seqm_d2 { double x, y; };
 template <int NP>
 struct JacobiCfg {
   static constexpr int M = 2 * NP;
-#ifndef SEQM_LDPAD0
-#define SEQM_LDPAD0 6  // the classes whose natural pad is 0 (NP = 16, 32, 48, 64): measured best of 0/2/4/6
-#endif
-  static constexpr int LD = M + (((NP / 2) % 8) ? ((NP / 2) % 8) : SEQM_LDPAD0);
   static constexpr int SR = (NP >= SEQM_SR8_FROM && NP % 8 == 0) ? 8 : 4;  // threads per row of V (more for the big classes: 1 CTA/SM there,
                                                  // so the CTA itself must bring enough warps to hide latency)
   static constexpr int SEG = M / SR;             // V entries per thread
@@ -84,38 +80,63 @@ struct JacobiCfg {
   static constexpr int MINBLOCKS = NP == 16 ? SEQM_JB16 : NP == 20 ? SEQM_JB20 : NP == 24 ? SEQM_JB24
                                    : NP == 28 ? SEQM_JB28 : NP == 32 ? SEQM_JB32 : 0;
   static constexpr int LDT = M + 4;  // staging stride of the tensor-core products: 4 or 12 mod 16, conflict-free
-  static constexpr int AREG = M * (LD > LDT ? LD : LDT);    // doubles reserved for A (also holds the staging tile)
+  // tile ownership (see the kernel): NT upper-triangular 2x2 tiles, the NA "part A" tiles on threads 0..NA-1, the NR others
+  // dealt TPX per thread over the remaining NO threads
+  static constexpr int NT = NP * (NP + 1) / 2, NA = 2 * NP, NR = NT - NA;
+  static constexpr int NO = (THREADS > NA) ? THREADS - NA : 1;
+  static constexpr int TPX = ((NR + NO - 1) / NO > 1) ? (NR + NO - 1) / NO : 1;
+  static constexpr int PL = TPX * THREADS;  // slots of one element plane of A (tile-major storage, jacobi_aidx)
+  static constexpr int AREG = (4 * PL > M * LDT) ? 4 * PL : M * LDT;  // doubles reserved for A (also holds the staging tile)
   static constexpr size_t SMEM = sizeof(double) * ((size_t)AREG + 4 * NP + 40 + M) + sizeof(int) * (2 * M + 4);
 };
 
-// element (r, c) of the plane-split matrix
-#define SEQM_AIDX(r, c) ((r) * LD + (((c) & 1) ? NP : 0) + ((c) >> 1))
+// Storage of the upper triangle of A (r <= c), TILE-MAJOR: element e = 2 (r & 1) + (c & 1) of the 2x2 tile (k, l) = (r/2, c/2)
+// lives in plane e at the slot of the tile's owner, slot = qt * THREADS + tid.  In an even step thread tid reads and writes
+// plane[e][qt * THREADS + tid] -- unit lane stride, no bank conflicts; in an odd step its tile is made of element 3 of even
+// tile (k, l), 2 of (k, l+1), 1 of (k+1, l) and 0 of (k+1, l+1), whose slots differ from its own by amounts that are
+// constant along a tile row, so conflicts are confined to the lanes where a warp crosses a tile row (1.15-1.35 wavefronts
+// per ideal one; the row-major, plane-split layout it replaces had 1.7-2.0, ncu and tools/probes/jacobi_banks.py).
+template <int NP>
+SEQM_HD int jacobi_slot(int k, int l) {  // owner slot of tile (k <= l)
+  typedef JacobiCfg<NP> K;
+  if (k == l) return k;
+  if (l == k + 1) return NP + k;
+  if (k == 0 && l == NP - 1) return 2 * NP - 1;
+  const int before = (k == 0) ? 0 : (NP - 3) + (k - 1) * (NP - 2) - (k - 1) * k / 2;  // rest tiles of the rows above
+  const int r = before + (l - k - 2);
+  return (r / K::NO) * K::THREADS + K::NA + (r % K::NO);
+}
+template <int NP>
+SEQM_HD int jacobi_aidx(int r, int c) {  // r <= c
+  return (2 * (r & 1) + (c & 1)) * JacobiCfg<NP>::PL + jacobi_slot<NP>(r >> 1, c >> 1);
+}
+#define SEQM_AIDX(r, c) jacobi_aidx<NP>((r), (c))
 
-// shared-memory offsets of tile (k <= l): (p_k,p_l) (p_k,q_l) (q_k,p_l) (q_k,q_l) in even (oe) and odd (oo) steps
+// shared-memory offsets of tile (k <= l): (p_k,p_l) (p_k,q_l) (q_k,p_l) (q_k,q_l) in even (oe) and odd (oo) steps; the
+// third element of a diagonal tile lies below the diagonal and is never accessed (its offset repeats the second)
 template <int NP>
 SEQM_HD void jacobi_tile_offsets(int k, int l, int* oe, int* oo) {
-  constexpr int LD = JacobiCfg<NP>::LD;
-  const int re = (2 * k) * LD;
-  oe[0] = re + l;
-  oe[1] = re + NP + l;
-  oe[2] = re + LD + l;
-  oe[3] = re + LD + NP + l;
-  const int r0 = (2 * k + 1) * LD;
+  constexpr int m = 2 * NP;
+  const bool diag = (k == l);
+  oe[0] = jacobi_aidx<NP>(2 * k, 2 * l);
+  oe[1] = jacobi_aidx<NP>(2 * k, 2 * l + 1);
+  oe[2] = diag ? oe[1] : jacobi_aidx<NP>(2 * k + 1, 2 * l);
+  oe[3] = jacobi_aidx<NP>(2 * k + 1, 2 * l + 1);
   if (l < NP - 1) {
-    oo[0] = r0 + NP + l;       // (2k+1, 2l+1)
-    oo[1] = r0 + l + 1;        // (2k+1, 2l+2)
-    oo[2] = r0 + LD + NP + l;  // (2k+2, 2l+1)
-    oo[3] = r0 + LD + l + 1;   // (2k+2, 2l+2)
-  } else if (k < NP - 1) {
-    oo[0] = r0 + NP + l;       // (2k+1, m-1)
-    oo[1] = NP + k;            // (2k+1, 0)  stored at (0, 2k+1)
-    oo[2] = r0 + LD + NP + l;  // (2k+2, m-1)
-    oo[3] = k + 1;             // (2k+2, 0)  stored at (0, 2k+2)
+    oo[0] = jacobi_aidx<NP>(2 * k + 1, 2 * l + 1);
+    oo[1] = jacobi_aidx<NP>(2 * k + 1, 2 * l + 2);
+    oo[2] = diag ? oo[1] : jacobi_aidx<NP>(2 * k + 2, 2 * l + 1);
+    oo[3] = jacobi_aidx<NP>(2 * k + 2, 2 * l + 2);
+  } else if (k < NP - 1) {  // the wrap pair (m-1, 0): column 0 is read at its mirrored location (0, r)
+    oo[0] = jacobi_aidx<NP>(2 * k + 1, m - 1);
+    oo[1] = jacobi_aidx<NP>(0, 2 * k + 1);
+    oo[2] = jacobi_aidx<NP>(2 * k + 2, m - 1);
+    oo[3] = jacobi_aidx<NP>(0, 2 * k + 2);
   } else {
-    oo[0] = r0 + NP + l;       // (m-1, m-1)
-    oo[1] = NP + l;            // (m-1, 0)   stored at (0, m-1)
+    oo[0] = jacobi_aidx<NP>(m - 1, m - 1);
+    oo[1] = jacobi_aidx<NP>(0, m - 1);
     oo[2] = oo[1];
-    oo[3] = 0;                 // (0, 0)
+    oo[3] = jacobi_aidx<NP>(0, 0);
   }
 }
 
@@ -142,7 +163,6 @@ SEQM_HD void jacobi_rest_tile(int r, int& k, int& l) {
 // (1, 0) for the wrap pair of odd steps
 template <int NP>
 SEQM_D seqm_d2 jacobi_pair_rotation(const double* A, int k, int ph, double tol, double tol_big, int* flag) {
-  constexpr int LD = JacobiCfg<NP>::LD;
   seqm_d2 ab;
   ab.x = 0.0;
   ab.y = 1.0;
@@ -151,12 +171,15 @@ SEQM_D seqm_d2 jacobi_pair_rotation(const double* A, int k, int ph, double tol, 
     ab.y = 0.0;
     return ab;
   }
-  const int p = 2 * k + ph, q = p + 1;
-  const double apq = A[SEQM_AIDX(p, q)];
+  // (p, q) = (2k + ph, 2k + ph + 1): even steps read the diagonal tile k, odd steps the corners of the diagonal tiles k, k+1
+  // and the third element of the super-diagonal tile (k, k+1)
+  constexpr int PL = JacobiCfg<NP>::PL;
+  const int ipq = ph ? 2 * PL + NP + k : PL + k, ipp = ph ? 3 * PL + k : k, iqq = ph ? k + 1 : 3 * PL + k;
+  const double apq = A[ipq];
   if (fabs(apq) > tol) {
     // |theta| <= pi/4 from two reciprocal square roots (no division on the critical path):
     // cos 2t = |d|/h, sin 2t = sgn(d) 2 a_pq / h, c = sqrt((1 + cos 2t)/2), s = sin 2t / (2c)
-    const double d = A[SEQM_AIDX(q, q)] - A[SEQM_AIDX(p, p)], b2 = 2.0 * apq;
+    const double d = A[iqq] - A[ipp], b2 = 2.0 * apq;
     const double rh = seqm_rsqrt(d * d + b2 * b2);
     const double c2 = 0.5 + 0.5 * fabs(d) * rh;
     const double ic = seqm_rsqrt(c2);
@@ -212,7 +235,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
                                      const double* __restrict__ Cguess, const int32_t* __restrict__ active,
                                      JacobiMix mix) {
   typedef JacobiCfg<NP> K;
-  constexpr int M = K::M, LD = K::LD, SEG = K::SEG, SR = K::SR;
+  constexpr int M = K::M, SEG = K::SEG, SR = K::SR;
   const int mol = b.mol_order[first + blockIdx.x];
   if (active && !active[mol]) return;
   const MolView v = mol_view(b, mol);
@@ -368,16 +391,18 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     }
 #endif
     SEQM_SYNC();
+    for (int t = tid; t < 4 * K::PL; t += nthr) A[t] = 0.0;  // unowned slots stay zero (the scan for max |A| reads them)
+    SEQM_SYNC();
     for (int t = tid; t < M * M; t += nthr) {
       const int i = t / M, j = t - i * M;
-      double a = 0.0;
-      if (i < n && j < n) a = (j >= i) ? G2[i * n + j] : G2[j * n + i];
-      A[SEQM_AIDX(i, j)] = a;
+      if (j >= i) A[SEQM_AIDX(i, j)] = (j < n) ? G2[i * n + j] : 0.0;
     }
   } else {
+    for (int t = tid; t < 4 * K::PL; t += nthr) A[t] = 0.0;
+    SEQM_SYNC();
     for (int t = tid; t < M * M; t += nthr) {
       const int i = t / M, j = t - i * M;
-      A[SEQM_AIDX(i, j)] = (i < n && j < n) ? Fm[i * n + j] : 0.0;
+      if (j >= i) A[SEQM_AIDX(i, j)] = (j < n) ? Fm[i * n + j] : 0.0;
     }
 #ifndef SEQM_HOSTEMU
 #pragma unroll
@@ -390,10 +415,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   SEQM_SYNC();
   const long long clk1 = SEQM_CLOCK();
   double dmax = 0.0;
-  for (int t = tid; t < M * LD; t += nthr) {
-    const int c = t % LD;
-    if (c < M) dmax = fmax(dmax, fabs(A[t]));
-  }
+  for (int t = tid; t < 4 * K::PL; t += nthr) dmax = fmax(dmax, fabs(A[t]));
   dmax = block_max(dmax, scr);
   const double tol = 1.0e-14 * fmax(dmax, 1.0e-300);
   // eigenvalues / eigenvectors requested for output (final solve): stricter early-finish threshold
@@ -406,13 +428,12 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   // first warps), are updated first, and those warps then work out the next step's rotations while all the other
   // threads update the remaining tiles and V: one block barrier per step, the rsqrt chain off the critical path.
   // The four shared-memory offsets of every owned tile in even and in odd steps are hoisted into registers.
-  constexpr int NT = NP * (NP + 1) / 2;
-  constexpr int NA = 2 * NP;                          // part-A tiles
+  constexpr int NT = K::NT;
+  constexpr int NA = K::NA;                           // part-A tiles
   constexpr int GA = ((NA + 31) / 32) * 32;           // threads of the warps that own them
-  constexpr int NR = NT - NA;                         // remaining tiles: l >= k + 2 without the corner
-  constexpr int NO = (K::THREADS > NA) ? K::THREADS - NA : 1;
-  constexpr int TPO = (NR + NO - 1) / NO;             // remaining tiles per non-part-A thread
-  constexpr int TPX = (TPO > 1) ? TPO : 1;
+  constexpr int NR = K::NR;                           // remaining tiles: l >= k + 2 without the corner
+  constexpr int NO = K::NO;
+  constexpr int TPX = K::TPX;                         // remaining tiles per non-part-A thread
 #ifndef SEQM_HOSTEMU
   // per owned tile: does it exist / is it diagonal, the shared-window byte addresses of its four elements in even
   // (ae) and odd (ao) steps and of its two rotation pairs in the cs buffer of even steps (odd: + NP * 16 bytes)
@@ -515,6 +536,10 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
       }
       // ---- V <- V M
 #ifndef SEQM_EXP_NOV  // SEQM_EXP_NOV: timing experiment only (tools/bench_eig.py), sweeps without the eigenvector update
+#ifdef SEQM_EXP_NOV_WARP0  // ... or without it in the warp that computes the rotation parameters only
+      if (tid < 32) {
+      } else
+#endif
       if (PH == 0) {
         seqm_static_for(std::make_integer_sequence<int, SEG / 2>{}, [&](auto jc) {
           constexpr int j = decltype(jc)::value;
