@@ -205,6 +205,16 @@ SEQM_D double seqm_lds(unsigned a) {
 }
 SEQM_D void seqm_sts(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 template <int OFF>
+SEQM_D double seqm_lds_at(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF>
+SEQM_D void seqm_sts_at(unsigned a, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+template <int OFF>
 SEQM_D seqm_d2 seqm_lds2(unsigned a) {
   seqm_d2 v;
   asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(a), "n"(OFF));
@@ -435,10 +445,12 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   constexpr int NO = K::NO;
   constexpr int TPX = K::TPX;                         // remaining tiles per non-part-A thread
 #ifndef SEQM_HOSTEMU
-  // per owned tile: does it exist / is it diagonal, the shared-window byte addresses of its four elements in even
-  // (ae) and odd (ao) steps and of its two rotation pairs in the cs buffer of even steps (odd: + NP * 16 bytes)
+  // per owned tile: does it exist / is it diagonal, the shared-window byte address of its slot in element plane 0 (even
+  // steps touch the four planes at that slot; the first element of an odd step is the slot's plane-3 entry), the
+  // addresses of the other three elements of its odd-step tile (ao) and of its two rotation pairs in the cs buffer of
+  // even steps (odd: + NP * 16 bytes)
   bool thas[TPX], tdiag[TPX];
-  unsigned ae[TPX][4], ao[TPX][4], ck_a[TPX], cl_a[TPX];
+  unsigned ab[TPX], ao[TPX][3], ck_a[TPX], cl_a[TPX];
   const unsigned A_u32 = seqm_smem_u32(A), cs_u32 = seqm_smem_u32(cs);
 #pragma unroll
   for (int qt = 0; qt < TPX; ++qt) {
@@ -453,11 +465,9 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     tdiag[qt] = k == l;
     int oe[4], oo[4];
     jacobi_tile_offsets<NP>(k < 0 ? 0 : k, l, oe, oo);
+    ab[qt] = A_u32 + 8u * (unsigned)oe[0];  // oe[e] = e * PL + slot, oo[0] = oe[3]
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ae[qt][e] = A_u32 + 8u * (unsigned)oe[e];
-      ao[qt][e] = A_u32 + 8u * (unsigned)oo[e];
-    }
+    for (int e = 0; e < 3; ++e) ao[qt][e] = A_u32 + 8u * (unsigned)oo[e + 1];
     ck_a[qt] = cs_u32 + 16u * (unsigned)(k < 0 ? 0 : k);
     cl_a[qt] = cs_u32 + 16u * (unsigned)l;
   }
@@ -514,18 +524,33 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
 #pragma unroll
       for (int qt = 0; qt < TPX; ++qt) {
         if (thas[qt]) {
-          const unsigned a00 = PH ? ao[qt][0] : ae[qt][0], a01 = PH ? ao[qt][1] : ae[qt][1];
-          const unsigned a10 = PH ? ao[qt][2] : ae[qt][2], a11 = PH ? ao[qt][3] : ae[qt][3];
+          constexpr int PB = 8 * K::PL;  // bytes between element planes
           const seqm_d2 ck = seqm_lds2<CUR>(ck_a[qt]), cl = seqm_lds2<CUR>(cl_a[qt]);
           const bool diag = tdiag[qt];
-          const double x0 = seqm_lds(a00), y0 = seqm_lds(a01), y1 = seqm_lds(a11);
-          const double x1 = diag ? y0 : seqm_lds(a10);
+          const unsigned a0 = ab[qt];
+          double x0, y0, x1, y1;
+          if (PH == 0) {
+            x0 = seqm_lds_at<0>(a0), y0 = seqm_lds_at<PB>(a0), y1 = seqm_lds_at<3 * PB>(a0);
+            x1 = diag ? y0 : seqm_lds_at<2 * PB>(a0);
+          } else {
+            x0 = seqm_lds_at<3 * PB>(a0), y0 = seqm_lds(ao[qt][0]), y1 = seqm_lds(ao[qt][2]);
+            x1 = diag ? y0 : seqm_lds(ao[qt][1]);
+          }
           const double bx0 = cl.x * x0 + cl.y * y0, by0 = cl.y * x0 - cl.x * y0;
           const double bx1 = cl.x * x1 + cl.y * y1, by1 = cl.y * x1 - cl.x * y1;
-          seqm_sts(a00, ck.x * bx0 + ck.y * bx1);
-          seqm_sts(a01, ck.x * by0 + ck.y * by1);
-          seqm_sts(a11, ck.y * by0 - ck.x * by1);
-          if (!diag) seqm_sts(a10, ck.y * bx0 - ck.x * bx1);
+          const double n00 = ck.x * bx0 + ck.y * bx1, n01 = ck.x * by0 + ck.y * by1;
+          const double n11 = ck.y * by0 - ck.x * by1, n10 = ck.y * bx0 - ck.x * bx1;
+          if (PH == 0) {
+            seqm_sts_at<0>(a0, n00);
+            seqm_sts_at<PB>(a0, n01);
+            seqm_sts_at<3 * PB>(a0, n11);
+            if (!diag) seqm_sts_at<2 * PB>(a0, n10);
+          } else {
+            seqm_sts_at<3 * PB>(a0, n00);
+            seqm_sts(ao[qt][0], n01);
+            seqm_sts(ao[qt][2], n11);
+            if (!diag) seqm_sts(ao[qt][1], n10);
+          }
         }
         if (qt == 0 && tid < GA) {
           // the part-A tiles are done: their warps (only) meet on named barrier 1 and compute the next rotations
