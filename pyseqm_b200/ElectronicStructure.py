@@ -43,7 +43,8 @@ class Electronic_Structure(torch.nn.Module):
         """Per-orbital atomic "charge" table (nmol, 4*molsize, molsize) of scf_loop.py:2346-2387, evaluated lazily
         from the eigenvectors of the last forward (it is a by-product nobody on the hot path consumes)."""
         if self._charge is None and self._charge_src is not None:
-            self._charge = orbital_charge_table(*self._charge_src)
+            mol, mo = self._charge_src  # index tensors of the molecule are themselves built on first access
+            self._charge = orbital_charge_table(mo, mol.nHeavy, mol.nHydro, mol.molsize)
         return self._charge
 
     @charge.setter
@@ -69,7 +70,7 @@ class Electronic_Structure(torch.nn.Module):
             self._charge = None
             self._charge_src = None
             if molecule.molecular_orbitals is not None and molecule.method != "PM6":  # scf_loop.py:2350: none for PM6
-                self._charge_src = (molecule.molecular_orbitals, molecule.nHeavy, molecule.nHydro, molecule.molsize)
+                self._charge_src = (molecule, molecule.molecular_orbitals)
         elif dm_prop == "XL-BOMD":
             (molecule.force, molecule.dm, molecule.Hf, molecule.Etot, molecule.Eelec, molecule.Enuc, molecule.Eiso,
              molecule.e_mo, molecule.e_gap, molecule.Electronic_entropy, molecule.dP2dt2, molecule.Krylov_Error,

@@ -80,12 +80,9 @@ class Molecule(torch.nn.Module):
         self.species = species
         self.coordinates = torch.nn.Parameter(coordinates)
         self.coordinates.requires_grad_(False)
-        if not torch.is_tensor(charges):
-            charges = charges * torch.ones(coordinates.shape[0], device=coordinates.device)
-        self.tot_charge = charges
-        if not torch.is_tensor(mult):
-            mult = mult * torch.ones(coordinates.shape[0], device=coordinates.device)
-        self.mult = mult
+        # tot_charge / mult and most index / mass attributes below are materialised on first access (__getattr__): the SCF
+        # path never reads them, and every eager tensor op here is host time inside an end-to-end step
+        self.__dict__["_charges_in"], self.__dict__["_mult_in"] = charges, mult
         self.seqm_parameters = seqm_parameters
         self.method = seqm_parameters["method"]
         if callable(learned_parameters):
@@ -108,21 +105,14 @@ class Molecule(torch.nn.Module):
             if t.requires_grad:
                 raise NotImplementedError("gradients with respect to learned parameters need autograd through the SCF; not on the B200 path")
             learned[name] = t.detach()
-        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned, charges=charges, table=table,
+        plan = engine.BatchPlan(lib, species, kernel_method, parameters=learned, charges=charges if torch.is_tensor(charges) else int(charges), table=table,
                                 outer_cutoff=seqm_parameters.get("pair_outer_cutoff", 1.0e10))
         self._plan = plan
         if seqm_parameters.get("elements") is None:
             seqm_parameters["elements"] = plan.elements
         dev = coordinates.device
         self.nmol, self.molsize = plan.nmol, plan.molsize
-        self.nHeavy, self.nHydro, self.nocc = plan.nheavy, plan.nhyd, plan.nocc
-        self.nSuperHeavy = torch.zeros_like(plan.nheavy)
-        if plan.d_mode:  # basics.py:239-269: nHeavy counts the sp-only heavy atoms, nSuperHeavy the d-shell ones
-            self.nSuperHeavy = plan.nsh
-            self.nHeavy = plan.nheavy - plan.nsh
-        self.Z = plan.Z
-        self.atom_molid = plan.atom_mol
-        self.idxi, self.idxj = plan.pair_i, plan.pair_j
+        # nHeavy / nHydro / nocc / nSuperHeavy / Z / atom_molid / idxi / idxj / norb / num_atoms / mass / mass_inverse and
         # maskd / mask / mask_l / ni / nj / pair_molid / xij / rij are derived on first access (see __getattr__):
         # the kernels never read them, they exist for the reference's attribute contract
         # pair_outer_cutoff (basics.py:209, 326): the pair list stays the dense triangular one; a pair at or beyond the
@@ -150,12 +140,6 @@ class Molecule(torch.nn.Module):
         else:
             self.alp = torch.zeros((zmax + 1, zmax + 1), dtype=torch.float64, device=dev)
             self.chi = torch.zeros_like(self.alp)
-        self.norb = self.nHydro + 4 * self.nHeavy + 9 * self.nSuperHeavy
-        non_zero = species != 0
-        self.num_atoms = non_zero.sum(dim=1).to(coordinates.dtype)
-        self.mass = const.mass[species].unsqueeze(2)
-        self.mass_inverse = torch.zeros_like(self.mass)
-        self.mass_inverse[non_zero] = 1.0 / self.mass[non_zero]
 
         self.force = None
         self.velocities = None
@@ -178,8 +162,34 @@ class Molecule(torch.nn.Module):
         self.n_scf_iter: Optional[int] = None  # the count the reference only prints (scf_loop.py:975-992)
 
     _LAZY = ("maskd", "mask", "mask_l", "ni", "nj", "pair_molid", "xij", "rij", "w")
+    _LAZY2 = ("tot_charge", "mult", "nHeavy", "nHydro", "nocc", "nSuperHeavy", "Z", "atom_molid", "idxi", "idxj", "norb",
+              "num_atoms", "mass", "mass_inverse")  # fmt: skip
+
+    def _lazy2(self, name):
+        d = self.__dict__
+        plan, dev = d["_plan"], self.coordinates.device
+        if name in ("tot_charge", "mult"):
+            v = d["_charges_in" if name == "tot_charge" else "_mult_in"]
+            d[name] = v if torch.is_tensor(v) else v * torch.ones(self.coordinates.shape[0], device=dev)
+        elif name in ("nHeavy", "nHydro", "nocc", "nSuperHeavy", "norb"):
+            d["nHydro"], d["nocc"] = plan.nhyd, plan.nocc
+            if plan.d_mode:  # basics.py:239-269: nHeavy counts the sp-only heavy atoms, nSuperHeavy the d-shell ones
+                d["nSuperHeavy"], d["nHeavy"] = plan.nsh, plan.nheavy - plan.nsh
+            else:
+                d["nSuperHeavy"], d["nHeavy"] = torch.zeros_like(plan.nheavy), plan.nheavy
+            d["norb"] = d["nHydro"] + 4 * d["nHeavy"] + 9 * d["nSuperHeavy"]
+        elif name in ("Z", "atom_molid", "idxi", "idxj"):
+            d["Z"], d["atom_molid"], d["idxi"], d["idxj"] = plan.Z, plan.atom_mol, plan.pair_i, plan.pair_j
+        else:
+            non_zero = self.species != 0
+            d["num_atoms"] = non_zero.sum(dim=1).to(self.coordinates.dtype)
+            d["mass"] = self.const.mass[self.species].unsqueeze(2)
+            d["mass_inverse"] = torch.where(non_zero.unsqueeze(2), 1.0 / d["mass"].clamp_min(1e-300), torch.zeros_like(d["mass"]))
+        return d[name]
 
     def __getattr__(self, name):
+        if name in Molecule._LAZY2 and "_plan" in self.__dict__:
+            return self._lazy2(name)
         if name in Molecule._LAZY and "_plan" in self.__dict__:
             plan = self.__dict__["_plan"]
             ms, pos = plan.molsize, plan.atom_local
