@@ -147,6 +147,11 @@ SEQM_GLOBAL void emat_reset_kernel(seqm_batch_t b, ScfWork W) {
   }
 }
 
+// History slots of the shared-memory path hold the UPPER TRIANGLE of the stored Fock matrix (symmetric) and residual
+// (antisymmetric) row-packed -- half the bytes that diis_store writes / reads back for the EMAT row and that
+// diis_extrapolate streams; the slot stride stays n*n (the large-molecule path keeps full matrices in the same buffers).
+SEQM_HD int diis_tri(int a, int c, int n) { return a * n - a * (a - 1) / 2 + (c - a); }  // a <= c
+
 // DIIS step 1 (scf_loop.py:994-1007): store F, residual R = F P - P F, max |R|, EMAT row `counter`.
 SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __restrict__ F, const double* __restrict__ P,
                                    int counter, int cF) {
@@ -179,7 +184,7 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
     const double f = in ? F[v.mat0 + r * n + c] : 0.0;
     sF[t] = f;
     sP[t] = in ? P[v.mat0 + r * n + c] : 0.0;
-    if (in) Fh[r * n + c] = f;
+    if (in && c >= r) Fh[diis_tri(r, c, n)] = f;
   }
   SEQM_SYNC();
   {
@@ -201,11 +206,11 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
         const int c = j0 + 2 * t4 + e;
         if (a >= n || c >= n || c <= a) continue;
         const double sv = rv[e];
-        Rh[a * n + c] = sv;
-        Rh[c * n + a] = -sv;
+        const int at = diis_tri(a, c, n);
+        Rh[at] = sv;
         rmax = fmax(rmax, fabs(sv));
         for (int q = 0; q < cF; ++q)
-          dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + a * n + c]);
+          dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + at]);
       }
     }
   }
@@ -217,7 +222,7 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
     const double f = F[v.mat0 + t];
     sF[t] = f;
     sP[t] = P[v.mat0 + t];
-    Fh[t] = f;
+    if (t % n >= t / n) Fh[diis_tri(t / n, t % n, n)] = f;
   }
   SEQM_SYNC();
   // R = F P - P F on the strict upper triangle (R is antisymmetric), 2x2 register blocks
@@ -245,15 +250,15 @@ SEQM_GLOBAL void diis_store_kernel(seqm_batch_t b, ScfWork W, const double* __re
       if ((e == 1 || e == 3) && j1 == j) continue;  // clamped duplicate column
       if ((e == 2 || e == 3) && i1 == i) continue;  // clamped duplicate row
       const double sv = rv[e];
-      Rh[a * n + c] = sv;
-      Rh[c * n + a] = -sv;
+      const int at = diis_tri(a, c, n);
+      Rh[at] = sv;
       rmax = fmax(rmax, fabs(sv));
       for (int q = 0; q < cF; ++q)
-        dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + a * n + c]);
+        dots[q] += sv * ((q == counter) ? sv : W.RES[h0 + (long long)q * nn + at]);
     }
   }
 #endif
-  for (int t = threadIdx.x; t < n; t += blockDim.x) Rh[t * n + t] = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) Rh[diis_tri(t, t, n)] = 0.0;
   rmax = block_max(rmax, red);
   double* E = W.EMAT + (long long)mol * SEQM_EM * SEQM_EM;
   for (int q = 0; q < cF; ++q) {
@@ -360,10 +365,16 @@ SEQM_GLOBAL void diis_extrapolate_kernel(seqm_batch_t b, ScfWork W, double* __re
   const long long h0 = v.mat0 * SEQM_NFOCK;
   double c[SEQM_NFOCK];
   for (int k = 0; k < cF; ++k) c[k] = W.coeff[(long long)mol * SEQM_NFOCK + k];
-  for (int t = threadIdx.x; t < nn; t += blockDim.x) {
+  const int n = v.n, ntri = n * (n + 1) / 2;
+  for (int t = threadIdx.x; t < ntri; t += blockDim.x) {  // packed index -> (r, cc >= r); both triangles get the same sum
+    int r = (int)((2.0 * n + 1.0 - sqrt((2.0 * n + 1.0) * (2.0 * n + 1.0) - 8.0 * t)) * 0.5);
+    while (diis_tri(r, r, n) > t) --r;                    // guard the floating-point row estimate
+    while (r + 1 < n && diis_tri(r + 1, r + 1, n) <= t) ++r;
+    const int cc = r + (t - diis_tri(r, r, n));
     double s = 0.0;
     for (int k = 0; k < cF; ++k) s += c[k] * W.FOCK[h0 + (long long)k * nn + t];
-    F[v.mat0 + t] = s;
+    F[v.mat0 + r * n + cc] = s;
+    F[v.mat0 + cc * n + r] = s;
   }
 }
 
