@@ -570,14 +570,17 @@ def main():
         # half-batches out of phase on two streams, where per-kernel event intervals overlap and cannot be summed
         prev_pipe = os.environ.get("SEQM_B200_PIPELINE")
         os.environ["SEQM_B200_PIPELINE"] = "1"
-        lib.jacobi_stats(reset=True)
-        lib.profile_enable(True)
-        flush.fill_(1.0)
-        torch.cuda.synchronize()
-        es(mol)
-        prof = lib.profile_collect()
-        lib.profile_enable(False)
-        jstats = lib.jacobi_stats(reset=True)
+        profs = []
+        for _ in range(3):  # three profile steps, per-kernel median: one step's event timing wanders by +-10 % between boxes
+            lib.jacobi_stats(reset=True)
+            lib.profile_enable(True)
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            es(mol)
+            profs.append(lib.profile_collect())
+            lib.profile_enable(False)
+            jstats = lib.jacobi_stats(reset=True)
+        prof = {k: (sorted(p_.get(k, (0.0, 0))[0] for p_ in profs)[1], profs[0][k][1]) for k in profs[0]}
         if prev_pipe is None:
             del os.environ["SEQM_B200_PIPELINE"]
         else:
