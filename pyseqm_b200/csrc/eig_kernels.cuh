@@ -245,7 +245,7 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
                                      const double* __restrict__ Cguess, const int32_t* __restrict__ active,
                                      JacobiMix mix) {
   typedef JacobiCfg<NP> K;
-  constexpr int M = K::M, SEG = K::SEG, SR = K::SR;
+  constexpr int M = K::M, SR = K::SR;
   const int mol = b.mol_order[first + blockIdx.x];
   if (active && !active[mol]) return;
   const MolView v = mol_view(b, mol);
@@ -262,8 +262,14 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
   const bool warm = (Cguess != nullptr);
   const long long clk0 = SEQM_CLOCK();
 #ifndef SEQM_HOSTEMU
-  double vr[SEG];  // V[row][seg*SEG .. seg*SEG+SEG-1]
-  const int vrow = tid / SR, vseg = tid % SR;
+  // V ownership: thread (row block, segment) keeps RB rows x SEG consecutive columns in registers.  RB = 2 where the
+  // segment length stays even (m a multiple of 16): every rotation pair read from shared memory then serves two rows,
+  // which halves the V update's share of the shared-memory traffic the sweep loop is bound by.
+  constexpr int RB = (SR == 4 && M % 16 == 0) ? 2 : 1;
+  constexpr int SRN = SR * RB;       // segments per row
+  constexpr int SEG = M / SRN;       // columns per segment (shadows K::SEG, which is the RB = 1 value)
+  double vr[RB][SEG];
+  const int vrow = (tid / SRN) * RB, vseg = tid % SRN;
 #else
   static double Vh[128 * 128];  // host emulation keeps V in memory (one "thread" plays all owners)
 #endif
@@ -286,10 +292,12 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
       }
       SEQM_SYNC();
 #pragma unroll
-      for (int e = 0; e < SEG; ++e) {
-        const int c = vseg * SEG + e;
-        vr[e] = (vrow < n && c < n) ? S[vrow * LDT + c] : ((vrow == c) ? 1.0 : 0.0);
-      }
+      for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+        for (int e = 0; e < SEG; ++e) {
+          const int rr = vrow + rb, c = vseg * SEG + e;
+          vr[rb][e] = (rr < n && c < n) ? S[rr * LDT + c] : ((rr == c) ? 1.0 : 0.0);
+        }
       const int warp = tid >> 5, nwarps = nthr >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
       // T = F C0 -> G
       for (int tile = warp; tile < nt8 * nt8; tile += nwarps) {
@@ -368,10 +376,11 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     }
 #ifndef SEQM_HOSTEMU
 #pragma unroll
-    for (int e = 0; e < SEG; ++e) {
-      const int c = vseg * SEG + e;
-      vr[e] = (vrow < n && c < n) ? S[vrow * n + c] : ((vrow == c) ? 1.0 : 0.0);
-    }
+    for (int rb = 0; rb < RB; ++rb)
+      for (int e = 0; e < SEG; ++e) {
+        const int rr = vrow + rb, c = vseg * SEG + e;
+        vr[rb][e] = (rr < n && c < n) ? S[rr * n + c] : ((rr == c) ? 1.0 : 0.0);
+      }
 #else
     for (int i = 0; i < M; ++i)
       for (int c = 0; c < M; ++c) Vh[i * M + c] = (i < n && c < n) ? S[i * n + c] : ((i == c) ? 1.0 : 0.0);
@@ -416,7 +425,9 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
     }
 #ifndef SEQM_HOSTEMU
 #pragma unroll
-    for (int e = 0; e < SEG; ++e) vr[e] = (vrow == vseg * SEG + e) ? 1.0 : 0.0;
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+      for (int e = 0; e < SEG; ++e) vr[rb][e] = (vrow + rb == vseg * SEG + e) ? 1.0 : 0.0;
 #else
     for (int i = 0; i < M; ++i)
       for (int c = 0; c < M; ++c) Vh[i * M + c] = (i == c) ? 1.0 : 0.0;
@@ -569,26 +580,40 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
         seqm_static_for(std::make_integer_sequence<int, SEG / 2>{}, [&](auto jc) {
           constexpr int j = decltype(jc)::value;
           const seqm_d2 c = seqm_lds2<CUR + 16 * j>(vcs_a);
-          const double x = vr[2 * j], y = vr[2 * j + 1];
-          vr[2 * j] = c.x * x + c.y * y;
-          vr[2 * j + 1] = c.y * x - c.x * y;
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb) {
+            const double x = vr[rb][2 * j], y = vr[rb][2 * j + 1];
+            vr[rb][2 * j] = c.x * x + c.y * y;
+            vr[rb][2 * j + 1] = c.y * x - c.x * y;
+          }
         });
       } else {
         const int lane = tid & 31;
-        const double first_old = vr[0], last_old = vr[SEG - 1];
-        const double y_next = __shfl_sync(0xffffffffu, first_old, (lane & ~(SR - 1)) | ((lane + 1) & (SR - 1)));
-        const double x_prev = __shfl_sync(0xffffffffu, last_old, (lane & ~(SR - 1)) | ((lane + SR - 1) & (SR - 1)));
+        double first_old[RB], last_old[RB], y_next[RB], x_prev[RB];
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          first_old[rb] = vr[rb][0];
+          last_old[rb] = vr[rb][SEG - 1];
+          y_next[rb] = __shfl_sync(0xffffffffu, first_old[rb], (lane & ~(SRN - 1)) | ((lane + 1) & (SRN - 1)));
+          x_prev[rb] = __shfl_sync(0xffffffffu, last_old[rb], (lane & ~(SRN - 1)) | ((lane + SRN - 1) & (SRN - 1)));
+        }
         seqm_static_for(std::make_integer_sequence<int, SEG / 2 - 1>{}, [&](auto jc) {
           constexpr int j = decltype(jc)::value;
           const seqm_d2 c = seqm_lds2<CUR + 16 * j>(vcs_a);
-          const double x = vr[2 * j + 1], y = vr[2 * j + 2];
-          vr[2 * j + 1] = c.x * x + c.y * y;
-          vr[2 * j + 2] = c.y * x - c.x * y;
+#pragma unroll
+          for (int rb = 0; rb < RB; ++rb) {
+            const double x = vr[rb][2 * j + 1], y = vr[rb][2 * j + 2];
+            vr[rb][2 * j + 1] = c.x * x + c.y * y;
+            vr[rb][2 * j + 2] = c.y * x - c.x * y;
+          }
         });
-        const seqm_d2 cn = seqm_lds2<CUR + 16 * (SEG / 2 - 1)>(vcs_a);  // pair (my last, next quarter's first)
-        const seqm_d2 cp = seqm_lds2<CUR>(vcp_a);                       // pair (previous quarter's last, my first)
-        vr[SEG - 1] = cn.x * last_old + cn.y * y_next;
-        vr[0] = cp.y * x_prev - cp.x * first_old;
+        const seqm_d2 cn = seqm_lds2<CUR + 16 * (SEG / 2 - 1)>(vcs_a);  // pair (my last, next segment's first)
+        const seqm_d2 cp = seqm_lds2<CUR>(vcp_a);                       // pair (previous segment's last, my first)
+#pragma unroll
+        for (int rb = 0; rb < RB; ++rb) {
+          vr[rb][SEG - 1] = cn.x * last_old[rb] + cn.y * y_next[rb];
+          vr[rb][0] = cp.y * x_prev[rb] - cp.x * first_old[rb];
+        }
       }
 #endif
       SEQM_SYNC();
@@ -637,7 +662,9 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
 #endif
 #ifdef SEQM_EXP_NOV
 #pragma unroll
-    for (int e = 0; e < SEG; ++e) vr[e] = (vrow == vseg * SEG + e) ? 1.0 : 0.0;
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+      for (int e = 0; e < SEG; ++e) vr[rb][e] = (vrow + rb == vseg * SEG + e) ? 1.0 : 0.0;
 #endif
     // quadratic convergence: once every rotation of a sweep was below tol_big (1e-6 |A| inside the SCF, 1e-8 |A|
     // when eigenpairs are returned) the off-diagonal left behind is O(tol_big^2 / gap): an occupied-virtual
@@ -677,7 +704,9 @@ SEQM_GLOBAL void SEQM_LAUNCH_BOUNDS2(JacobiCfg<NP>::THREADS, JacobiCfg<NP>::MINB
 #ifndef SEQM_HOSTEMU
   constexpr int LV = K::LDT;  // row stride 4 mod 16: conflict-free tensor-core fragment loads
 #pragma unroll
-  for (int e = 0; e < SEG; ++e) V[vrow * LV + vseg * SEG + e] = vr[e];
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int e = 0; e < SEG; ++e) V[(vrow + rb) * LV + vseg * SEG + e] = vr[rb][e];
 #else
   constexpr int LV = M;
   for (int t = 0; t < M * M; ++t) V[t] = Vh[t];
