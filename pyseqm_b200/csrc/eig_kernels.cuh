@@ -41,9 +41,10 @@ struct alignas(16) seqm_d2 { double x, y; };
 //   * the upper triangle of A lives in shared memory tile-major (jacobi_aidx): one plane per element of the 2x2 tiles,
 //     indexed by the owner slot of the tile, so the even step is a unit-stride 64-bit access and the odd step is unit
 //     stride along every tile row (the kernel is bound by shared-memory wavefronts: ncu).
-//   * V never touches shared memory during the sweeps: thread (row i, segment s) keeps m/SR consecutive
-//     entries of row i in registers (SR = 4 threads per row, 8 for the classes with NP >= 40); the one pair that
-//     straddles two segments in odd steps is exchanged with two 64-bit shuffles inside the SR-lane group.
+//   * V never touches shared memory during the sweeps: a thread keeps RB rows x m/(SR RB) consecutive columns in
+//     registers (SR = 4 threads per row, 8 for the classes with NP >= 40; RB = 2 rows where m is a multiple of 16, so that
+//     every rotation pair read from shared memory serves two rows); the pairs that straddle two segments in odd steps
+//     are exchanged with 64-bit shuffles inside the segment group of lanes.
 //   * per pair l the transform is x' = a x + b y, y' = b x - a y with (a,b) = (sin, cos) [rotate + swap],
 //     (0,1) [swap only, |a_pq| below threshold] or (1,0) for the wrap pair (m-1,0) of odd steps (identity up
 //     to the sign of slot 0, which is irrelevant for an eigenbasis).
